@@ -1,0 +1,71 @@
+// avc_common.cuh -- shared helpers for the sm_100a kernels of libavc_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/avc_b200.h"
+
+#define AVC_CUDA_TRY(expr)                      \
+  do {                                          \
+    cudaError_t e__ = (expr);                   \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+#define AVC_LAUNCH_TRY()                        \
+  do {                                          \
+    cudaError_t e__ = cudaGetLastError();       \
+    if (e__ != cudaSuccess) return (int)e__;    \
+  } while (0)
+#define AVC_TRY(expr)                           \
+  do {                                          \
+    int r__ = (expr);                           \
+    if (r__ != 0) return r__;                   \
+  } while (0)
+
+namespace avc {
+
+constexpr float kSqrtHalf = 0.70710678118654752440f;
+constexpr float kBeta = 100.0f;      // nn.Softplus(beta=100), models/fields.py:70
+constexpr float kThresh = 20.0f;     // torch's default softplus threshold
+
+// scalar slots of the per-call context block (workspace header)
+enum { CTX_INV_S = 0, CTX_EIK_NUM = 1, CTX_EIK_DEN = 2, CTX_INVS_BAR = 3, CTX_FLOATS = 64 };
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// softplus_beta with torch's threshold rule: beta*z > 20 -> identity.
+__device__ __forceinline__ float softplus100(float z) {
+  float bz = z * kBeta;
+  return bz > kThresh ? z : log1pf(expf(bz)) / kBeta;
+}
+// first derivative (torch softplus_backward: e/(e+1) with e = exp(beta z); 1 above the threshold)
+__device__ __forceinline__ float softplus100_d1(float z) {
+  float bz = z * kBeta;
+  if (bz > kThresh) return 1.0f;
+  float e = expf(bz);
+  return e / (e + 1.0f);
+}
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// A carve-out allocator over the caller-provided workspace (256-byte aligned pieces).
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base((char*)p), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = base ? (T*)(base + off) : nullptr;
+    off += count * sizeof(T);
+    return r;
+  }
+  size_t used() const { return (off + 255) & ~(size_t)255; }
+};
+
+}  // namespace avc

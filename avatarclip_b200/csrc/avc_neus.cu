@@ -1,0 +1,619 @@
+// avc_neus.cu -- host orchestration + C ABI of the NeuS render forward / backward.
+//
+// Kernel sequence (one chunk of rays; see oracle/neus_manual.py for the same steps on the CPU):
+//   pack            k_pack_linear per linear (weight-norm folded once per call)
+//   placement       k_coarse_z -> [k_encode_samples -> value chain -> k_thin_nt(sdf)] -> k_upsample
+//                   -> ... -> k_merge                      (renderer.py:336-352)
+//   fine forward    k_encode_fine -> value chain (gemm_nt + EpiValue, stash z) -> sdf / feature heads
+//                   -> k_chain_start -> gradient chain (gemm_nt + EpiChain) -> k_normal
+//                   -> colour net (gemm_nt + EpiColor0/EpiRelu, k_thin_nt heads) -> k_composite_fwd
+//   backward        k_composite_bwd -> colour backward -> k_dge -> second-order sweep (gemm_nt +
+//                   EpiChainBwd, gemm_tn) -> value backward (gemm_nt + EpiDgrad, gemm_tn) -> k_wn_backward
+#include <cstdio>
+#include <cstring>
+
+#include "avc_common.cuh"
+#include "avc_gemm_simt.cuh"
+#include "avc_neus_kernels.cuh"
+#include "avc_neus_plan.cuh"
+
+using namespace avc;
+
+namespace {
+
+inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// -------------------------------------------------------------------------------- packing
+int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStream_t st) {
+  for (int l = 0; l <= pl.L; ++l) {
+    const LinDim& d = pl.sdf[l];
+    PackJob j;
+    memset(&j, 0, sizeof(j));
+    j.v = params + d.off_v; j.g = params + d.off_g; j.b = params + d.off_b;
+    j.N = d.N; j.K = d.K;
+    j.c0[0] = 0; j.c1[0] = d.K;
+    j.W[0] = pack + d.pk_W; j.ldw[0] = d.Kp;
+    j.WT[0] = pack + d.pk_WT;
+    j.bias = pack + d.pk_b;
+    if (l < pl.L) {
+      j.ldwt[0] = d.Np;
+    } else {
+      j.ldwt[0] = pl.Fp;
+      j.row_shift = 1; j.bias_shift = 1;
+      j.row0 = pack + pl.pk_wsdf; j.row0_b = pack + pl.pk_bsdf;
+    }
+    k_pack_linear<<<d.N, 128, 0, st>>>(j);
+  }
+  for (int l = 0; l < pl.Lc; ++l) {
+    const LinDim& d = pl.col[l];
+    PackJob j;
+    memset(&j, 0, sizeof(j));
+    j.v = params + d.off_v; j.g = params + d.off_g; j.b = params + d.off_b;
+    j.N = d.N; j.K = d.K;
+    if (l == 0) {
+      j.c0[0] = 6; j.c1[0] = d.K;                 // feature columns
+      j.W[0] = pack + d.pk_W; j.ldw[0] = pl.Fp;
+      j.WT[0] = pack + d.pk_WT; j.ldwt[0] = pl.Hc;
+      j.c0[1] = 0; j.c1[1] = 6;                   // points + normals columns
+      j.W[1] = pack + pl.pk_c0x; j.ldw[1] = 8;
+      j.WT[1] = pack + pl.pk_c0xT; j.ldwt[1] = pl.Hc;
+    } else {
+      j.c0[0] = 0; j.c1[0] = d.K;
+      j.W[0] = pack + d.pk_W; j.ldw[0] = pl.Hc;
+      j.WT[0] = pack + d.pk_WT; j.ldwt[0] = pl.Hc;
+    }
+    j.bias = pack + d.pk_b;
+    k_pack_linear<<<d.N, 128, 0, st>>>(j);
+  }
+  for (int h = 0; h < 2; ++h) {   // colour head lin{Lc} -> rows 0..2, extra_lin -> rows 3..5 of W6
+    const LinDim& d = h == 0 ? pl.col[pl.Lc] : pl.extra;
+    PackJob j;
+    memset(&j, 0, sizeof(j));
+    j.v = params + d.off_v; j.g = params + d.off_g; j.b = params + d.off_b;
+    j.N = 3; j.K = pl.Hc;
+    j.c0[0] = 0; j.c1[0] = pl.Hc;
+    j.W[0] = pack + pl.pk_W6; j.ldw[0] = pl.Hc;
+    j.bias = pack + pl.pk_b6;
+    j.dst_row_off = 3 * h;
+    k_pack_linear<<<3, 128, 0, st>>>(j);
+  }
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+// zero the padding of the packed buffer once per call (padding rows/cols must be exactly zero)
+int zero_pack(const NeusPlan& pl, float* pack, cudaStream_t st) {
+  AVC_CUDA_TRY(cudaMemsetAsync(pack, 0, sizeof(float) * (size_t)pl.pack_floats, st));
+  return 0;
+}
+
+EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
+  EncodeTargets t;
+  memset(&t, 0, sizeof(t));
+  t.in0 = w.in[0]; t.ld0 = pl.sdf[0].Kp;
+  for (int l = 1; l <= pl.L; ++l) {
+    if (!pl.sdf[l].skip) continue;
+    if (t.n_skip >= 4) break;
+    t.skip_ptr[t.n_skip] = w.in[l];
+    t.skip_ld[t.n_skip] = pl.sdf[l].Kp;
+    t.skip_col[t.n_skip] = pl.sdf[l].K - pl.E;
+    ++t.n_skip;
+  }
+  return t;
+}
+
+// -------------------------------------------------------------------------------- value chain
+// in[0] (and the skip columns) must hold the encoding of Pn points.  stash: keep z[l].
+// Leaves in[L] ready; writes sdf[Pn] (thin) and, when want_feat, feat[Pn][Fp].
+int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, bool want_feat, float* sdf_out,
+                cudaStream_t st) {
+  const float* pack = w.pack;
+  for (int l = 0; l < pl.L; ++l) {
+    const LinDim& d = pl.sdf[l];
+    EpiValue e;
+    e.bias = pack + d.pk_b;
+    e.Z = stash ? w.z[l] : nullptr; e.ldz = d.Np;
+    e.OUT = w.in[l + 1]; e.ldo = pl.sdf[l + 1].Kp;
+    e.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
+    e.N = d.N;
+    AVC_TRY(launch_gemm_nt(st, Pn, d.N, d.Kp, w.in[l], d.Kp, pack + d.pk_W, d.Kp, e));
+  }
+  const LinDim& dl = pl.sdf[pl.L];
+  OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale};
+  k_thin_nt<1, OutSdf><<<blocks_for(Pn, 8), 256, 0, st>>>(w.in[pl.L], dl.Kp, dl.Kp, pack + pl.pk_wsdf, dl.Kp,
+                                                           pack + pl.pk_bsdf, Pn, os);
+  AVC_LAUNCH_TRY();
+  if (want_feat) {
+    EpiBias e{pack + dl.pk_b, w.feat, pl.Fp, pl.F};
+    AVC_TRY(launch_gemm_nt(st, Pn, pl.F, dl.Kp, w.in[pl.L], dl.Kp, pack + dl.pk_W, dl.Kp, e));
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------- placement
+int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, const float* rays_d, const float* near,
+                  const float* far, const float* jitter, int Rc, float* z_out_raymajor, cudaStream_t st) {
+  const int T = 128;
+  k_coarse_z<<<blocks_for(Rc, T), T, 0, st>>>(near, far, jitter, pl.n0, Rc, w.zA);
+  AVC_LAUNCH_TRY();
+  if (pl.cfg.n_importance == 0) {
+    k_transpose_z<<<blocks_for((int64_t)pl.n0 * Rc, 256), 256, 0, st>>>(w.zA, pl.n0, Rc, z_out_raymajor);
+    AVC_LAUNCH_TRY();
+    return 0;
+  }
+  EncodeTargets t = make_targets(pl, w);
+  int64_t Pn = (int64_t)pl.n0 * Rc;
+  k_encode_samples<<<blocks_for(Pn, 128), 128, 0, st>>>(rays_o, rays_d, w.zA, pl.n0, Rc, pl.cfg.sdf_scale,
+                                                        pl.cfg.sdf_multires, pl.E, pl.EP, t);
+  AVC_LAUNCH_TRY();
+  AVC_TRY(value_chain(pl, w, Pn, false, false, w.sA, st));
+  float *zc = w.zA, *sc = w.sA, *zn = w.zB, *sn = w.sB;
+  int n = pl.n0;
+  for (int i = 0; i < pl.steps; ++i) {
+    const bool last = (i + 1 == pl.steps);
+    float inv_s = 64.0f * (float)(1 << i);                                     // renderer.py:346
+    k_upsample<<<blocks_for(Rc, T), T, 0, st>>>(rays_o, rays_d, zc, sc, n, Rc, inv_s, pl.per, w.wS, w.newZ);
+    AVC_LAUNCH_TRY();
+    if (!last) {
+      Pn = (int64_t)pl.per * Rc;
+      k_encode_samples<<<blocks_for(Pn, 128), 128, 0, st>>>(rays_o, rays_d, w.newZ, pl.per, Rc, pl.cfg.sdf_scale,
+                                                            pl.cfg.sdf_multires, pl.E, pl.EP, t);
+      AVC_LAUNCH_TRY();
+      AVC_TRY(value_chain(pl, w, Pn, false, false, w.newS, st));
+    }
+    k_merge<<<blocks_for(Rc, T), T, 0, st>>>(zc, sc, n, w.newZ, last ? nullptr : w.newS, pl.per, Rc, zn, sn,
+                                              last ? z_out_raymajor : nullptr);
+    AVC_LAUNCH_TRY();
+    float* tz = zc; zc = zn; zn = tz;
+    float* ts = sc; sc = sn; sn = ts;
+    n += pl.per;
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------- fine forward
+struct ChunkIO {
+  const float *rays_o, *rays_d, *background;   // already offset to the chunk
+  int bg_kind;
+  float cos_anneal;
+  int64_t Rc;
+  avc_neus_outputs out;                        // already offset to the chunk (gradient_error not offset)
+};
+
+CompositeArgs make_composite_args(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io) {
+  CompositeArgs A;
+  A.rays_d = io.rays_d; A.z_vals = io.out.z_vals; A.sdf = w.sdf; A.cin = w.cin; A.rgb6 = w.rgb6;
+  A.background = io.background; A.bg_kind = io.bg_kind; A.ctx = w.ctx; A.cos_anneal = io.cos_anneal;
+  A.sample_dist = 2.0f / (float)pl.n0;                                         // renderer.py:304
+  A.S = pl.S; A.Rc = io.Rc;
+  return A;
+}
+
+// Runs the fine pass on io.out.z_vals; with write_outputs=false only the stash is (re)built.
+int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool write_outputs, cudaStream_t st) {
+  const int64_t P = io.Rc * pl.S;
+  const float* pack = w.pack;
+  EncodeTargets t = make_targets(pl, w);
+  k_encode_fine<<<blocks_for(P, 128), 128, 0, st>>>(io.rays_o, io.rays_d, io.out.z_vals, pl.S, io.Rc,
+                                                    2.0f / (float)pl.n0, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
+                                                    pl.EP, w.cin, write_outputs ? io.out.mid_z_vals : nullptr,
+                                                    write_outputs ? io.out.inside_sphere : nullptr, t);
+  AVC_LAUNCH_TRY();
+  AVC_TRY(value_chain(pl, w, P, true, true, w.sdf, st));
+  // ---- gradient chain
+  {
+    const LinDim& dL = pl.sdf[pl.L];
+    const LinDim& dp = pl.sdf[pl.L - 1];
+    int64_t tot = P * (int64_t)(dp.Np > pl.EP ? dp.Np : pl.EP);
+    k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
+                                                        w.z[pl.L - 1], dp.N, dp.Np, P, w.qt[pl.L - 1], w.ge);
+    AVC_LAUNCH_TRY();
+    for (int l = pl.L - 1; l >= 1; --l) {
+      const LinDim& d = pl.sdf[l];
+      const LinDim& dq = pl.sdf[l - 1];
+      EpiChain e;
+      e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
+      e.Zprev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
+      AVC_TRY(launch_gemm_nt(st, P, d.K, d.Np, w.qt[l], d.Np, pack + d.pk_WT, d.Np, e));
+    }
+    const LinDim& d0 = pl.sdf[0];
+    EpiGe eg{w.ge, pl.EP, pl.E};
+    AVC_TRY(launch_gemm_nt(st, P, pl.E, d0.Np, w.qt[0], d0.Np, pack + d0.pk_WT, d0.Np, eg));
+    k_normal<<<blocks_for(P, 128), 128, 0, st>>>(w.ge, pl.EP, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P, w.cin,
+                                                 write_outputs ? io.out.gradients : nullptr);
+    AVC_LAUNCH_TRY();
+  }
+  // ---- colour net
+  {
+    const LinDim& c0 = pl.col[0];
+    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, w.ch[1], pl.Hc};
+    AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Fp, w.feat, pl.Fp, pack + c0.pk_W, pl.Fp, e0));
+    for (int l = 1; l < pl.Lc; ++l) {
+      const LinDim& c = pl.col[l];
+      EpiRelu e{pack + c.pk_b, w.ch[l + 1], pl.Hc};
+      AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, pack + c.pk_W, pl.Hc, e));
+    }
+    OutHeads oh{w.rgb6};
+    k_thin_nt<6, OutHeads><<<blocks_for(P, 8), 256, 0, st>>>(w.ch[pl.Lc], pl.Hc, pl.Hc, pack + pl.pk_W6, pl.Hc,
+                                                             pack + pl.pk_b6, P, oh);
+    AVC_LAUNCH_TRY();
+  }
+  if (write_outputs) {
+    CompositeArgs A = make_composite_args(pl, w, io);
+    k_composite_fwd<<<blocks_for(io.Rc, 8), 256, 0, st>>>(A, io.out.color_fine, io.out.extra_color_fine, io.out.s_val,
+                                                          io.out.cdf_fine, io.out.weight_sum, io.out.weight_max,
+                                                          io.out.weights, w.ray_part);
+    AVC_LAUNCH_TRY();
+    k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, io.Rc, 0, w.ctx + CTX_EIK_NUM);
+    k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, io.Rc, 1, w.ctx + CTX_EIK_DEN);
+    AVC_LAUNCH_TRY();
+  }
+  return 0;
+}
+
+// -------------------------------------------------------------------------------- backward
+template <int NI>
+int thin_tn(cudaStream_t st, const float* S, int lds, float s_scale, const float* Hm, int ldh, int NC, int64_t P,
+            float* out, int si, int sc, float* bout) {
+  const int rows = 1024;
+  k_thin_tn<NI><<<blocks_for(P, rows), 256, 0, st>>>(S, lds, s_scale, Hm, ldh, NC, P, rows, out, si, sc, bout);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float scale, float* out) {
+  const int rows = 512;
+  k_colsum<<<blocks_for(P, rows), 256, 0, st>>>(X, ld, NC, P, rows, scale, out);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+// Accumulates dense dW / db of every linear into w.wbar (v / b slots of the flat layout) and the
+// inv_s adjoint into ctx[CTX_INVS_BAR].  Requires the forward stash of this chunk in `w`.
+int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const avc_neus_cotangents& cot,
+                  cudaStream_t st) {
+  const int64_t P = io.Rc * pl.S;
+  const float* pack = w.pack;
+  float* wbar = w.wbar;
+  // ---- compositing
+  CompositeArgs A = make_composite_args(pl, w, io);
+  CompositeBwdArgs G;
+  G.g_color = cot.color_fine; G.g_extra = cot.extra_color_fine; G.g_wsum = cot.weight_sum; G.g_wmax = cot.weight_max;
+  G.g_w = cot.weights; G.g_cdf = cot.cdf_fine; G.g_n = cot.gradients; G.g_gerr = cot.gradient_error;
+  G.weights = io.out.weights;
+  G.y6bar = w.y6bar; G.sdfbar = w.sdfbar; G.nbar = w.nbar; G.ray_part = w.ray_part;
+  k_composite_bwd<<<blocks_for(io.Rc, 8), 256, 0, st>>>(A, G);
+  AVC_LAUNCH_TRY();
+  k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, io.Rc, 2, w.ctx + CTX_INVS_BAR);
+  AVC_LAUNCH_TRY();
+
+  // ---- colour heads: lin{Lc} <- y6bar[:,0:3], extra_lin <- y6bar[:,3:6]   (models/fields.py:172-181)
+  {
+    const LinDim& dh = pl.col[pl.Lc];
+    const LinDim& dx = pl.extra;
+    AVC_TRY(thin_tn<3>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b));
+    AVC_TRY(thin_tn<3>(st, w.y6bar + 3, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dx.off_v, pl.Hc, 1, wbar + dx.off_b));
+    k_heads_dgrad<<<blocks_for(P * pl.Hc, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0]);
+    AVC_LAUNCH_TRY();
+  }
+  // ---- colour hidden linears l = Lc-1 .. 0 ; cbar_l lives in w.cbar[cur]
+  int cur = 0;
+  for (int l = pl.Lc - 1; l >= 0; --l) {
+    const LinDim& c = pl.col[l];
+    float* cb = w.cbar[cur];
+    AVC_TRY(colsum(st, cb, pl.Hc, pl.Hc, P, 1.f, wbar + c.off_b));
+    if (l > 0) {
+      AVC_TRY(launch_gemm_tn(st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.ch[l], pl.Hc, wbar + c.off_v, c.K));
+      EpiDgradRelu e{w.ch[l], w.cbar[cur ^ 1], pl.Hc};
+      AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Hc, cb, pl.Hc, pack + c.pk_WT, pl.Hc, e));
+      cur ^= 1;
+    } else {
+      // lin0 input = [x(3), n(3), feat(F)]: dW[:, 6:] += cbar^T feat ; dW[:, :6] += cbar^T cin6
+      AVC_TRY(launch_gemm_tn(st, P, pl.Hc, pl.F, cb, pl.Hc, w.feat, pl.Fp, wbar + c.off_v + 6, c.K));
+      AVC_TRY(thin_tn<6>(st, w.cin, 8, 1.f, cb, pl.Hc, pl.Hc, P, wbar + c.off_v, 1, c.K, nullptr));
+      // featbar = cbar . W0[:, 6:]
+      EpiStore es{w.featbar, pl.Fp, pl.F};
+      AVC_TRY(launch_gemm_nt(st, P, pl.F, pl.Hc, cb, pl.Hc, pack + c.pk_WT, pl.Hc, es));
+      // nbar += cbar . W0[:, 3:6]   (d/d points is discarded: pts is a leaf, models/fields.py:97)
+      OutNbarAdd on{w.nbar};
+      k_thin_nt<6, OutNbarAdd><<<blocks_for(P, 8), 256, 0, st>>>(cb, pl.Hc, pl.Hc, pack + pl.pk_c0xT, pl.Hc, nullptr,
+                                                                 P, on);
+      AVC_LAUNCH_TRY();
+    }
+  }
+
+  // ---- SDF: second-order sweep in forward layer order
+  int ucur = 0;
+  {
+    const LinDim& d0 = pl.sdf[0];
+    k_dge<<<blocks_for(P, 128), 128, 0, st>>>(w.cin, w.nbar, pl.EP, pl.E, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P,
+                                              w.ubar[0], d0.Kp, w.gebar);
+    AVC_LAUNCH_TRY();
+  }
+  for (int l = 0; l <= pl.L; ++l) {
+    const LinDim& d = pl.sdf[l];
+    float* ub = w.ubar[ucur];            // ubar_l : [P][Kp_l]
+    if (l == pl.L) {
+      // qt_L = e_0: only row 0 of W_L receives  sum_p ubar_L
+      AVC_TRY(colsum(st, ub, d.Kp, d.K, P, 1.f, wbar + d.off_v));
+      break;
+    }
+    AVC_TRY(launch_gemm_tn(st, P, d.N, d.K, w.qt[l], d.Np, ub, d.Kp, wbar + d.off_v, d.K));
+    const LinDim& dn = pl.sdf[l + 1];
+    EpiChainBwd e;
+    e.N = d.N; e.Np = d.Np; e.Z = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
+    e.UNEXT = w.ubar[ucur ^ 1]; e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
+    AVC_TRY(launch_gemm_nt(st, P, d.N, d.Kp, ub, d.Kp, pack + d.pk_W, d.Kp, e));
+    if (dn.skip) {
+      k_fill_gebar<<<blocks_for(P * pl.E, 256), 256, 0, st>>>(w.gebar, pl.EP, pl.E, P, w.ubar[ucur ^ 1], dn.Kp,
+                                                              dn.K - pl.E);
+      AVC_LAUNCH_TRY();
+    }
+    ucur ^= 1;
+  }
+
+  // ---- SDF: value backward in reverse layer order
+  {
+    const LinDim& dL = pl.sdf[pl.L];
+    const float inv_scale = 1.0f / pl.cfg.sdf_scale;
+    // last linear: row 0 (sdf) via thin ops, rows 1.. (features) via the GEMM tiles
+    AVC_TRY(thin_tn<1>(st, w.sdfbar, 1, inv_scale, w.in[pl.L], dL.Kp, dL.K, P, wbar + dL.off_v, 0, 1, wbar + dL.off_b));
+    AVC_TRY(launch_gemm_tn(st, P, pl.F, dL.K, w.featbar, pl.Fp, w.in[pl.L], dL.Kp, wbar + dL.off_v + dL.K, dL.K));
+    AVC_TRY(colsum(st, w.featbar, pl.Fp, pl.F, P, 1.f, wbar + dL.off_b + 1));
+    const LinDim& dp = pl.sdf[pl.L - 1];
+    EpiDgrad e;
+    e.Nprev = dp.N; e.Npp = dp.Np; e.s = dL.skip ? kSqrtHalf : 1.f;
+    e.Zprev = w.z[pl.L - 1]; e.ZBARprev = w.zbar[pl.L - 1];
+    e.sdfbar = w.sdfbar; e.wsdf = pack + pl.pk_wsdf; e.sdf_inv_scale = inv_scale;
+    AVC_TRY(launch_gemm_nt(st, P, dp.N, pl.Fp, w.featbar, pl.Fp, pack + dL.pk_WT, pl.Fp, e));
+  }
+  for (int l = pl.L - 1; l >= 0; --l) {
+    const LinDim& d = pl.sdf[l];
+    AVC_TRY(launch_gemm_tn(st, P, d.N, d.K, w.zbar[l], d.Np, w.in[l], d.Kp, wbar + d.off_v, d.K));
+    AVC_TRY(colsum(st, w.zbar[l], d.Np, d.N, P, 1.f, wbar + d.off_b));
+    if (l == 0) break;
+    const LinDim& dp = pl.sdf[l - 1];
+    EpiDgrad e;
+    e.Nprev = dp.N; e.Npp = dp.Np; e.s = d.skip ? kSqrtHalf : 1.f;
+    e.Zprev = w.z[l - 1]; e.ZBARprev = w.zbar[l - 1];
+    e.sdfbar = nullptr; e.wsdf = nullptr; e.sdf_inv_scale = 1.f;
+    AVC_TRY(launch_gemm_nt(st, P, dp.N, d.Np, w.zbar[l], d.Np, pack + d.pk_WT, d.Np, e));
+  }
+  return 0;
+}
+
+int weight_norm_backward_all(const NeusPlan& pl, const float* params, const float* wbar, float* grads,
+                             cudaStream_t st) {
+  auto one = [&](const LinDim& d) {
+    k_wn_backward<<<d.N, 128, 0, st>>>(params + d.off_v, params + d.off_g, wbar + d.off_v, wbar + d.off_b, d.N, d.K,
+                                       grads + d.off_g, grads + d.off_v, grads + d.off_b);
+  };
+  for (int l = 0; l <= pl.L; ++l) one(pl.sdf[l]);
+  for (int l = 0; l <= pl.Lc; ++l) one(pl.col[l]);
+  one(pl.extra);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+int check_ptr16(const void* p) { return ((uintptr_t)p & 15u) ? AVC_E_ALIGN : 0; }
+
+avc_neus_outputs offset_outputs(const avc_neus_outputs& o, int64_t r0, int S) {
+  avc_neus_outputs q = o;
+  q.color_fine += r0 * 3; q.extra_color_fine += r0 * 3; q.s_val += r0; q.cdf_fine += r0 * S;
+  q.weight_sum += r0; q.weight_max += r0; q.gradients += r0 * S * 3; q.weights += r0 * S;
+  q.mid_z_vals += r0 * S; q.inside_sphere += r0 * S; q.z_vals += r0 * S;
+  return q;
+}
+
+avc_neus_cotangents offset_cot(const avc_neus_cotangents& c, int64_t r0, int S) {
+  avc_neus_cotangents q = c;
+  if (q.color_fine) q.color_fine += r0 * 3;
+  if (q.extra_color_fine) q.extra_color_fine += r0 * 3;
+  if (q.s_val) q.s_val += r0;
+  if (q.cdf_fine) q.cdf_fine += r0 * S;
+  if (q.weight_sum) q.weight_sum += r0;
+  if (q.weight_max) q.weight_max += r0;
+  if (q.gradients) q.gradients += r0 * S * 3;
+  if (q.weights) q.weights += r0 * S;
+  return q;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int avc_abi_version(void) { return AVC_ABI_VERSION; }
+const char* avc_build_arch(void) { return "sm_100a"; }
+
+int avc_neus_param_count(const avc_neus_cfg* cfg, int64_t* n_params) {
+  if (!cfg || !n_params) return AVC_E_NULL;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  *n_params = pl.n_params;
+  return 0;
+}
+
+int avc_neus_param_offset(const avc_neus_cfg* cfg, int net, int layer, int which, int64_t* offset, int64_t* numel) {
+  if (!cfg || !offset || !numel) return AVC_E_NULL;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  const LinDim* d = nullptr;
+  if (net == 0) { if (layer < 0 || layer > pl.L) return AVC_E_SIZE; d = &pl.sdf[layer]; }
+  else if (net == 1) { if (layer < 0 || layer > pl.Lc) return AVC_E_SIZE; d = &pl.col[layer]; }
+  else if (net == 2) d = &pl.extra;
+  else if (net == 3) { *offset = pl.off_var; *numel = 1; return 0; }
+  else return AVC_E_BADCFG;
+  if (which == 0) { *offset = d->off_g; *numel = d->N; }
+  else if (which == 1) { *offset = d->off_v; *numel = (int64_t)d->N * d->K; }
+  else if (which == 2) { *offset = d->off_b; *numel = d->N; }
+  else return AVC_E_BADCFG;
+  return 0;
+}
+
+int avc_neus_workspace_bytes(const avc_neus_cfg* cfg, int64_t max_rays_per_chunk, size_t* bytes) {
+  if (!cfg || !bytes) return AVC_E_NULL;
+  if (max_rays_per_chunk <= 0) return AVC_E_SIZE;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  NeusWs w;
+  carve_ws(pl, max_rays_per_chunk, nullptr, &w);
+  *bytes = w.bytes;
+  return 0;
+}
+
+int avc_neus_render_fwd(const avc_neus_cfg* cfg, const float* params, const float* rays_o, const float* rays_d,
+                        const float* near, const float* far, const float* jitter, const float* background,
+                        int bg_kind, const float* z_vals_in, float cos_anneal_ratio, int64_t R,
+                        const avc_neus_outputs* out, void* workspace, size_t workspace_bytes,
+                        int64_t max_rays_per_chunk, avc_stream_t stream) {
+  if (!cfg || !params || !rays_o || !rays_d || !out || !workspace) return AVC_E_NULL;
+  if (!z_vals_in && (!near || !far)) return AVC_E_NULL;
+  if (!out->color_fine || !out->extra_color_fine || !out->s_val || !out->cdf_fine || !out->weight_sum ||
+      !out->weight_max || !out->gradients || !out->weights || !out->mid_z_vals || !out->gradient_error ||
+      !out->inside_sphere || !out->z_vals)
+    return AVC_E_NULL;
+  if (bg_kind < 0 || bg_kind > 2 || (bg_kind != 0 && !background)) return AVC_E_BADCFG;
+  if (R <= 0 || max_rays_per_chunk <= 0) return AVC_E_SIZE;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
+  AVC_TRY(check_ptr16(workspace)); AVC_TRY(check_ptr16(params)); AVC_TRY(check_ptr16(out->z_vals));
+  const int64_t Rc_max = R < max_rays_per_chunk ? R : max_rays_per_chunk;
+  NeusWs w;
+  carve_ws(pl, Rc_max, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  AVC_TRY(zero_pack(pl, w.pack, st));
+  AVC_TRY(pack_weights(pl, params, w.pack, st));
+  k_ctx_init<<<1, 32, 0, st>>>(params, pl.off_var, w.ctx, 1);
+  AVC_LAUNCH_TRY();
+
+  for (int64_t r0 = 0; r0 < R; r0 += Rc_max) {
+    const int64_t Rc = (R - r0) < Rc_max ? (R - r0) : Rc_max;
+    ChunkIO io;
+    io.rays_o = rays_o + r0 * 3; io.rays_d = rays_d + r0 * 3;
+    io.background = (bg_kind == 2) ? background + r0 : background;
+    io.bg_kind = bg_kind; io.cos_anneal = cos_anneal_ratio; io.Rc = Rc;
+    io.out = offset_outputs(*out, r0, pl.S);
+    if (z_vals_in && z_vals_in + r0 * pl.S == io.out.z_vals) {
+      // caller passed the output buffer itself: depths already in place
+    } else if (z_vals_in) {
+      AVC_CUDA_TRY(cudaMemcpyAsync(io.out.z_vals, z_vals_in + r0 * pl.S, sizeof(float) * Rc * pl.S,
+                                   cudaMemcpyDeviceToDevice, st));
+    } else {
+      AVC_TRY(place_samples(pl, w, io.rays_o, io.rays_d, near + r0, far + r0, jitter ? jitter + r0 : nullptr,
+                            (int)Rc, io.out.z_vals, st));
+    }
+    AVC_TRY(fine_forward(pl, w, io, true, st));
+  }
+  k_finalize_fwd<<<1, 32, 0, st>>>(w.ctx, out->gradient_error);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+int avc_neus_render_bwd(const avc_neus_cfg* cfg, const float* params, const float* rays_o, const float* rays_d,
+                        const float* background, int bg_kind, float cos_anneal_ratio, int64_t R,
+                        const avc_neus_outputs* fwd_out, const avc_neus_cotangents* cot, float* grad_params,
+                        void* workspace, size_t workspace_bytes, int64_t max_rays_per_chunk, int32_t flags,
+                        avc_stream_t stream) {
+  if (!cfg || !params || !rays_o || !rays_d || !fwd_out || !cot || !grad_params || !workspace) return AVC_E_NULL;
+  if (!fwd_out->z_vals || !fwd_out->weights) return AVC_E_NULL;
+  if (bg_kind < 0 || bg_kind > 2 || (bg_kind != 0 && !background)) return AVC_E_BADCFG;
+  if (R <= 0 || max_rays_per_chunk <= 0) return AVC_E_SIZE;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
+  AVC_TRY(check_ptr16(workspace)); AVC_TRY(check_ptr16(params)); AVC_TRY(check_ptr16(grad_params));
+  const int64_t Rc_max = R < max_rays_per_chunk ? R : max_rays_per_chunk;
+  NeusWs w;
+  carve_ws(pl, Rc_max, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool single = (R <= Rc_max) && !(flags & AVC_BWD_RECOMPUTE);
+
+  // The workspace still holds pack / ctx sums / (single chunk) the stash of the matching forward.
+  // Multi-chunk calls rebuild the stash per chunk from the saved depths.
+  AVC_CUDA_TRY(cudaMemsetAsync(w.wbar, 0, sizeof(float) * (size_t)pl.n_params, st));
+  k_ctx_init<<<1, 32, 0, st>>>(params, pl.off_var, w.ctx, 1);
+  AVC_LAUNCH_TRY();
+  for (int64_t r0 = 0; r0 < R; r0 += Rc_max) {   // eikonal normaliser over ALL rays of the call
+    const int64_t Rc = (R - r0) < Rc_max ? (R - r0) : Rc_max;
+    k_relax_count<<<blocks_for(Rc, 128), 128, 0, st>>>(rays_o + r0 * 3, rays_d + r0 * 3, fwd_out->z_vals + r0 * pl.S,
+                                                       pl.S, Rc, 2.0f / (float)pl.n0, w.ray_part);
+    k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, Rc, 1, w.ctx + CTX_EIK_DEN);
+    AVC_LAUNCH_TRY();
+  }
+  if (!single) {
+    AVC_TRY(zero_pack(pl, w.pack, st));
+    AVC_TRY(pack_weights(pl, params, w.pack, st));
+  }
+  for (int64_t r0 = 0; r0 < R; r0 += Rc_max) {
+    const int64_t Rc = (R - r0) < Rc_max ? (R - r0) : Rc_max;
+    ChunkIO io;
+    io.rays_o = rays_o + r0 * 3; io.rays_d = rays_d + r0 * 3;
+    io.background = (bg_kind == 2) ? background + r0 : background;
+    io.bg_kind = bg_kind; io.cos_anneal = cos_anneal_ratio; io.Rc = Rc;
+    io.out = offset_outputs(*fwd_out, r0, pl.S);
+    if (!single) AVC_TRY(fine_forward(pl, w, io, false, st));
+    avc_neus_cotangents c = offset_cot(*cot, r0, pl.S);
+    AVC_TRY(fine_backward(pl, w, io, c, st));
+  }
+  AVC_TRY(weight_norm_backward_all(pl, params, w.wbar, grad_params, st));
+  k_variance_grad<<<1, 256, 0, st>>>(params, pl.off_var, w.ctx, cot->s_val, R, grad_params + pl.off_var);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float* pts, int64_t P, float* sdf_out,
+                       void* workspace, size_t workspace_bytes, avc_stream_t stream) {
+  if (!cfg || !params || !pts || !sdf_out || !workspace) return AVC_E_NULL;
+  if (P <= 0) return AVC_E_SIZE;
+  NeusPlan pl;
+  AVC_TRY(build_plan(cfg, &pl));
+  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
+  // the workspace is sized in rays; a chunk of Rc rays offers Rc * S point rows
+  size_t one = 0;
+  AVC_TRY(avc_neus_workspace_bytes(cfg, 1, &one));
+  NeusWs w;
+  int64_t Rc = 1;
+  {   // largest Rc that fits (bytes grow linearly in Rc)
+    NeusWs w2; carve_ws(pl, 2, nullptr, &w2);
+    size_t per = w2.bytes - one;
+    if (workspace_bytes < one) return AVC_E_SIZE;
+    Rc = 1 + (int64_t)((workspace_bytes - one) / (per ? per : 1));
+    while (Rc > 1) { carve_ws(pl, Rc, nullptr, &w); if (w.bytes <= workspace_bytes) break; --Rc; }
+  }
+  carve_ws(pl, Rc, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  AVC_TRY(zero_pack(pl, w.pack, st));
+  AVC_TRY(pack_weights(pl, params, w.pack, st));
+  const int64_t cap = Rc * pl.S;
+  EncodeTargets t = make_targets(pl, w);
+  for (int64_t p0 = 0; p0 < P; p0 += cap) {
+    int64_t n = (P - p0) < cap ? (P - p0) : cap;
+    k_encode_points<<<blocks_for(n, 128), 128, 0, st>>>(pts + p0 * 3, n, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
+                                                        pl.EP, t);
+    AVC_LAUNCH_TRY();
+    AVC_TRY(value_chain(pl, w, n, false, false, sdf_out + p0, st));
+  }
+  return 0;
+}
+
+int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, int64_t step, float grad_scale, avc_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return AVC_E_NULL;
+  if (n <= 0 || step < 1) return AVC_E_SIZE;
+  double bc1 = 1.0 - pow((double)beta1, (double)step);
+  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  k_adam<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                               eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,979 @@
+// avc_neus_kernels.cuh -- device code of the NeuS path other than the GEMM tiles: weight packing,
+// hierarchical sample placement, positional encoding, the thin (<= 8 wide) contractions, the
+// per-ray compositing forward / backward and the epilogue functors plugged into the GEMM tiles.
+//
+// Reference citations are relative to AvatarGen/AppearanceGen of hongfz16/AvatarCLIP.
+#pragma once
+#include "avc_common.cuh"
+
+namespace avc {
+
+// =============================================================================================
+// Weight packing: W = g * v / ||v||_row  (torch.nn.utils.weight_norm, models/fields.py:65-66,142-143)
+// One block per output row.  Destinations: up to two column segments, each written row-major
+// (W, leading dim ldw) and transposed (WT, leading dim ldwt); rows < row_shift of segment 0 go to
+// `row0` instead (the sdf row of the last SDF linear).
+// =============================================================================================
+struct PackJob {
+  const float* v; const float* g; const float* b;
+  int N, K;
+  int c0[2], c1[2];          // source column ranges of the two segments (c1 <= c0 => unused)
+  float* W[2]; int ldw[2];   // W[s][(n - row_shift) * ldw + (c - c0)]
+  float* WT[2]; int ldwt[2]; // WT[s][(c - c0) * ldwt + (n - row_shift)]
+  int row_shift;             // 0, or 1 for the last SDF linear
+  float* row0; float* row0_b;  // destination of row 0 when row_shift == 1
+  float* bias; int bias_shift; // bias[n - bias_shift] for n >= bias_shift
+  int dst_row_off;           // added to (n - row_shift): packs lin{Lc} and extra_lin into W6
+};
+
+__global__ void __launch_bounds__(128) k_pack_linear(PackJob j) {
+  const int n = blockIdx.x;
+  if (n >= j.N) return;
+  const float* vr = j.v + (size_t)n * j.K;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < j.K; k += blockDim.x) ss += vr[k] * vr[k];
+  __shared__ float red[4];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = red[0] + red[1] + red[2] + red[3];
+  const float sc = j.g[n] / sqrtf(tot);
+  if (n < j.row_shift) {
+    for (int k = threadIdx.x; k < j.K; k += blockDim.x) j.row0[k] = sc * vr[k];
+    if (threadIdx.x == 0 && j.row0_b) j.row0_b[0] = j.b[n];
+    return;
+  }
+  const int dn = n - j.row_shift + j.dst_row_off;
+  for (int s = 0; s < 2; ++s) {
+    if (j.c1[s] <= j.c0[s]) continue;
+    for (int k = j.c0[s] + threadIdx.x; k < j.c1[s]; k += blockDim.x) {
+      float w = sc * vr[k];
+      if (j.W[s]) j.W[s][(size_t)dn * j.ldw[s] + (k - j.c0[s])] = w;
+      if (j.WT[s]) j.WT[s][(size_t)(k - j.c0[s]) * j.ldwt[s] + dn] = w;
+    }
+  }
+  if (threadIdx.x == 0 && j.bias && n >= j.bias_shift) j.bias[n - j.bias_shift + j.dst_row_off] = j.b[n];
+}
+
+// Weight-norm backward: Wbar (dense, in the v slot of `wbar`) -> gbar, vbar; bias grads copied.
+//   gbar = sum_k Wbar * vhat ; vbar = g/||v|| (Wbar - gbar vhat)        (vhat = v/||v||)
+__global__ void __launch_bounds__(128)
+k_wn_backward(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ Wbar,
+              const float* __restrict__ bbar, int N, int K, float* __restrict__ gg, float* __restrict__ gv,
+              float* __restrict__ gb) {
+  const int n = blockIdx.x;
+  if (n >= N) return;
+  const float* vr = v + (size_t)n * K;
+  const float* wr = Wbar + (size_t)n * K;
+  float ss = 0.f, dot = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { ss += vr[k] * vr[k]; dot += wr[k] * vr[k]; }
+  __shared__ float r1[4], r2[4];
+  ss = warp_sum(ss); dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = ss; r2[threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  ss = r1[0] + r1[1] + r1[2] + r1[3];
+  dot = r2[0] + r2[1] + r2[2] + r2[3];
+  const float nv = sqrtf(ss);
+  const float gbar = dot / nv;
+  const float gn = g[n] / nv;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) gv[(size_t)n * K + k] = gn * (wr[k] - gbar * vr[k] / nv);
+  if (threadIdx.x == 0) { gg[n] = gbar; gb[n] = bbar[n]; }
+}
+
+// =============================================================================================
+// Positional encoding (models/embedder.py:11-36): e = [y, sin(2^k y), cos(2^k y)]_{k<L}, y = scale*x.
+// =============================================================================================
+struct EncodeTargets {
+  float* in0; int ld0;              // in[0]: [P][EP]  <- e (padding columns zeroed)
+  int n_skip;                       // skip layers: in[l][:, K-E .. K) <- e / sqrt(2)
+  float* skip_ptr[4]; int skip_ld[4]; int skip_col[4];
+};
+
+__device__ __forceinline__ void encode_point(float x0, float x1, float x2, float scale, int multires, int E, int EP,
+                                             int64_t p, const EncodeTargets& t) {
+  const float y[3] = {x0 * scale, x1 * scale, x2 * scale};
+  float* r0 = t.in0 + (size_t)p * t.ld0;
+  auto put = [&](int c, float v) {
+    r0[c] = v;
+    for (int s = 0; s < t.n_skip; ++s) t.skip_ptr[s][(size_t)p * t.skip_ld[s] + t.skip_col[s] + c] = v * kSqrtHalf;
+  };
+  put(0, y[0]); put(1, y[1]); put(2, y[2]);
+  float f = 1.f;
+  for (int k = 0; k < multires; ++k) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sn, cs;
+      sincosf(y[c] * f, &sn, &cs);
+      put(3 + 6 * k + c, sn);
+      put(6 + 6 * k + c, cs);
+    }
+    f *= 2.f;
+  }
+  for (int c = E; c < EP; ++c) r0[c] = 0.f;
+}
+
+// Sampling passes: points in SAMPLE-MAJOR order p = j * Rc + r taken from z[j][r] (first nz rows).
+__global__ void k_encode_samples(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                 const float* __restrict__ z, int nz, int Rc, float scale, int multires, int E, int EP,
+                                 EncodeTargets t) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= (int64_t)nz * Rc) return;
+  int r = (int)(p % Rc);
+  float zz = z[p];
+  // renderer.py:337 / :182: pts = rays_o + rays_d * z  (separately rounded mul and add, as torch does)
+  float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], zz));
+  float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], zz));
+  float x2 = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], zz));
+  encode_point(x0, x1, x2, scale, multires, E, EP, p, t);
+}
+
+// Arbitrary query points [P][3] (SDFNetwork.sdf for extract_fields).
+__global__ void k_encode_points(const float* __restrict__ pts, int64_t P, float scale, int multires, int E, int EP,
+                                EncodeTargets t) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  encode_point(pts[p * 3 + 0], pts[p * 3 + 1], pts[p * 3 + 2], scale, multires, E, EP, p, t);
+}
+
+// Fine pass (render_core, renderer.py:208-219): ray-major p = r * S + j.  Section midpoints, dists,
+// mid_z / inside_sphere outputs, cin[p] = (x, 0,0,0, 0,0), encoding.
+__global__ void k_encode_fine(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              const float* __restrict__ z_vals, int S, int64_t Rc, float sample_dist,
+                              float scale, int multires, int E, int EP, float* __restrict__ cin,
+                              float* __restrict__ mid_z_out, float* __restrict__ inside_out, EncodeTargets t) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= Rc * S) return;
+  int64_t r = p / S;
+  int j = (int)(p - r * S);
+  float z0 = z_vals[p];
+  float dist = (j + 1 < S) ? __fsub_rn(z_vals[p + 1], z0) : sample_dist;
+  float mid = __fadd_rn(z0, __fmul_rn(dist, 0.5f));
+  float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], mid));
+  float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], mid));
+  float x2 = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], mid));
+  float4* c = reinterpret_cast<float4*>(cin + (size_t)p * 8);
+  c[0] = make_float4(x0, x1, x2, 0.f);
+  c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (mid_z_out) mid_z_out[p] = mid;
+  if (inside_out) {
+    float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+    inside_out[p] = nrm < 1.0f ? 1.f : 0.f;
+  }
+  encode_point(x0, x1, x2, scale, multires, E, EP, p, t);
+}
+
+// =============================================================================================
+// Hierarchical sample placement (renderer.py:302-352, 133-193, 39-69).  One thread per ray; every
+// per-ray array lives in sample-major global buffers [j][r] so that a warp's accesses coalesce.
+// Discontinuous decisions (bin search, radius < 1) use separately rounded mul/add like torch eager.
+// =============================================================================================
+__device__ __forceinline__ float torch_linspace(float start, float end, int n, int j) {
+  // at::linspace (float): step = (end-start)/(n-1); first half start + step*j, second half end - step*(n-1-j)
+  if (n == 1) return start;
+  float step = (end - start) / (float)(n - 1);
+  return (j < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)j)) : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - j)));
+}
+
+__global__ void k_coarse_z(const float* __restrict__ near, const float* __restrict__ far,
+                           const float* __restrict__ jitter, int n, int Rc, float* __restrict__ z) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rc) return;
+  float nr = near[r], fr = far[r];
+  float span = __fsub_rn(fr, nr);
+  float jit = 0.f;
+  if (jitter) jit = __fdiv_rn(__fmul_rn(jitter[r], 2.0f), (float)n);   // renderer.py:319
+  for (int j = 0; j < n; ++j) {
+    float zz = __fadd_rn(nr, __fmul_rn(span, torch_linspace(0.f, 1.f, n, j)));  // renderer.py:305-306
+    if (jitter) zz = __fadd_rn(zz, jit);
+    z[(size_t)j * Rc + r] = zz;
+  }
+}
+
+__device__ __forceinline__ float ray_radius(const float* o, const float* d, float z) {
+  float x0 = __fadd_rn(o[0], __fmul_rn(d[0], z));
+  float x1 = __fadd_rn(o[1], __fmul_rn(d[1], z));
+  float x2 = __fadd_rn(o[2], __fmul_rn(d[2], z));
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+}
+
+// up_sample (renderer.py:133-177) + sample_pdf(det=True) (:39-69).  n = current samples per ray.
+__global__ void k_upsample(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                           const float* __restrict__ z, const float* __restrict__ sdf, int n, int Rc,
+                           float inv_s, int per, float* __restrict__ wscr, float* __restrict__ newz) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rc) return;
+  const float o[3] = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
+  const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
+  float z_prev = z[r], s_prev = sdf[r];
+  float rad_prev = ray_radius(o, d, z_prev);
+  float prev_cos = 0.f, T = 1.f, wsum = 0.f;
+  for (int j = 0; j + 1 < n; ++j) {
+    float z_next = z[(size_t)(j + 1) * Rc + r], s_next = sdf[(size_t)(j + 1) * Rc + r];
+    float rad_next = ray_radius(o, d, z_next);
+    float inside = (rad_prev < 1.0f || rad_next < 1.0f) ? 1.f : 0.f;
+    float mid_sdf = __fmul_rn(__fadd_rn(s_prev, s_next), 0.5f);
+    float dist = __fsub_rn(z_next, z_prev);
+    float cosv = __fdiv_rn(__fsub_rn(s_next, s_prev), __fadd_rn(dist, 1e-5f));
+    float cm = fminf(prev_cos, cosv);
+    prev_cos = cosv;
+    cm = fminf(fmaxf(cm, -1e3f), 0.0f) * inside;
+    float half = __fmul_rn(__fmul_rn(cm, dist), 0.5f);
+    float prev_esti = __fsub_rn(mid_sdf, half);
+    float next_esti = __fadd_rn(mid_sdf, half);
+    float pc = sigmoidf_acc(__fmul_rn(prev_esti, inv_s));
+    float nc = sigmoidf_acc(__fmul_rn(next_esti, inv_s));
+    float alpha = __fdiv_rn(__fadd_rn(__fsub_rn(pc, nc), 1e-5f), __fadd_rn(pc, 1e-5f));
+    float w = __fadd_rn(__fmul_rn(alpha, T), 1e-5f);          // weights + 1e-5 (renderer.py:41)
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f));
+    wscr[(size_t)j * Rc + r] = w;
+    wsum = __fadd_rn(wsum, w);
+    z_prev = z_next; s_prev = s_next; rad_prev = rad_next;
+  }
+  // inverse CDF with a two-pointer walk: cdf[0] = 0, cdf[k] = cdf[k-1] + pdf[k-1], k < n
+  int k = 1;
+  float c_km1 = 0.f;
+  float c_k = __fdiv_rn(wscr[r], wsum);
+  float ustart = 0.5f / (float)per, uend = 1.0f - 0.5f / (float)per;
+  for (int t = 0; t < per; ++t) {
+    float u = torch_linspace(ustart, uend, per, t);
+    while (k < n && c_k <= u) {       // searchsorted(right=True): count of entries <= u
+      c_km1 = c_k;
+      ++k;
+      if (k < n) c_k = __fadd_rn(c_km1, __fdiv_rn(wscr[(size_t)(k - 1) * Rc + r], wsum));
+    }
+    int below = k - 1;
+    int above = (k < n) ? k : n - 1;
+    float cb = c_km1, ca = (k < n) ? c_k : c_km1;
+    float zb = z[(size_t)below * Rc + r], za = z[(size_t)above * Rc + r];
+    float denom = __fsub_rn(ca, cb);
+    if (denom < 1e-5f) denom = 1.0f;
+    float tt = __fdiv_rn(__fsub_rn(u, cb), denom);
+    newz[(size_t)t * Rc + r] = __fadd_rn(zb, __fmul_rn(tt, __fsub_rn(za, zb)));
+  }
+}
+
+// cat_z_vals (renderer.py:179-193): merge two ascending lists (old entries first on ties).
+// When out_raymajor != NULL the merged depths are also written ray-major [r][n+per] (final round).
+__global__ void k_merge(const float* __restrict__ z, const float* __restrict__ sdf, int n,
+                        const float* __restrict__ newz, const float* __restrict__ news, int per, int Rc,
+                        float* __restrict__ zo, float* __restrict__ so, float* __restrict__ out_raymajor) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rc) return;
+  int a = 0, b = 0;
+  float za = z[r], zb = newz[r];
+  for (int o = 0; o < n + per; ++o) {
+    bool take_a = (b >= per) || (a < n && za <= zb);
+    float zv, sv = 0.f;
+    if (take_a) {
+      zv = za;
+      if (news) sv = sdf[(size_t)a * Rc + r];
+      ++a;
+      if (a < n) za = z[(size_t)a * Rc + r];
+    } else {
+      zv = zb;
+      if (news) sv = news[(size_t)b * Rc + r];
+      ++b;
+      if (b < per) zb = newz[(size_t)b * Rc + r];
+    }
+    zo[(size_t)o * Rc + r] = zv;
+    if (news) so[(size_t)o * Rc + r] = sv;
+    if (out_raymajor) out_raymajor[(size_t)r * (n + per) + o] = zv;
+  }
+}
+
+__global__ void k_transpose_z(const float* __restrict__ z, int n, int Rc, float* __restrict__ out_raymajor) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n * Rc) return;
+  int r = (int)(i / n), j = (int)(i % n);
+  out_raymajor[i] = z[(size_t)j * Rc + r];
+}
+
+// =============================================================================================
+// Thin contractions (<= 8 outputs): one warp per row, lanes stride the reduction with float4 loads.
+//   v[i] = sum_k A[p,k] * W[i*ldw + k]  (+ b[i]);  Out functor consumes the NI values.
+// =============================================================================================
+template <int NI, typename Out>
+__global__ void __launch_bounds__(256)
+k_thin_nt(const float* __restrict__ A, int lda, int K, const float* __restrict__ W, int ldw,
+          const float* __restrict__ b, int64_t P, Out out) {
+  int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= P) return;
+  const int lane = threadIdx.x & 31;
+  float acc[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) acc[i] = 0.f;
+  const float* ar = A + (size_t)p * lda;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 a = *reinterpret_cast<const float4*>(ar + k);
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      float4 w = *reinterpret_cast<const float4*>(W + (size_t)i * ldw + k);
+      acc[i] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[i]))));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NI; ++i) acc[i] = warp_sum(acc[i]) + (b ? b[i] : 0.f);
+  if (lane == 0) out(p, acc);
+}
+
+struct OutSdf {     // sdf = z_L[0] / scale   (models/fields.py:88)
+  float* sdf; float inv_scale;
+  __device__ void operator()(int64_t p, const float* v) const { sdf[p] = v[0] * inv_scale; }
+};
+struct OutHeads {   // sigmoid of both colour heads (models/fields.py:180-184) -> rgb6[p][8]
+  float* rgb6;
+  __device__ void operator()(int64_t p, const float* v) const {
+    float4 a = make_float4(sigmoidf_acc(v[0]), sigmoidf_acc(v[1]), sigmoidf_acc(v[2]), sigmoidf_acc(v[3]));
+    float4 b = make_float4(sigmoidf_acc(v[4]), sigmoidf_acc(v[5]), 0.f, 0.f);
+    reinterpret_cast<float4*>(rgb6 + (size_t)p * 8)[0] = a;
+    reinterpret_cast<float4*>(rgb6 + (size_t)p * 8)[1] = b;
+  }
+};
+struct OutNbarAdd { // nbar[p][0..2] += d loss / d normal coming through colour lin0 (columns 3..5)
+  float* nbar;
+  __device__ void operator()(int64_t p, const float* v) const {
+    nbar[(size_t)p * 4 + 0] += v[3]; nbar[(size_t)p * 4 + 1] += v[4]; nbar[(size_t)p * 4 + 2] += v[5];
+  }
+};
+
+// out[i*si + c*sc] += sum_p S[p*lds + i] * Hm[p*ldh + c]   (i < NI, c < NC);  optional s_scale on S;
+// optional bout[i] += sum_p S[p,i].  Blocks split the rows; threads own columns.
+template <int NI>
+__global__ void __launch_bounds__(256)
+k_thin_tn(const float* __restrict__ S, int lds, float s_scale, const float* __restrict__ Hm, int ldh, int NC,
+          int64_t P, int rows_per_block, float* __restrict__ out, int si, int sc, float* __restrict__ bout) {
+  __shared__ float sS[64][NI];
+  const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t p1 = min(P, p0 + (int64_t)rows_per_block);
+  float bacc = 0.f;
+  for (int cb = 0; cb < NC; cb += blockDim.x) {
+    const int c = cb + threadIdx.x;
+    float acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[i] = 0.f;
+    for (int64_t pb = p0; pb < p1; pb += 64) {
+      int nr = (int)min((int64_t)64, p1 - pb);
+      __syncthreads();
+      for (int t = threadIdx.x; t < nr * NI; t += blockDim.x) {
+        int rr = t / NI, ii = t % NI;
+        sS[rr][ii] = S[(size_t)(pb + rr) * lds + ii] * s_scale;
+      }
+      __syncthreads();
+      if (c < NC) {
+        for (int rr = 0; rr < nr; ++rr) {
+          float h = Hm[(size_t)(pb + rr) * ldh + c];
+#pragma unroll
+          for (int i = 0; i < NI; ++i) acc[i] = fmaf(sS[rr][i], h, acc[i]);
+        }
+      }
+      if (bout && cb == 0 && threadIdx.x < NI)
+        for (int rr = 0; rr < nr; ++rr) bacc += sS[rr][threadIdx.x];
+    }
+    if (c < NC) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) atomicAdd(out + (size_t)i * si + (size_t)c * sc, acc[i]);
+    }
+  }
+  if (bout && threadIdx.x < NI) atomicAdd(bout + threadIdx.x, bacc);
+}
+
+// out[c] += scale * sum_p X[p*ld + c], c < NC
+__global__ void __launch_bounds__(256)
+k_colsum(const float* __restrict__ X, int ld, int NC, int64_t P, int rows_per_block, float scale,
+         float* __restrict__ out) {
+  const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t p1 = min(P, p0 + (int64_t)rows_per_block);
+  for (int c = threadIdx.x; c < NC; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t p = p0; p < p1; ++p) acc += X[(size_t)p * ld + c];
+    atomicAdd(out + c, acc * scale);
+  }
+}
+
+// =============================================================================================
+// Gradient chain helpers (SDFNetwork.gradient, models/fields.py:96-107, as a reverse sweep).
+// =============================================================================================
+// u_L = row 0 of W_L (constant):  qt[L-1] = softplus'(z[L-1]) * ua_L ; ge initialised.
+__global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL, int E, int EP,
+                              const float* __restrict__ zprev, int Nprev, int Npp, int64_t P,
+                              float* __restrict__ qt, float* __restrict__ ge) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = P * (int64_t)Npp;
+  if (i < tot) {
+    int64_t p = i / Npp;
+    int c = (int)(i - p * Npp);
+    float v = 0.f;
+    if (c < Nprev) {
+      float ua = wsdf[c] * (skipL ? kSqrtHalf : 1.f);
+      v = softplus100_d1(zprev[i]) * ua;
+    }
+    qt[i] = v;
+  }
+  if (i < P * (int64_t)EP) {
+    int64_t p = i / EP;
+    int e = (int)(i - p * EP);
+    ge[i] = (skipL && e < E) ? wsdf[KL - E + e] * kSqrtHalf : 0.f;
+  }
+}
+
+// n = D(y)^T ge  (grad_x sdf); writes cin[p][3..5] and the `gradients` output.
+__global__ void k_normal(const float* __restrict__ ge, int EP, int multires, float scale, int64_t P,
+                         float* __restrict__ cin, float* __restrict__ grad_out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* g = ge + (size_t)p * EP;
+  float* c = cin + (size_t)p * 8;
+  float n[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float y = c[a] * scale;
+    float acc = g[a];
+    float f = 1.f;
+    for (int k = 0; k < multires; ++k) {
+      float sn, cs;
+      sincosf(y * f, &sn, &cs);
+      acc += f * (cs * g[3 + 6 * k + a] - sn * g[6 + 6 * k + a]);
+      f *= 2.f;
+    }
+    n[a] = acc;
+  }
+  c[3] = n[0]; c[4] = n[1]; c[5] = n[2];
+  if (grad_out) { grad_out[p * 3 + 0] = n[0]; grad_out[p * 3 + 1] = n[1]; grad_out[p * 3 + 2] = n[2]; }
+}
+
+// gebar = D(y) nbar -> ubar0[p][EP] (padding zeroed) and gebar[p][EP].
+__global__ void k_dge(const float* __restrict__ cin, const float* __restrict__ nbar, int EP, int E, int multires,
+                      float scale, int64_t P, float* __restrict__ ubar0, int ldu, float* __restrict__ gebar) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const float* c = cin + (size_t)p * 8;
+  const float nb[3] = {nbar[p * 4 + 0], nbar[p * 4 + 1], nbar[p * 4 + 2]};
+  float* u = ubar0 + (size_t)p * ldu;
+  float* g = gebar + (size_t)p * EP;
+  auto put = [&](int col, float v) { u[col] = v; g[col] = v; };
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float y = c[a] * scale;
+    put(a, nb[a]);
+    float f = 1.f;
+    for (int k = 0; k < multires; ++k) {
+      float sn, cs;
+      sincosf(y * f, &sn, &cs);
+      put(3 + 6 * k + a, f * cs * nb[a]);
+      put(6 + 6 * k + a, -f * sn * nb[a]);
+      f *= 2.f;
+    }
+  }
+  for (int col = E; col < EP; ++col) put(col, 0.f);
+  for (int col = EP; col < ldu; ++col) u[col] = 0.f;
+}
+
+// ubar[p][col0 + e] = gebar[p][e] / sqrt(2)   (the encoding half of a skip layer's input adjoint)
+__global__ void k_fill_gebar(const float* __restrict__ gebar, int EP, int E, int64_t P, float* __restrict__ ubar,
+                             int ldu, int col0) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * (int64_t)E) return;
+  int64_t p = i / E;
+  int e = (int)(i - p * E);
+  ubar[(size_t)p * ldu + col0 + e] = gebar[(size_t)p * EP + e] * kSqrtHalf;
+}
+
+// cbar[p][c] = (sum_i y6bar[p][i] * W6[i][c]) * [h[p][c] > 0]   (heads dgrad + ReLU mask)
+__global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __restrict__ W6, int Hc,
+                              const float* __restrict__ h, int64_t P, float* __restrict__ cbar) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * (int64_t)Hc) return;
+  int64_t p = i / Hc;
+  int c = (int)(i - p * Hc);
+  const float* y = y6bar + (size_t)p * 8;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) acc = fmaf(y[k], W6[(size_t)k * Hc + c], acc);
+  cbar[i] = h[i] > 0.f ? acc : 0.f;
+}
+
+// =============================================================================================
+// GEMM epilogue functors.  (row, col..col+3, acc) with col % 4 == 0; N = valid output width.
+// =============================================================================================
+#define AVC_EPI_UNPACK float v[4] = {a.x, a.y, a.z, a.w}
+
+// value chain: z = acc + b ; Z[row] = z (padding zero) ; OUT[row][col] = softplus(z) * oscale (col < N)
+struct EpiValue {
+  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+    float zz[4], hh[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      bool ok = col + i < N;
+      zz[i] = ok ? v[i] + bias[col + i] : 0.f;
+      hh[i] = softplus100(zz[i]) * oscale;
+    }
+    if (Z) *reinterpret_cast<float4*>(Z + (size_t)row * ldz + col) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+    if (col + 3 < N) {
+      *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+    } else {
+      for (int i = 0; i < 4 && col + i < N; ++i) OUT[(size_t)row * ldo + col + i] = hh[i];
+    }
+  }
+};
+
+// out = acc + b (feature rows of the last SDF linear)
+struct EpiBias {
+  const float* bias; float* OUT; int ldo; int N;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] + bias[col + i] : 0.f;
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// gradient chain, layer l >= 1: u = acc (width K_l).  Columns < Nprev: ua = u * s, qt_prev = sp'(z_prev) * ua;
+// columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
+struct EpiChain {
+  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = col + i;
+      if (c < Nprev) {
+        QTprev[(size_t)row * Npp + c] = softplus100_d1(Zprev[(size_t)row * Npp + c]) * v[i] * s;
+      } else {
+        if (c < Npp) QTprev[(size_t)row * Npp + c] = 0.f;
+        int e = c - Nprev;
+        if (e < E) GE[(size_t)row * EP + e] += v[i] * kSqrtHalf;
+      }
+    }
+  }
+};
+
+// gradient chain, layer 0: ge += acc  (width E)
+struct EpiGe {
+  float* GE; int EP; int E;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col + i < E) GE[(size_t)row * EP + col + i] += v[i];
+  }
+};
+
+// colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
+struct EpiColor0 {
+  const float* bias; const float* cin; const float* Wx; float* OUT; int ldo;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+    const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)(col + i) * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(Wx + (size_t)(col + i) * 8 + 4);
+      float z = v[i] + bias[col + i];
+      z = fmaf(c0.x, w0.x, z); z = fmaf(c0.y, w0.y, z); z = fmaf(c0.z, w0.z, z);
+      z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
+      v[i] = fmaxf(z, 0.f);
+    }
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+struct EpiRelu {
+  const float* bias; float* OUT; int ldo;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i] + bias[col + i], 0.f);
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// colour dgrad: out = acc * [h > 0]
+struct EpiDgradRelu {
+  const float* Hm; float* OUT; int ld;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+    const float4 h = *reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col);
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) =
+        make_float4(h.x > 0.f ? v[0] : 0.f, h.y > 0.f ? v[1] : 0.f, h.z > 0.f ? v[2] : 0.f, h.w > 0.f ? v[3] : 0.f);
+  }
+};
+
+struct EpiStore {
+  float* OUT; int ldo; int N;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] : 0.f;
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+
+// second-order sweep, layer l < L: qbar = acc (width N_l).
+//   ubar_next[row][col] = sp'(z_l) * qbar * s_next            (col < N_l)
+//   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
+struct EpiChainBwd {
+  int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+    float zb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = col + i;
+      if (c < N) {
+        float s1 = softplus100_d1(Z[(size_t)row * Np + c]);
+        UNEXT[(size_t)row * ldu + c] = s1 * v[i] * s_next;
+        zb[i] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * v[i];
+      } else {
+        zb[i] = 0.f;
+      }
+    }
+    *reinterpret_cast<float4*>(ZBAR + (size_t)row * Np + col) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+  }
+};
+
+// value backward dgrad into layer l-1: abar = (acc [+ sdfbar[row] * wsdf[col]]) * s ;
+//   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev)
+struct EpiDgrad {
+  int Nprev, Npp; float s; const float* Zprev; float* ZBARprev; const float* sdfbar; const float* wsdf;
+  float sdf_inv_scale;
+  __device__ void operator()(int row, int col, float4 a) const {
+    AVC_EPI_UNPACK;
+    float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = col + i;
+      if (c < Nprev) {
+        float ab = v[i];
+        if (sdfbar) ab = fmaf(sb, wsdf[c], ab);
+        size_t o = (size_t)row * Npp + c;
+        ZBARprev[o] = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+      }
+    }
+  }
+};
+
+// =============================================================================================
+// Compositing (render_core, renderer.py:234-286).  One warp per ray; samples in blocks of 32.
+// =============================================================================================
+struct CompositeArgs {
+  const float* rays_d;      // [Rc][3]
+  const float* z_vals;      // [Rc][S]
+  const float* sdf;         // [P]
+  const float* cin;         // [P][8]
+  const float* rgb6;        // [P][8]
+  const float* background;  // NULL | [3] | [Rc]
+  int bg_kind;
+  const float* ctx;         // ctx[CTX_INV_S]
+  float cos_anneal;
+  float sample_dist;
+  int S; int64_t Rc;
+};
+
+struct SampleTerms { float alpha, araw, Pp, Pn, ep, en, tc, dist, gn, relax; };
+
+__device__ __forceinline__ SampleTerms sample_terms(const CompositeArgs& A, int64_t r, int j, float inv_s,
+                                                    const float d[3]) {
+  SampleTerms t;
+  int64_t p = r * A.S + j;
+  float z0 = A.z_vals[p];
+  t.dist = (j + 1 < A.S) ? __fsub_rn(A.z_vals[p + 1], z0) : A.sample_dist;
+  const float4 c0 = *reinterpret_cast<const float4*>(A.cin + (size_t)p * 8);
+  const float4 c1 = *reinterpret_cast<const float4*>(A.cin + (size_t)p * 8 + 4);
+  const float n0 = c0.w, n1 = c1.x, n2 = c1.y;
+  float sdf = A.sdf[p];
+  t.tc = d[0] * n0 + d[1] * n1 + d[2] * n2;                                   // renderer.py:237
+  float ic = -(fmaxf(-t.tc * 0.5f + 0.5f, 0.f) * (1.0f - A.cos_anneal) + fmaxf(-t.tc, 0.f) * A.cos_anneal);
+  t.en = sdf + ic * t.dist * 0.5f;                                            // :245-246
+  t.ep = sdf - ic * t.dist * 0.5f;
+  t.Pp = sigmoidf_acc(t.ep * inv_s);
+  t.Pn = sigmoidf_acc(t.en * inv_s);
+  t.araw = (t.Pp - t.Pn + 1e-5f) / (t.Pp + 1e-5f);                            // :251-254
+  t.alpha = fminf(fmaxf(t.araw, 0.f), 1.f);
+  t.gn = sqrtf(n0 * n0 + n1 * n1 + n2 * n2);
+  float xn = sqrtf(c0.x * c0.x + c0.y * c0.y + c0.z * c0.z);
+  t.relax = xn < 1.2f ? 1.f : 0.f;                                            // :258
+  return t;
+}
+
+__device__ __forceinline__ float warp_excl_prod(float v, float* total) {
+  // exclusive prefix product over lanes; *total = product of all lanes
+  const int lane = threadIdx.x & 31;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc *= t;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  float ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  return lane == 0 ? 1.f : ex;
+}
+
+__global__ void __launch_bounds__(256)
+k_composite_fwd(CompositeArgs A, float* __restrict__ color, float* __restrict__ extra, float* __restrict__ s_val,
+                float* __restrict__ cdf, float* __restrict__ wsum_out, float* __restrict__ wmax_out,
+                float* __restrict__ weights, float* __restrict__ ray_part) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= A.Rc) return;
+  const int lane = threadIdx.x & 31;
+  const float inv_s = A.ctx[CTX_INV_S];
+  const float d[3] = {A.rays_d[r * 3], A.rays_d[r * 3 + 1], A.rays_d[r * 3 + 2]};
+  float carry = 1.f;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float wsum = 0.f, wmax = -1.f, eik_num = 0.f, eik_den = 0.f;
+  for (int j0 = 0; j0 < A.S; j0 += 32) {
+    const int j = j0 + lane;
+    const bool ok = j < A.S;
+    SampleTerms t;
+    float one_m = 1.f;
+    if (ok) {
+      t = sample_terms(A, r, j, inv_s, d);
+      one_m = 1.f - t.alpha + 1e-7f;                                          // :268
+    }
+    float total;
+    float T = carry * warp_excl_prod(one_m, &total);
+    carry *= total;
+    if (ok) {
+      const int64_t p = r * A.S + j;
+      float w = t.alpha * T;
+      weights[p] = w;
+      cdf[p] = t.Pp;
+      const float4 q0 = *reinterpret_cast<const float4*>(A.rgb6 + (size_t)p * 8);
+      const float4 q1 = *reinterpret_cast<const float4*>(A.rgb6 + (size_t)p * 8 + 4);
+      acc[0] += w * q0.x; acc[1] += w * q0.y; acc[2] += w * q0.z;
+      acc[3] += w * q0.w; acc[4] += w * q1.x; acc[5] += w * q1.y;
+      wsum += w;
+      wmax = fmaxf(wmax, w);
+      float e = t.gn - 1.f;
+      eik_num += t.relax * e * e;                                             // :284-286
+      eik_den += t.relax;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) acc[i] = warp_sum(acc[i]);
+  wsum = warp_sum(wsum); eik_num = warp_sum(eik_num); eik_den = warp_sum(eik_den);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) {
+    float bg[3] = {0.f, 0.f, 0.f};
+    if (A.bg_kind == 1) { bg[0] = A.background[0]; bg[1] = A.background[1]; bg[2] = A.background[2]; }
+    else if (A.bg_kind == 2) { bg[0] = bg[1] = bg[2] = A.background[r]; }
+    color[r * 3 + 0] = acc[0]; color[r * 3 + 1] = acc[1]; color[r * 3 + 2] = acc[2];
+    extra[r * 3 + 0] = acc[3] + bg[0] * (1.f - wsum);                          // :277-279 (extra_color=True)
+    extra[r * 3 + 1] = acc[4] + bg[1] * (1.f - wsum);
+    extra[r * 3 + 2] = acc[5] + bg[2] * (1.f - wsum);
+    wsum_out[r] = wsum; wmax_out[r] = wmax;
+    s_val[r] = 1.0f / inv_s;                                                   // :293, :383
+    ray_part[r * 4 + 0] = eik_num; ray_part[r * 4 + 1] = eik_den;
+  }
+}
+
+struct CompositeBwdArgs {
+  const float* g_color; const float* g_extra; const float* g_wsum; const float* g_wmax;
+  const float* g_w; const float* g_cdf; const float* g_n; const float* g_gerr;
+  const float* weights;     // forward output [Rc][S] (for the argmax of weight_max)
+  float* y6bar; float* sdfbar; float* nbar; float* ray_part;
+};
+
+__global__ void __launch_bounds__(256) k_composite_bwd(CompositeArgs A, CompositeBwdArgs G) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= A.Rc) return;
+  const int lane = threadIdx.x & 31;
+  const float inv_s = A.ctx[CTX_INV_S];
+  const float eik_den_total = A.ctx[CTX_EIK_DEN];
+  const float g_gerr = G.g_gerr ? G.g_gerr[0] : 0.f;
+  const float d[3] = {A.rays_d[r * 3], A.rays_d[r * 3 + 1], A.rays_d[r * 3 + 2]};
+  float gc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (G.g_color) { gc[0] = G.g_color[r * 3]; gc[1] = G.g_color[r * 3 + 1]; gc[2] = G.g_color[r * 3 + 2]; }
+  if (G.g_extra) { gc[3] = G.g_extra[r * 3]; gc[4] = G.g_extra[r * 3 + 1]; gc[5] = G.g_extra[r * 3 + 2]; }
+  float wbar_common = G.g_wsum ? G.g_wsum[r] : 0.f;
+  if (A.bg_kind == 1) wbar_common -= gc[3] * A.background[0] + gc[4] * A.background[1] + gc[5] * A.background[2];
+  else if (A.bg_kind == 2) wbar_common -= (gc[3] + gc[4] + gc[5]) * A.background[r];
+  const int nb = (A.S + 31) >> 5;
+
+  // argmax of the stored weights (first occurrence), only when weight_max has a cotangent
+  int amax = -1;
+  float g_wmax = 0.f;
+  if (G.g_wmax) {
+    g_wmax = G.g_wmax[r];
+    float best = -1.f; int bi = 0x7fffffff;
+    for (int j = lane; j < A.S; j += 32) {
+      float w = G.weights[r * A.S + j];
+      if (w > best) { best = w; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    amax = bi;
+  }
+
+  // pass A: recompute alpha, T, w and the total cotangent of w per sample
+  SampleTerms tt[8];
+  float Tj[8], wb[8], ww[8];
+  float carry = 1.f;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    if (b >= nb) break;
+    const int j = b * 32 + lane;
+    const bool ok = j < A.S;
+    float one_m = 1.f;
+    if (ok) { tt[b] = sample_terms(A, r, j, inv_s, d); one_m = 1.f - tt[b].alpha + 1e-7f; }
+    float total;
+    float T = carry * warp_excl_prod(one_m, &total);
+    carry *= total;
+    Tj[b] = T; wb[b] = 0.f; ww[b] = 0.f;
+    if (ok) {
+      const int64_t p = r * A.S + j;
+      float w = tt[b].alpha * T;
+      ww[b] = w;
+      const float4 q0 = *reinterpret_cast<const float4*>(A.rgb6 + (size_t)p * 8);
+      const float4 q1 = *reinterpret_cast<const float4*>(A.rgb6 + (size_t)p * 8 + 4);
+      float wbar = wbar_common + (G.g_w ? G.g_w[p] : 0.f);
+      wbar += gc[0] * q0.x + gc[1] * q0.y + gc[2] * q0.z + gc[3] * q0.w + gc[4] * q1.x + gc[5] * q1.y;
+      if (j == amax) wbar += g_wmax;
+      wb[b] = wbar;
+      // colour heads: rgb6bar = w * g ; through the sigmoid
+      float y[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+      float o6[8];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) o6[i] = w * gc[i] * y[i] * (1.f - y[i]);
+      o6[6] = o6[7] = 0.f;
+      reinterpret_cast<float4*>(G.y6bar + (size_t)p * 8)[0] = make_float4(o6[0], o6[1], o6[2], o6[3]);
+      reinterpret_cast<float4*>(G.y6bar + (size_t)p * 8)[1] = make_float4(o6[4], o6[5], 0.f, 0.f);
+    }
+  }
+  // pass B: suffix sums  Asuf_j = sum_{t > j} wbar_t w_t   (reverse order over blocks and lanes)
+  float invs_bar = 0.f;
+  float suffix_carry = 0.f;
+#pragma unroll
+  for (int b = 7; b >= 0; --b) {
+    if (b >= nb) continue;
+    const int j = b * 32 + lane;
+    const bool ok = j < A.S;
+    float v = ok ? wb[b] * ww[b] : 0.f;
+    float inc = v;   // inclusive suffix scan over lanes (lane 31 -> 0)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      float t = __shfl_down_sync(0xffffffffu, inc, o);
+      if (lane + o < 32) inc += t;
+    }
+    float block_total = __shfl_sync(0xffffffffu, inc, 0);
+    float Asuf = inc - v + suffix_carry;
+    suffix_carry += block_total;
+    if (ok) {
+      const SampleTerms& t = tt[b];
+      const int64_t p = r * A.S + j;
+      float abar = wb[b] * Tj[b] - Asuf / (1.f - t.alpha + 1e-7f);
+      if (!(t.araw >= 0.f && t.araw <= 1.f)) abar = 0.f;                       // clip(0,1) (:254)
+      float den = t.Pp + 1e-5f;
+      float Ppbar = abar * t.Pn / (den * den) + (G.g_cdf ? G.g_cdf[p] : 0.f);
+      float Pnbar = -abar / den;
+      float dPp = t.Pp * (1.f - t.Pp), dPn = t.Pn * (1.f - t.Pn);
+      float epbar = Ppbar * dPp * inv_s, enbar = Pnbar * dPn * inv_s;
+      invs_bar += Ppbar * dPp * t.ep + Pnbar * dPn * t.en;
+      G.sdfbar[p] = epbar + enbar;
+      float icbar = (enbar - epbar) * t.dist * 0.5f;
+      float tcbar = icbar * (0.5f * (1.f - A.cos_anneal) * (t.tc < 1.f ? 1.f : 0.f) + A.cos_anneal * (t.tc < 0.f ? 1.f : 0.f));
+      const float4 c0 = *reinterpret_cast<const float4*>(A.cin + (size_t)p * 8);
+      const float4 c1 = *reinterpret_cast<const float4*>(A.cin + (size_t)p * 8 + 4);
+      float n[3] = {c0.w, c1.x, c1.y};
+      float eik = (t.gn > 0.f) ? g_gerr * t.relax * 2.f * (t.gn - 1.f) / (eik_den_total + 1e-5f) / t.gn : 0.f;
+      float nb3[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) nb3[a] = tcbar * d[a] + eik * n[a] + (G.g_n ? G.g_n[p * 3 + a] : 0.f);
+      *reinterpret_cast<float4*>(G.nbar + (size_t)p * 4) = make_float4(nb3[0], nb3[1], nb3[2], 0.f);
+    }
+  }
+  invs_bar = warp_sum(invs_bar);
+  if (lane == 0) G.ray_part[r * 4 + 2] = invs_bar;
+}
+
+// Deterministic single-block reductions of the per-ray partials into ctx.
+__global__ void __launch_bounds__(1024) k_reduce_ray_part(const float* __restrict__ ray_part, int64_t Rc, int comp,
+                                                          float* __restrict__ dst) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t r = threadIdx.x; r < Rc; r += blockDim.x) s += ray_part[r * 4 + comp];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) dst[0] += v;
+  }
+}
+
+// Eikonal normaliser sum_p [ ||x_p|| < 1.2 ] recomputed from the geometry alone (renderer.py:258),
+// so that the backward does not depend on scalars left in the workspace by the forward.
+__global__ void k_relax_count(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              const float* __restrict__ z_vals, int S, int64_t Rc, float sample_dist,
+                              float* __restrict__ ray_part) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= Rc) return;
+  float cnt = 0.f;
+  for (int j = 0; j < S; ++j) {
+    float z0 = z_vals[r * S + j];
+    float dist = (j + 1 < S) ? __fsub_rn(z_vals[r * S + j + 1], z0) : sample_dist;
+    float mid = __fadd_rn(z0, __fmul_rn(dist, 0.5f));
+    float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], mid));
+    float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], mid));
+    float x2 = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], mid));
+    cnt += sqrtf(x0 * x0 + x1 * x1 + x2 * x2) < 1.2f ? 1.f : 0.f;
+  }
+  ray_part[r * 4 + 1] = cnt;
+}
+
+__global__ void k_ctx_init(const float* __restrict__ params, int64_t off_var, float* __restrict__ ctx, int zero_sums) {
+  if (threadIdx.x == 0) {
+    float e = expf(params[off_var] * 10.0f);                                   // models/fields.py:276
+    ctx[CTX_INV_S] = fminf(fmaxf(e, 1e-6f), 1e6f);                             // renderer.py:234
+    if (zero_sums) { ctx[CTX_EIK_NUM] = 0.f; ctx[CTX_EIK_DEN] = 0.f; }
+    ctx[CTX_INVS_BAR] = 0.f;
+  }
+}
+
+__global__ void k_finalize_fwd(const float* __restrict__ ctx, float* __restrict__ gerr_out) {
+  if (threadIdx.x == 0) gerr_out[0] = ctx[CTX_EIK_NUM] / (ctx[CTX_EIK_DEN] + 1e-5f);   // renderer.py:286
+}
+
+// variance gradient: inv_s = clip(exp(10 v)); s_val = 1/inv_s.
+__global__ void __launch_bounds__(256)
+k_variance_grad(const float* __restrict__ params, int64_t off_var, const float* __restrict__ ctx,
+                const float* __restrict__ g_sval, int64_t R, float* __restrict__ grad_var) {
+  __shared__ float red[8];
+  float s = 0.f;
+  if (g_sval) for (int64_t r = threadIdx.x; r < R; r += blockDim.x) s += g_sval[r];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    float inv_s = ctx[CTX_INV_S];
+    float e = expf(params[off_var] * 10.0f);
+    float bar = ctx[CTX_INVS_BAR] - tot / (inv_s * inv_s);
+    grad_var[0] = (e > 1e-6f && e < 1e6f) ? bar * 10.0f * inv_s : 0.f;
+  }
+}
+
+// Fused Adam (torch.optim.Adam defaults; main.py:145,536-538).
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                       float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
+                       float bc2_sqrt, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
+  float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+}  // namespace avc

@@ -1,0 +1,161 @@
+/* avc_b200.h -- C ABI of libavc_b200.so: B200-native (sm_100a) kernels for the AvatarCLIP
+ * appearance-optimisation hot path.
+ *
+ * The reference (hongfz16/AvatarCLIP, AvatarGen/AppearanceGen) is pure Python/PyTorch and has
+ * no FFI layer of its own; the seam it offers is the Python object protocol used by
+ * `Runner` (main.py:147-151, 418-420).  Each entry point below replaces the torch-eager
+ * implementation of one reference function; the citation names it (paths relative to
+ * AvatarGen/AppearanceGen).  INTEGRATION.md shows the ctypes binding a maintainer of the
+ * reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (a torch tensor), fp32 unless noted;
+ *   - every function enqueues work on `stream` and returns immediately (no host sync);
+ *   - nothing allocates: scratch is sized by the *_workspace_bytes queries and passed in;
+ *   - return value: 0 ok, <0 AVC_E_* (invalid argument), >0 a cudaError_t;
+ *   - no global mutable state; safe to call from one host thread per device.
+ */
+#ifndef AVC_B200_H
+#define AVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* avc_stream_t; /* cudaStream_t */
+
+#define AVC_OK 0
+#define AVC_E_BADCFG (-1)   /* unsupported network / renderer configuration            */
+#define AVC_E_NULL (-2)     /* a required pointer is NULL                               */
+#define AVC_E_SIZE (-3)     /* workspace too small / size mismatch                      */
+#define AVC_E_ALIGN (-4)    /* pointer not 16-byte aligned                              */
+#define AVC_E_NOSTASH (-5)  /* backward called on a workspace with no matching forward  */
+
+#define AVC_ABI_VERSION 1
+int avc_abi_version(void);
+/* Compiled-for architecture string, e.g. "sm_100a". */
+const char* avc_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * NeuS renderer: SDFNetwork + RenderingNetwork + SingleVarianceNetwork + NeuSRenderer.render
+ * (models/fields.py:9-107,111-185,270-276; models/embedder.py:6-51; models/renderer.py:39-69,
+ * 133-397).  Supported: mode 'no_view_dir', multires_view 0, squeeze_out, extra_color,
+ * weight_norm, n_outside 0 -- i.e. every conf shipped under confs/ (SURVEY.md fact 1).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct avc_neus_cfg {
+  /* SDFNetwork ctor (models/fields.py:10-21) */
+  int32_t sdf_d_in;        /* 3 */
+  int32_t sdf_d_out;       /* d_hidden + 1 in every conf: sdf + feature vector */
+  int32_t sdf_d_hidden;
+  int32_t sdf_n_layers;    /* number of hidden layers; linears = n_layers + 1 */
+  uint32_t sdf_skip_mask;  /* bit l set <=> l in skip_in */
+  int32_t sdf_multires;
+  float sdf_scale;
+  /* RenderingNetwork ctor (models/fields.py:112-122); d_in = 6 (points, normals) */
+  int32_t col_d_feature;
+  int32_t col_d_hidden;
+  int32_t col_n_layers;
+  /* NeuSRenderer ctor (models/renderer.py:73-93) */
+  int32_t n_samples;
+  int32_t n_importance;
+  int32_t up_sample_steps;
+  /* arithmetic engine for the MLP contractions: 0 = fp32 CUDA-core (FFMA) tiles,
+   * 1 = tcgen05 tensor-core tiles with two-term split operands (3 MMAs per product) */
+  int32_t engine;
+} avc_neus_cfg;
+
+/* Flat parameter vector layout (fp32), identical for the gradient vector:
+ *   for each SDF linear l = 0..n_layers:    weight_g[out], weight_v[out*in], bias[out]
+ *   for each colour linear l = 0..n_layers: weight_g, weight_v, bias
+ *   extra_lin:                              weight_g[3], weight_v[3*d_hidden], bias[3]
+ *   variance[1]
+ * (the reference's state-dict tensors `linK.weight_g/weight_v/bias`, `extra_lin.*`, `variance`,
+ * in named_parameters() order).  avc_neus_param_count returns the total length. */
+int avc_neus_param_count(const avc_neus_cfg* cfg, int64_t* n_params);
+/* Offset (in floats) of tensor `which` (0 = weight_g, 1 = weight_v, 2 = bias) of linear `layer`
+ * of net `net` (0 = sdf, 1 = colour, 2 = extra_lin (layer ignored), 3 = variance). */
+int avc_neus_param_offset(const avc_neus_cfg* cfg, int net, int layer, int which, int64_t* offset,
+                          int64_t* numel);
+
+/* Bytes of scratch for rendering up to `max_rays_per_chunk` rays per internal chunk. */
+int avc_neus_workspace_bytes(const avc_neus_cfg* cfg, int64_t max_rays_per_chunk, size_t* bytes);
+
+typedef struct avc_neus_outputs { /* the dict of models/renderer.py:385-397, all [R, ...] row-major */
+  float* color_fine;       /* [R,3]   */
+  float* extra_color_fine; /* [R,3]   */
+  float* s_val;            /* [R,1]   */
+  float* cdf_fine;         /* [R,S]   */
+  float* weight_sum;       /* [R,1]   */
+  float* weight_max;       /* [R,1]   */
+  float* gradients;        /* [R,S,3] */
+  float* weights;          /* [R,S]   */
+  float* mid_z_vals;       /* [R,S]   */
+  float* gradient_error;   /* [1]     */
+  float* inside_sphere;    /* [R,S]   */
+  float* z_vals;           /* [R,S]  sorted sample depths (saved for the backward) */
+} avc_neus_outputs;
+
+/* NeuSRenderer.render forward (models/renderer.py:302-397).
+ *   params      flat parameter vector (see above)
+ *   rays_o/d    [R,3];  near/far [R]
+ *   jitter      [R] values (u-0.5) of renderer.py:317-319, or NULL for perturb = 0
+ *   background  NULL, or [3] (bg_kind 1: one colour, main.py:393), or [R] (bg_kind 2: per-ray grey,
+ *               main.py:395-405)
+ *   z_vals_in   NULL, or [R,S] sorted depths to composite on (skips the placement passes)
+ * S = n_samples + n_importance.  The workspace keeps what the backward needs when the call
+ * fits one chunk; otherwise the backward recomputes per chunk from out->z_vals. */
+int avc_neus_render_fwd(const avc_neus_cfg* cfg, const float* params, const float* rays_o,
+                        const float* rays_d, const float* near, const float* far,
+                        const float* jitter, const float* background, int bg_kind,
+                        const float* z_vals_in, float cos_anneal_ratio, int64_t R,
+                        const avc_neus_outputs* out, void* workspace, size_t workspace_bytes,
+                        int64_t max_rays_per_chunk, avc_stream_t stream);
+
+typedef struct avc_neus_cotangents { /* d loss / d output; NULL = zero */
+  const float* color_fine;       /* [R,3]   */
+  const float* extra_color_fine; /* [R,3]   */
+  const float* s_val;            /* [R,1]   */
+  const float* cdf_fine;         /* [R,S]   */
+  const float* weight_sum;       /* [R,1]   */
+  const float* weight_max;       /* [R,1]   */
+  const float* gradients;        /* [R,S,3] */
+  const float* weights;          /* [R,S]   */
+  const float* gradient_error;   /* [1]     */
+} avc_neus_cotangents;
+
+/* Backward of avc_neus_render_fwd w.r.t. every parameter (the autograd graph the reference builds
+ * at models/fields.py:96-107 + main.py:537, second-order terms included).  Overwrites
+ * grad_params[n_params].  z_vals / weights etc. are the forward's outputs. */
+int avc_neus_render_bwd(const avc_neus_cfg* cfg, const float* params, const float* rays_o,
+                        const float* rays_d, const float* background, int bg_kind,
+                        float cos_anneal_ratio, int64_t R, const avc_neus_outputs* fwd_out,
+                        const avc_neus_cotangents* cot, float* grad_params, void* workspace,
+                        size_t workspace_bytes, int64_t max_rays_per_chunk, int32_t flags,
+                        avc_stream_t stream);
+/* flags for avc_neus_render_bwd: rebuild the forward stash from fwd_out->z_vals even for a
+ * single-chunk call (use when the workspace was reused by another call since the forward; the
+ * eikonal normaliser is then taken from fwd_out). */
+#define AVC_BWD_RECOMPUTE 1
+
+/* SDFNetwork.sdf on arbitrary points (models/fields.py:90-91; used by extract_fields,
+ * renderer.py:10-25): sdf_out[P]. */
+int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float* pts, int64_t P,
+                       float* sdf_out, void* workspace, size_t workspace_bytes,
+                       avc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused Adam over the flat parameter vector (torch.optim.Adam defaults, main.py:145,536-538):
+ * p -= lr * mhat / (sqrt(vhat) + eps); `step` is the 1-based step count; grad_scale multiplies g
+ * first (1/world_size after the gradient all-reduce).
+ * ------------------------------------------------------------------------------------------ */
+int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                  avc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVC_B200_H */
