@@ -1,0 +1,813 @@
+// avc_clip.cu -- CLIP ViT-B/32 image tower forward + input-gradient backward and the cosine loss.
+//
+// Replaces openai/CLIP's VisionTransformer as called from AvatarGen/AppearanceGen/main.py:509-526
+// (RandomResizedCrop(scale=(1,1)) == whole-image bilinear resize, Normalize, encode_image, cosine).
+// Weights are frozen (main.py:260): no weight gradients exist, so the backward only needs the
+// non-linearities' inputs (LayerNorm inputs, q/k/v, the c_fc pre-activation).
+//
+// Shapes: M = B*T token rows (T = 50), width 768.  Every GEMM here has M <= 128*k rows and streams its
+// fp16 weight matrix exactly once: they are weight-bandwidth bound, not FLOP bound, so the tiles are
+// small (64 x 32 per CTA), deep (3-stage cp.async) and split over K where N alone cannot fill the SMs.
+#include <cuda_fp16.h>
+
+#include "avc_common.cuh"
+
+using namespace avc;
+
+namespace {
+
+constexpr int kT = 50;   // tokens are derived from cfg at run time; kT only documents ViT-B/32
+
+// ------------------------------------------------------------------------------------------------
+// fp16 tensor-core GEMM  C[M,N] = A[M,K] . W[N,K]^T  (mma.sync m16n8k16, fp32 accumulate).
+// CTA: 128 threads, tile 64 x 32, BK = 64, 3-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
+// Epilogue functor: epi(row, col, v0, v1, ksplit_index) for two consecutive columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 32, GBK = 64, GST = 3, GPAD = 8;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <typename Epi>
+__global__ void __launch_bounds__(128)
+k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
+         int k_per_split, Epi epi) {
+  __shared__ __align__(16) __half sA[GST][GBM][GBK + GPAD];
+  __shared__ __align__(16) __half sW[GST][GBN][GBK + GPAD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM;
+  const int kb = blockIdx.z * k_per_split;
+  const int ke = min(K, kb + k_per_split);
+  const int nk = (ke - kb + GBK - 1) / GBK;
+
+  auto issue = [&](int kt, int st) {
+    const int k0 = kb + kt * GBK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {        // A: 64 rows x 8 chunks
+      int c = tid + i * 128;
+      int r = c >> 3, ch = c & 7;
+      bool ok = (m0 + r) < M;
+      const __half* src = A + (size_t)(ok ? (m0 + r) : 0) * lda + k0 + ch * 8;
+      cp_async16(&sA[st][r][ch * 8], src, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {        // W: 32 rows x 8 chunks
+      int c = tid + i * 128;
+      int r = c >> 3, ch = c & 7;
+      const __half* src = Wt + (size_t)(n0 + r) * ldw + k0 + ch * 8;
+      cp_async16(&sW[st][r][ch * 8], src, true);
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int s = 0; s < GST - 1; ++s) {
+    if (s < nk) issue(s, s);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GST - 2>();
+    __syncthreads();
+    if (kt + GST - 1 < nk) issue(kt + GST - 1, (kt + GST - 1) % GST);
+    cp_async_commit();
+    const int st = kt % GST;
+#pragma unroll
+    for (int kk = 0; kk < GBK; kk += 16) {
+      unsigned a[4];
+      {
+        unsigned addr = (unsigned)__cvta_generic_to_shared(&sA[st][warp * 16 + (lane & 15)][kk + (lane >> 4) * 8]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+      }
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {   // two pairs of n8 tiles
+        unsigned b[4];
+        unsigned addr = (unsigned)__cvta_generic_to_shared(
+            &sW[st][np * 16 + (lane & 7) + (lane >> 4) * 8][kk + ((lane >> 3) & 1) * 8]);
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float* c = acc[np * 2 + h];
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+              : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+              : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[h * 2]), "r"(b[h * 2 + 1]));
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+  const int r0 = m0 + warp * 16 + (lane >> 2);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    int col = n0 + t * 8 + (lane & 3) * 2;
+    if (r0 < M) epi(r0, col, acc[t][0], acc[t][1], (int)blockIdx.z);
+    if (r0 + 8 < M) epi(r0 + 8, col, acc[t][2], acc[t][3], (int)blockIdx.z);
+  }
+}
+
+template <typename Epi>
+int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw, int M, int N, int K, int ksplit,
+           const Epi& epi) {
+  if (N % GBN || K % GBK) return AVC_E_BADCFG;
+  int kper = (int)round_up(ceil_div(K, ksplit), GBK);
+  ksplit = ceil_div(K, kper);
+  dim3 grid(N / GBN, ceil_div(M, GBM), ksplit);
+  k_gemm16<Epi><<<grid, 128, 0, st>>>(A, lda, Wt, ldw, M, N, K, kper, epi);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+// ---- epilogues -----------------------------------------------------------------------------------
+struct EpiPatch {   // token row b*T + 1 + p  <-  acc + positional_embedding[1+p]
+  float* x; const float* pos; int T, Wd, np;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    int b = row / np, p = row - b * np;
+    size_t o = ((size_t)b * T + 1 + p) * Wd + col;
+    x[o] = v0 + pos[(size_t)(1 + p) * Wd + col];
+    x[o + 1] = v1 + pos[(size_t)(1 + p) * Wd + col + 1];
+  }
+};
+struct EpiBiasStore {   // out = acc + b
+  float* out; int ld; const float* bias;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    out[(size_t)row * ld + col] = v0 + bias[col];
+    out[(size_t)row * ld + col + 1] = v1 + bias[col + 1];
+  }
+};
+struct EpiResidual {    // x += acc (+ bias once): split-K partials meet in fp32 atomics
+  float* x; int ld; const float* bias;
+  __device__ void operator()(int row, int col, float v0, float v1, int ks) const {
+    if (ks == 0) { v0 += bias[col]; v1 += bias[col + 1]; }
+    atomicAdd(x + (size_t)row * ld + col, v0);
+    atomicAdd(x + (size_t)row * ld + col + 1, v1);
+  }
+};
+struct EpiFc {          // pre = acc + b ; g = QuickGELU(pre) = pre * sigmoid(1.702 pre)
+  float* pre; __half* g; int ld; const float* bias;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    float p0 = v0 + bias[col], p1 = v1 + bias[col + 1];
+    size_t o = (size_t)row * ld + col;
+    pre[o] = p0; pre[o + 1] = p1;
+    *reinterpret_cast<__half2*>(g + o) = __floats2half2_rn(p0 * sigmoidf_acc(1.702f * p0), p1 * sigmoidf_acc(1.702f * p1));
+  }
+};
+struct EpiDfc {         // (row-scaled) dpre = acc * QuickGELU'(pre) -> fp16 operand of the next GEMM
+  const float* pre; __half* out; int ld;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    size_t o = (size_t)row * ld + col;
+    float p0 = pre[o], p1 = pre[o + 1];
+    float s0 = sigmoidf_acc(1.702f * p0), s1 = sigmoidf_acc(1.702f * p1);
+    float d0 = v0 * (s0 + 1.702f * p0 * s0 * (1.f - s0));
+    float d1 = v1 * (s1 + 1.702f * p1 * s1 * (1.f - s1));
+    *reinterpret_cast<__half2*>(out + o) = __floats2half2_rn(d0, d1);
+  }
+};
+struct EpiAccumUnscale {  // dst += acc / rowscale   (split-K)
+  float* dst; int ld; const float* rowscale;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    float inv = 1.0f / rowscale[row];
+    atomicAdd(dst + (size_t)row * ld + col, v0 * inv);
+    atomicAdd(dst + (size_t)row * ld + col + 1, v1 * inv);
+  }
+};
+struct EpiStoreUnscale {  // dst = acc / rowscale
+  float* dst; int ld; const float* rowscale;
+  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+    float inv = 1.0f / rowscale[row];
+    dst[(size_t)row * ld + col] = v0 * inv;
+    dst[(size_t)row * ld + col + 1] = v1 * inv;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Pre-processing: bilinear resize (align_corners=False, no antialias) + Normalize, written directly as
+// the im2col operand of the patch-embedding GEMM: row b*np + patch, column c*p*p + (y%p)*p + (x%p).
+// ------------------------------------------------------------------------------------------------
+__constant__ float kMean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+__constant__ float kStd[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+
+struct ResizeTap { int i0, i1; float l; };
+__device__ __forceinline__ ResizeTap resize_tap(int dst, float scale, int in) {
+  float src = ((float)dst + 0.5f) * scale - 0.5f;    // area_pixel_compute_source_index, align_corners=False
+  if (src < 0.f) src = 0.f;
+  int i0 = (int)src;
+  if (i0 > in - 1) i0 = in - 1;
+  ResizeTap t;
+  t.i0 = i0; t.i1 = i0 + ((i0 < in - 1) ? 1 : 0); t.l = src - (float)i0;
+  return t;
+}
+
+__global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int B, int IS, int P,
+                             __half* __restrict__ a0, int mode) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)B * 3 * IS * IS;
+  if (i >= tot) return;
+  int x = (int)(i % IS); int64_t r = i / IS;
+  int y = (int)(r % IS); r /= IS;
+  int c = (int)(r % 3); int b = (int)(r / 3);
+  if (mode == 1) {     // already normalised NCHW image [B][3][IS][IS]: im2col only
+    int g1 = IS / P;
+    int patch1 = (y / P) * g1 + (x / P);
+    int col1 = c * P * P + (y % P) * P + (x % P);
+    a0[((size_t)b * g1 * g1 + patch1) * (3 * P * P) + col1] = __float2half_rn(canvas[i]);
+    return;
+  }
+  ResizeTap ty = resize_tap(y, (float)H / (float)IS, H), tx = resize_tap(x, (float)W / (float)IS, W);
+  const float* cv = canvas + (size_t)b * H * W * 3;
+  auto px = [&](int yy, int xx) { return cv[((size_t)yy * W + xx) * 3 + c]; };
+  float top = px(ty.i0, tx.i0) * (1.f - tx.l) + px(ty.i0, tx.i1) * tx.l;
+  float bot = px(ty.i1, tx.i0) * (1.f - tx.l) + px(ty.i1, tx.i1) * tx.l;
+  float v = (top * (1.f - ty.l) + bot * ty.l - kMean[c]) / kStd[c];
+  int g = IS / P;
+  int patch = (y / P) * g + (x / P);
+  int col = c * P * P + (y % P) * P + (x % P);
+  a0[((size_t)b * g * g + patch) * (3 * P * P) + col] = __float2half_rn(v);
+}
+
+// adjoint: d canvas += bilinear^T ( d img / std ), d img read from the im2col gradient
+__global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W, int B, int IS, int P,
+                                 float* __restrict__ dcanvas, int mode) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t tot = (int64_t)B * 3 * IS * IS;
+  if (i >= tot) return;
+  int x = (int)(i % IS); int64_t r = i / IS;
+  int y = (int)(r % IS); r /= IS;
+  int c = (int)(r % 3); int b = (int)(r / 3);
+  int g = IS / P;
+  int patch = (y / P) * g + (x / P);
+  int col = c * P * P + (y % P) * P + (x % P);
+  if (mode == 1) { dcanvas[i] = dpatch[((size_t)b * g * g + patch) * (3 * P * P) + col]; return; }
+  float gv = dpatch[((size_t)b * g * g + patch) * (3 * P * P) + col] / kStd[c];
+  ResizeTap ty = resize_tap(y, (float)H / (float)IS, H), tx = resize_tap(x, (float)W / (float)IS, W);
+  float* dc = dcanvas + (size_t)b * H * W * 3;
+  auto add = [&](int yy, int xx, float w) { atomicAdd(dc + ((size_t)yy * W + xx) * 3 + c, gv * w); };
+  add(ty.i0, tx.i0, (1.f - ty.l) * (1.f - tx.l));
+  add(ty.i0, tx.i1, (1.f - ty.l) * tx.l);
+  add(ty.i1, tx.i0, ty.l * (1.f - tx.l));
+  add(ty.i1, tx.i1, ty.l * tx.l);
+}
+
+__global__ void k_cls_rows(const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
+                           float* __restrict__ x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Wd) return;
+  int b = i / Wd, c = i - b * Wd;
+  x[(size_t)b * T * Wd + c] = cls[c] + pos[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (fp32 statistics, eps 1e-5): one warp per row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
+            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)row * Wd;
+  float s = 0.f;
+  for (int c = lane; c < Wd; c += 32) s += xr[c];
+  float mean = warp_sum(s) / (float)Wd;
+  float v = 0.f;
+  for (int c = lane; c < Wd; c += 32) { float d = xr[c] - mean; v += d * d; }
+  float rstd = rsqrtf(warp_sum(v) / (float)Wd + 1e-5f);
+  for (int c = lane; c < Wd; c += 32) {
+    float xv = xr[c];
+    float yv = (xv - mean) * rstd * g[c] + b[c];
+    if (y32) y32[(size_t)row * Wd + c] = yv;
+    if (y16) y16[(size_t)row * Wd + c] = __float2half_rn(yv);
+    if (save_x) save_x[(size_t)row * Wd + c] = xv;
+  }
+}
+
+// dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))
+__global__ void __launch_bounds__(256)
+k_layernorm_bwd(const float* __restrict__ x, const float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
+                float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (size_t)row * row_stride_x;
+  const float* dr = dy + (size_t)row * row_stride_dy;
+  float s = 0.f;
+  for (int c = lane; c < Wd; c += 32) s += xr[c];
+  float mean = warp_sum(s) / (float)Wd;
+  float v = 0.f;
+  for (int c = lane; c < Wd; c += 32) { float d = xr[c] - mean; v += d * d; }
+  float rstd = rsqrtf(warp_sum(v) / (float)Wd + 1e-5f);
+  float a = 0.f, bq = 0.f;
+  for (int c = lane; c < Wd; c += 32) {
+    float dg = dr[c] * g[c];
+    a += dg; bq += dg * (xr[c] - mean) * rstd;
+  }
+  a = warp_sum(a) / (float)Wd; bq = warp_sum(bq) / (float)Wd;
+  float* o = dx + (size_t)row * row_stride_dx;
+  for (int c = lane; c < Wd; c += 32) {
+    float xh = (xr[c] - mean) * rstd;
+    float r = rstd * (dr[c] * g[c] - a - xh * bq);
+    o[c] = accumulate ? o[c] + r : r;
+  }
+}
+
+// fp32 -> fp16 with a per-row power-of-two scale so that max|row| lands in [1,2): keeps tiny
+// gradients out of the fp16 subnormal range.  scale[row] is undone in the consuming GEMM's epilogue.
+__global__ void __launch_bounds__(256)
+k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __half* __restrict__ dst,
+                    float* __restrict__ scale, const int* __restrict__ row_map) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const float* s = src + (size_t)(row_map ? row_map[row] : row) * ld_src;
+  float mx = 0.f;
+  for (int c = lane; c < N; c += 32) mx = fmaxf(mx, fabsf(s[c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sc = 1.f;
+  if (mx > 0.f && isfinite(mx)) {
+    int e;
+    frexpf(mx, &e);               // mx = m * 2^e, m in [0.5, 1)
+    sc = ldexpf(1.f, 1 - e);      // mx * sc in [1, 2)
+  }
+  for (int c = lane; c < N; c += 32) dst[(size_t)row * N + c] = __float2half_rn(s[c] * sc);
+  if (lane == 0) scale[row] = sc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention, one CTA per (image, head): T <= 64 tokens, head dim 64.  fp32 throughout.
+// qkv: [M][3W] fp32 (q | k | v).  o16: [M][W] fp16 operand of out_proj.
+// ------------------------------------------------------------------------------------------------
+constexpr int AT = 64;   // max tokens
+constexpr int AD = 64;   // head dim
+
+__global__ void __launch_bounds__(128)
+k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
+  extern __shared__ float sm[];
+  float* q = sm;                  // [T][AD+1]
+  float* k = q + AT * (AD + 1);
+  float* v = k + AT * (AD + 1);
+  float* S = v + AT * (AD + 1);   // [T][AT+1]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const float* base = qkv + (size_t)b * T * 3 * Wd;
+  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
+    int t = i / AD, d = i % AD;
+    const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
+    q[t * (AD + 1) + d] = r[0]; k[t * (AD + 1) + d] = r[Wd]; v[t * (AD + 1) + d] = r[2 * Wd];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    int a = i / T, c = i % T;
+    float s = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < AD; ++d) s = fmaf(q[a * (AD + 1) + d], k[c * (AD + 1) + d], s);
+    S[a * (AT + 1) + c] = s * 0.125f;          // 1/sqrt(64)
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int a = warp; a < T; a += 4) {
+    float mx = -1e30f;
+    for (int c = lane; c < T; c += 32) mx = fmaxf(mx, S[a * (AT + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < T; c += 32) { float e = expf(S[a * (AT + 1) + c] - mx); S[a * (AT + 1) + c] = e; sum += e; }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int c = lane; c < T; c += 32) S[a * (AT + 1) + c] *= inv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
+    int a = i / AD, d = i % AD;
+    float o = 0.f;
+    for (int c = 0; c < T; ++c) o = fmaf(S[a * (AT + 1) + c], v[c * (AD + 1) + d], o);
+    o16[((size_t)b * T + a) * Wd + h * AD + d] = __float2half_rn(o);
+  }
+}
+
+// backward: recompute P; dqkv[M][3W] fp32 from dO[M][W] fp32
+__global__ void __launch_bounds__(128)
+k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
+                float* __restrict__ dqkv) {
+  extern __shared__ float sm[];
+  float* q = sm;
+  float* k = q + AT * (AD + 1);
+  float* v = k + AT * (AD + 1);
+  float* dO_s = v + AT * (AD + 1);
+  float* Pm = dO_s + AT * (AD + 1);     // [T][AT+1]
+  float* dS = Pm + AT * (AT + 1);
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const float* base = qkv + (size_t)b * T * 3 * Wd;
+  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
+    int t = i / AD, d = i % AD;
+    const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
+    q[t * (AD + 1) + d] = r[0]; k[t * (AD + 1) + d] = r[Wd]; v[t * (AD + 1) + d] = r[2 * Wd];
+    dO_s[t * (AD + 1) + d] = dO[((size_t)b * T + t) * Wd + h * AD + d];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    int a = i / T, c = i % T;
+    float s = 0.f, dp = 0.f;
+#pragma unroll 16
+    for (int d = 0; d < AD; ++d) {
+      s = fmaf(q[a * (AD + 1) + d], k[c * (AD + 1) + d], s);
+      dp = fmaf(dO_s[a * (AD + 1) + d], v[c * (AD + 1) + d], dp);
+    }
+    Pm[a * (AT + 1) + c] = s * 0.125f;
+    dS[a * (AT + 1) + c] = dp;               // dP for now
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int a = warp; a < T; a += 4) {
+    float mx = -1e30f;
+    for (int c = lane; c < T; c += 32) mx = fmaxf(mx, Pm[a * (AT + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < T; c += 32) { float e = expf(Pm[a * (AT + 1) + c] - mx); Pm[a * (AT + 1) + c] = e; sum += e; }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum, dot = 0.f;
+    for (int c = lane; c < T; c += 32) { float p = Pm[a * (AT + 1) + c] * inv; Pm[a * (AT + 1) + c] = p; dot += p * dS[a * (AT + 1) + c]; }
+    dot = warp_sum(dot);
+    for (int c = lane; c < T; c += 32) dS[a * (AT + 1) + c] = Pm[a * (AT + 1) + c] * (dS[a * (AT + 1) + c] - dot) * 0.125f;
+  }
+  __syncthreads();
+  float* dbase = dqkv + (size_t)b * T * 3 * Wd;
+  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
+    int t = i / AD, d = i % AD;
+    float dq = 0.f, dk = 0.f, dv = 0.f;
+    for (int c = 0; c < T; ++c) {
+      dq = fmaf(dS[t * (AT + 1) + c], k[c * (AD + 1) + d], dq);       // dQ[t] = sum_c dS[t][c] K[c]
+      dk = fmaf(dS[c * (AT + 1) + t], q[c * (AD + 1) + d], dk);       // dK[t] = sum_c dS[c][t] Q[c]
+      dv = fmaf(Pm[c * (AT + 1) + t], dO_s[c * (AD + 1) + d], dv);    // dV[t] = sum_c P[c][t] dO[c]
+    }
+    float* r = dbase + (size_t)t * 3 * Wd + h * AD + d;
+    r[0] = dq; r[Wd] = dk; r[2 * Wd] = dv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Head: ln_post(x[b,0]) @ proj -> emb ; cosine with the text embedding.  One CTA per image.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_head_fwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
+           const float* __restrict__ proj, int OD, const float* __restrict__ text, float* __restrict__ emb,
+           float* __restrict__ cos_out, float* __restrict__ ynorm) {
+  extern __shared__ float sm[];
+  float* y = sm;             // [Wd]
+  float* e = y + Wd;         // [OD]
+  __shared__ float red[3][8];
+  const int b = blockIdx.x;
+  const float* xr = x + (size_t)b * T * Wd;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < Wd; c += blockDim.x) s += xr[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int i = 0; i < 8; ++i) mean += red[0][i];
+  mean /= (float)Wd;
+  float v = 0.f;
+  for (int c = threadIdx.x; c < Wd; c += blockDim.x) { float d = xr[c] - mean; v += d * d; }
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = v;
+  __syncthreads();
+  float var = 0.f;
+  for (int i = 0; i < 8; ++i) var += red[0][i];
+  float rstd = rsqrtf(var / (float)Wd + 1e-5f);
+  for (int c = threadIdx.x; c < Wd; c += blockDim.x) {
+    float yy = (xr[c] - mean) * rstd * g[c] + bta[c];
+    y[c] = yy;
+    ynorm[(size_t)b * Wd + c] = yy;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+    float a = 0.f;
+    for (int c = 0; c < Wd; ++c) a = fmaf(y[c], proj[(size_t)c * OD + o], a);
+    e[o] = a;
+    emb[(size_t)b * OD + o] = a;
+  }
+  __syncthreads();
+  float ee = 0.f, tt = 0.f, et = 0.f;
+  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+    float a = e[o], t = text[(size_t)b * OD + o];
+    ee += a * a; tt += t * t; et += a * t;
+  }
+  ee = warp_sum(ee); tt = warp_sum(tt); et = warp_sum(et);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ee; red[1][threadIdx.x >> 5] = tt; red[2][threadIdx.x >> 5] = et; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, t = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; t += red[1][i]; c += red[2][i]; }
+    // torch.cosine_similarity: x.y / max(||x|| * ||y||, eps), eps = 1e-8
+    cos_out[b] = c / fmaxf(sqrtf(a) * sqrtf(t), 1e-8f);
+  }
+}
+
+// d cos / d emb -> through proj and ln_post -> dx rows (cls row gets the gradient, other rows zero)
+__global__ void __launch_bounds__(256)
+k_head_bwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ proj,
+           int OD, const float* __restrict__ text, const float* __restrict__ emb, const float* __restrict__ g_cos,
+           const float* __restrict__ g_emb, float* __restrict__ dx) {
+  extern __shared__ float sm[];
+  float* de = sm;            // [OD]
+  float* dy = de + OD;       // [Wd]
+  __shared__ float red[3][8];
+  const int b = blockIdx.x;
+  float ee = 0.f, tt = 0.f, et = 0.f;
+  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+    float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
+    ee += a * a; tt += t * t; et += a * t;
+  }
+  ee = warp_sum(ee); tt = warp_sum(tt); et = warp_sum(et);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ee; red[1][threadIdx.x >> 5] = tt; red[2][threadIdx.x >> 5] = et; }
+  __syncthreads();
+  float a2 = 0.f, t2 = 0.f, c = 0.f;
+  for (int i = 0; i < 8; ++i) { a2 += red[0][i]; t2 += red[1][i]; c += red[2][i]; }
+  float na = sqrtf(a2), nt = sqrtf(t2);
+  float gc = g_cos ? g_cos[b] : 0.f;
+  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+    float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
+    // d/d a [ a.t / (|a||t|) ] = t/(|a||t|) - (a.t) a / (|a|^3 |t|)
+    float d = (g_cos && na > 0.f && nt > 0.f) ? gc * (t / (na * nt) - c * a / (na * na * na * nt)) : 0.f;
+    if (g_emb) d += g_emb[(size_t)b * OD + o];
+    de[o] = d;
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+    float s = 0.f;
+    for (int o = 0; o < OD; ++o) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
+    dy[cc] = s;
+  }
+  __syncthreads();
+  // LayerNorm backward on the cls row
+  const float* xr = x + (size_t)b * T * Wd;
+  float s = 0.f;
+  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) s += xr[cc];
+  s = warp_sum(s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+  for (int i = 0; i < 8; ++i) mean += red[0][i];
+  mean /= (float)Wd;
+  float v = 0.f;
+  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) { float d = xr[cc] - mean; v += d * d; }
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = v;
+  __syncthreads();
+  float var = 0.f;
+  for (int i = 0; i < 8; ++i) var += red[0][i];
+  float rstd = rsqrtf(var / (float)Wd + 1e-5f);
+  float pa = 0.f, pb = 0.f;
+  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+    float dg = dy[cc] * g[cc];
+    pa += dg; pb += dg * (xr[cc] - mean) * rstd;
+  }
+  pa = warp_sum(pa); pb = warp_sum(pb);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[1][threadIdx.x >> 5] = pa; red[2][threadIdx.x >> 5] = pb; }
+  __syncthreads();
+  float A = 0.f, Bq = 0.f;
+  for (int i = 0; i < 8; ++i) { A += red[1][i]; Bq += red[2][i]; }
+  A /= (float)Wd; Bq /= (float)Wd;
+  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+    float xh = (xr[cc] - mean) * rstd;
+    dx[(size_t)b * T * Wd + cc] = rstd * (dy[cc] * g[cc] - A - xh * Bq);
+  }
+  for (int64_t i = threadIdx.x; i < (int64_t)(T - 1) * Wd; i += blockDim.x) dx[(size_t)b * T * Wd + Wd + i] = 0.f;
+}
+
+__global__ void k_patch_row_map(int B, int T, int* __restrict__ map) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int np = T - 1;
+  if (i >= B * np) return;
+  int b = i / np, p = i - b * np;
+  map[i] = b * T + 1 + p;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct ClipWs {
+  __half* a0;        // [B*np][3pp] im2col operand
+  float* x;          // [M][W] residual stream
+  float* tok_pre;    // [M][W] tokens before ln_pre
+  float* xs;         // [2*layers][M][W] LayerNorm inputs (ln_1, ln_2 per block)
+  float* x_final;    // [M][W]
+  __half* h16;       // [M][W]
+  float* qkv;        // [layers][M][3W]
+  __half* o16;       // [M][W]
+  float* fc_pre;     // [layers][M][mlp]
+  __half* g16;       // [M][mlp]
+  float* emb;        // [B][OD] (copy for the backward)
+  float* ynorm;      // [B][W]
+  // backward
+  float* dx;         // [M][W]
+  float* dtmp;       // [M][W]
+  float* dO;         // [M][W]
+  float* dqkv;       // [M][3W]
+  __half* d16a;      // [M][max(W,3W,mlp)]
+  __half* d16b;      // [M][mlp]
+  float* scale;      // [M]
+  float* dpatch;     // [B*np][3pp]
+  int* rowmap;       // [B*np]
+  size_t bytes;
+};
+
+int clip_dims(const avc_clip_cfg* c, int* T, int* np, int* pp3) {
+  if (!c) return AVC_E_NULL;
+  if (c->image_size <= 0 || c->patch <= 0 || c->image_size % c->patch) return AVC_E_BADCFG;
+  int g = c->image_size / c->patch;
+  *np = g * g; *T = *np + 1; *pp3 = 3 * c->patch * c->patch;
+  if (*T > AT) return AVC_E_BADCFG;
+  if (c->width % 64 || c->heads <= 0 || c->width / c->heads != AD || c->width % c->heads) return AVC_E_BADCFG;
+  if (c->mlp % 64 || *pp3 % 64 || c->layers < 1 || c->layers > AVC_CLIP_MAX_LAYERS || c->out_dim < 1) return AVC_E_BADCFG;
+  return 0;
+}
+
+void carve_clip(const avc_clip_cfg& c, int B, int T, int np, int pp3, void* base, ClipWs* w) {
+  Carver cv(base);
+  const int64_t M = (int64_t)B * T, Wd = c.width;
+  w->a0 = cv.take<__half>((int64_t)B * np * pp3);
+  w->x = cv.take<float>(M * Wd);
+  w->tok_pre = cv.take<float>(M * Wd);
+  w->xs = cv.take<float>((int64_t)2 * c.layers * M * Wd);
+  w->x_final = cv.take<float>(M * Wd);
+  w->h16 = cv.take<__half>(M * Wd);
+  w->qkv = cv.take<float>((int64_t)c.layers * M * 3 * Wd);
+  w->o16 = cv.take<__half>(M * Wd);
+  w->fc_pre = cv.take<float>((int64_t)c.layers * M * c.mlp);
+  w->g16 = cv.take<__half>(M * c.mlp);
+  w->emb = cv.take<float>((int64_t)B * c.out_dim);
+  w->ynorm = cv.take<float>((int64_t)B * Wd);
+  w->dx = cv.take<float>(M * Wd);
+  w->dtmp = cv.take<float>(M * Wd);
+  w->dO = cv.take<float>(M * Wd);
+  w->dqkv = cv.take<float>(M * 3 * Wd);
+  int64_t mx = c.mlp > 3 * Wd ? c.mlp : 3 * Wd;
+  w->d16a = cv.take<__half>(M * mx);
+  w->d16b = cv.take<__half>(M * mx);
+  w->scale = cv.take<float>(M);
+  w->dpatch = cv.take<float>((int64_t)B * np * pp3);
+  w->rowmap = cv.take<int>((int64_t)B * np);
+  w->bytes = cv.used();
+}
+
+int set_attn_smem(int fwd_bytes, int bwd_bytes) {
+  AVC_CUDA_TRY(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_bytes));
+  AVC_CUDA_TRY(cudaFuncSetAttribute(k_attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_bytes));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int avc_clip_workspace_bytes(const avc_clip_cfg* cfg, int32_t B, size_t* bytes) {
+  if (!cfg || !bytes) return AVC_E_NULL;
+  if (B < 1) return AVC_E_SIZE;
+  int T, np, pp3;
+  AVC_TRY(clip_dims(cfg, &T, &np, &pp3));
+  ClipWs w;
+  carve_clip(*cfg, B, T, np, pp3, nullptr, &w);
+  *bytes = w.bytes;
+  return 0;
+}
+
+int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const float* canvases, int32_t H,
+                      int32_t W, int32_t B, int32_t input_mode, const float* text_emb, float* emb_out,
+                      float* cos_out, void* workspace, size_t workspace_bytes, avc_stream_t stream) {
+  if (!cfg || !wt || !canvases || !text_emb || !emb_out || !cos_out || !workspace) return AVC_E_NULL;
+  if (B < 1 || H < 1 || W < 1) return AVC_E_SIZE;
+  if (input_mode != 0 && input_mode != 1) return AVC_E_BADCFG;
+  if (input_mode == 1 && (H != cfg->image_size || W != cfg->image_size)) return AVC_E_SIZE;
+  int T, np, pp3;
+  AVC_TRY(clip_dims(cfg, &T, &np, &pp3));
+  if (((uintptr_t)workspace & 15u)) return AVC_E_ALIGN;
+  ClipWs w;
+  carve_clip(*cfg, B, T, np, pp3, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Wd = cfg->width, M = B * T, IS = cfg->image_size;
+  const int attn_fwd_smem = (3 * AT * (AD + 1) + AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_bwd_smem = (4 * AT * (AD + 1) + 2 * AT * (AT + 1)) * (int)sizeof(float);
+  AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
+
+  int64_t npx = (int64_t)B * 3 * IS * IS;
+  k_preprocess<<<(int)((npx + 255) / 256), 256, 0, st>>>(canvases, H, W, B, IS, cfg->patch, w.a0, input_mode);
+  k_cls_rows<<<(B * Wd + 255) / 256, 256, 0, st>>>(wt->cls, wt->pos, B, T, Wd, w.tok_pre);
+  AVC_LAUNCH_TRY();
+  {
+    EpiPatch e{w.tok_pre, wt->pos, T, Wd, np};
+    AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 1, e));
+  }
+  k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr);
+  AVC_LAUNCH_TRY();
+  for (int l = 0; l < cfg->layers; ++l) {
+    const avc_clip_layer_weights& lw = wt->layer[l];
+    float* xs1 = w.xs + (size_t)(2 * l) * M * Wd;
+    float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
+    float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
+    float* fcp = w.fc_pre + (size_t)l * M * cfg->mlp;
+    k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1);
+    AVC_LAUNCH_TRY();
+    { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
+      AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e)); }
+    k_attention<<<B * cfg->heads, 128, attn_fwd_smem, st>>>(qkv, T, Wd, cfg->heads, w.o16);
+    AVC_LAUNCH_TRY();
+    { EpiResidual e{w.x, Wd, lw.b_out};
+      AVC_TRY(gemm16(st, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 2, e)); }
+    k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2);
+    AVC_LAUNCH_TRY();
+    { EpiFc e{fcp, w.g16, cfg->mlp, lw.b_fc};
+      AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_fc, Wd, M, cfg->mlp, Wd, 1, e)); }
+    { EpiResidual e{w.x, Wd, lw.b_proj};
+      AVC_TRY(gemm16(st, w.g16, cfg->mlp, (const __half*)lw.w_proj, cfg->mlp, M, Wd, cfg->mlp, 4, e)); }
+  }
+  AVC_CUDA_TRY(cudaMemcpyAsync(w.x_final, w.x, sizeof(float) * (size_t)M * Wd, cudaMemcpyDeviceToDevice, st));
+  k_head_fwd<<<B, 256, (Wd + cfg->out_dim) * sizeof(float), st>>>(w.x_final, T, Wd, wt->ln_post_g, wt->ln_post_b,
+                                                                 wt->proj, cfg->out_dim, text_emb, w.emb, cos_out,
+                                                                 w.ynorm);
+  AVC_LAUNCH_TRY();
+  AVC_CUDA_TRY(cudaMemcpyAsync(emb_out, w.emb, sizeof(float) * (size_t)B * cfg->out_dim, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32_t H, int32_t W, int32_t B,
+                      int32_t input_mode, const float* text_emb, const float* g_cos, const float* g_emb,
+                      float* d_canvases, void* workspace, size_t workspace_bytes, avc_stream_t stream) {
+  if (!cfg || !wt || !text_emb || !d_canvases || !workspace) return AVC_E_NULL;
+  if (!g_cos && !g_emb) return AVC_E_NULL;
+  if (B < 1 || H < 1 || W < 1) return AVC_E_SIZE;
+  if (input_mode != 0 && input_mode != 1) return AVC_E_BADCFG;
+  int T, np, pp3;
+  AVC_TRY(clip_dims(cfg, &T, &np, &pp3));
+  ClipWs w;
+  carve_clip(*cfg, B, T, np, pp3, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int Wd = cfg->width, M = B * T, IS = cfg->image_size, mlp = cfg->mlp;
+  const int attn_fwd_smem = (3 * AT * (AD + 1) + AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_bwd_smem = (4 * AT * (AD + 1) + 2 * AT * (AT + 1)) * (int)sizeof(float);
+  AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
+
+  k_head_bwd<<<B, 256, (Wd + cfg->out_dim) * sizeof(float), st>>>(w.x_final, T, Wd, wt->ln_post_g, wt->proj,
+                                                                 cfg->out_dim, text_emb, w.emb, g_cos, g_emb, w.dx);
+  AVC_LAUNCH_TRY();
+  for (int l = cfg->layers - 1; l >= 0; --l) {
+    const avc_clip_layer_weights& lw = wt->layer[l];
+    const float* xs1 = w.xs + (size_t)(2 * l) * M * Wd;
+    const float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
+    const float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
+    const float* fcp = w.fc_pre + (size_t)l * M * mlp;
+    // ---- MLP branch: x_out = x_mid + c_proj(QuickGELU(c_fc(ln_2(x_mid))))
+    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
+    AVC_LAUNCH_TRY();
+    { EpiDfc e{fcp, w.d16b, mlp};
+      AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_proj_t, Wd, M, mlp, Wd, 1, e)); }
+    AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
+    { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
+      AVC_TRY(gemm16(st, w.d16b, mlp, (const __half*)lw.w_fc_t, mlp, M, Wd, mlp, 4, e)); }
+    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd);
+    AVC_LAUNCH_TRY();
+    // ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
+    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
+    AVC_LAUNCH_TRY();
+    { EpiStoreUnscale e{w.dO, Wd, w.scale};
+      AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_out_t, Wd, M, Wd, Wd, 1, e)); }
+    k_attention_bwd<<<B * cfg->heads, 128, attn_bwd_smem, st>>>(qkv, w.dO, T, Wd, cfg->heads, w.dqkv);
+    AVC_LAUNCH_TRY();
+    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, nullptr);
+    AVC_LAUNCH_TRY();
+    AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
+    { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
+      AVC_TRY(gemm16(st, w.d16a, 3 * Wd, (const __half*)lw.w_qkv_t, 3 * Wd, M, Wd, 3 * Wd, 3, e)); }
+    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd);
+    AVC_LAUNCH_TRY();
+  }
+  // ln_pre, patch embedding, pre-processing
+  k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, w.dx, M, Wd, wt->ln_pre_g, w.dtmp, 0, Wd, Wd, Wd);
+  k_patch_row_map<<<ceil_div(B * np, 128), 128, 0, st>>>(B, T, w.rowmap);
+  k_to_half_rowscaled<<<ceil_div(B * np, 8), 256, 0, st>>>(w.dtmp, B * np, Wd, Wd, w.d16a, w.scale, w.rowmap);
+  AVC_LAUNCH_TRY();
+  { EpiStoreUnscale e{w.dpatch, pp3, w.scale};
+    AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)wt->w_patch_t, Wd, B * np, pp3, Wd, 1, e)); }
+  AVC_CUDA_TRY(cudaMemsetAsync(d_canvases, 0, sizeof(float) * (size_t)B * H * W * 3, st));
+  int64_t npx = (int64_t)B * 3 * IS * IS;
+  k_preprocess_bwd<<<(int)((npx + 255) / 256), 256, 0, st>>>(w.dpatch, H, W, B, IS, cfg->patch, d_canvases, input_mode);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+}  // extern "C"

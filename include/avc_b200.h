@@ -146,6 +146,65 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
                        float* sdf_out, void* workspace, size_t workspace_bytes,
                        avc_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * CLIP ViT-B/32 image tower + cosine loss (openai/CLIP `VisionTransformer`, un-vendored
+ * third-party dependency of the reference; call sites main.py:259-261 (load, frozen),
+ * :509-526 (resize -> normalise -> encode_image -> cosine against the cached text embedding)).
+ * Weights are frozen (main.py:260), so the backward is input-gradient only.
+ * GEMM operands are fp16 (clip.load keeps fp16 weights on CUDA), accumulation, the residual
+ * stream, LayerNorm and softmax are fp32.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct avc_clip_cfg {
+  int32_t image_size; /* 224 */
+  int32_t patch;      /* 32  */
+  int32_t width;      /* 768 */
+  int32_t layers;     /* 12  */
+  int32_t heads;      /* 12  */
+  int32_t mlp;        /* 3072 */
+  int32_t out_dim;    /* 512 */
+} avc_clip_cfg;
+
+typedef struct avc_clip_layer_weights { /* transformer.resblocks.{i}.* ; *_t = transposed copy */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void *w_qkv, *w_qkv_t;   /* fp16 [3W,W], [W,3W]  attn.in_proj_weight  */
+  const float* b_qkv;            /* [3W]                 attn.in_proj_bias    */
+  const void *w_out, *w_out_t;   /* fp16 [W,W]           attn.out_proj.weight */
+  const float* b_out;
+  const void *w_fc, *w_fc_t;     /* fp16 [mlp,W], [W,mlp]  mlp.c_fc.weight    */
+  const float* b_fc;
+  const void *w_proj, *w_proj_t; /* fp16 [W,mlp], [mlp,W]  mlp.c_proj.weight  */
+  const float* b_proj;
+} avc_clip_layer_weights;
+
+#define AVC_CLIP_MAX_LAYERS 24
+typedef struct avc_clip_weights {
+  const void *w_patch, *w_patch_t; /* fp16 [W, 3*patch*patch] (conv1.weight flattened), [3*p*p, W] */
+  const float *cls, *pos;          /* class_embedding [W], positional_embedding [T,W] */
+  const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  const float* proj;               /* fp32 [W, out_dim] */
+  avc_clip_layer_weights layer[AVC_CLIP_MAX_LAYERS];
+} avc_clip_weights;
+
+int avc_clip_workspace_bytes(const avc_clip_cfg* cfg, int32_t B, size_t* bytes);
+
+/* B canvases [B][H][W][3] (fp32, values in [0,1]; the reshape of main.py:510) -> whole-image bilinear
+ * resize to image_size^2 (align_corners=False, no antialias) -> Normalize(mean,std) (main.py:261)
+ * -> encode_image -> emb_out[B][out_dim]; cos_out[b] = cosine(emb_out[b], text_emb[b]) (main.py:513). */
+int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* w, const float* canvases,
+                      int32_t H, int32_t W, int32_t B, int32_t input_mode, const float* text_emb,
+                      float* emb_out, float* cos_out, void* workspace, size_t workspace_bytes,
+                      avc_stream_t stream);
+/* input_mode 0: canvases as above.  input_mode 1: `canvases` is an already resized + normalised NCHW
+ * image batch [B][3][image_size][image_size] (the argument of perceptor.encode_image, main.py:512);
+ * H = W = image_size.
+ * Backward: d loss / d input given g_cos[b] = d loss / d cos_out[b] and/or g_emb[b][out_dim] =
+ * d loss / d emb_out (either may be NULL); uses what the forward left in the workspace.  Overwrites
+ * d_canvases (same shape as the forward input). */
+int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* w, int32_t H, int32_t W, int32_t B,
+                      int32_t input_mode, const float* text_emb, const float* g_cos, const float* g_emb,
+                      float* d_canvases, void* workspace, size_t workspace_bytes, avc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over the flat parameter vector (torch.optim.Adam defaults, main.py:145,536-538):
  * p -= lr * mhat / (sqrt(vhat) + eps); `step` is the 1-based step count; grad_scale multiplies g
