@@ -85,15 +85,16 @@ class FlatParams:
         return [grad[o:o + m].view(p.shape) for p, o, m in self.slots]
 
 
-class _RenderFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, renderer, rays_o, rays_d, near, far, jitter, background, bg_kind, cos_anneal, z_in, *params):
-        L = _lib.lib()
-        fp: FlatParams = renderer._flat
-        cfg = fp.cfg
-        R = rays_o.shape[0]
-        S = cfg.n_samples + cfg.n_importance
-        dev = rays_o.device
+def render_forward_raw(renderer, rays_o, rays_d, near, far, jitter, background, bg_kind, cos_anneal, z_in,
+                       keep_ws: bool, out: Optional[Dict[str, torch.Tensor]] = None):
+    """One avc_neus_render_fwd call.  Returns (outputs dict incl. z_vals, workspace, chunk)."""
+    L = _lib.lib()
+    fp: FlatParams = renderer._flat
+    cfg = fp.cfg
+    R = rays_o.shape[0]
+    S = cfg.n_samples + cfg.n_importance
+    dev = rays_o.device
+    if out is None:
         f = dict(dtype=torch.float32, device=dev)
         out = {
             "color_fine": torch.empty(R, 3, **f), "extra_color_fine": torch.empty(R, 3, **f),
@@ -103,48 +104,65 @@ class _RenderFn(torch.autograd.Function):
             "mid_z_vals": torch.empty(R, S, **f), "gradient_error": torch.empty((), **f),
             "inside_sphere": torch.empty(R, S, **f), "z_vals": torch.empty(R, S, **f),
         }
-        chunk = min(R, renderer.max_rays_per_chunk)
-        ws = renderer._workspace(chunk, keep=any(p.requires_grad for p in params) and torch.is_grad_enabled())
-        o = NeusOutputs(**{k: v.data_ptr() for k, v in out.items()})
-        _lib.check(L.avc_neus_render_fwd(C.byref(cfg), _lib.ptr(fp.flat), _lib.ptr(rays_o), _lib.ptr(rays_d),
-                                         _lib.ptr(near), _lib.ptr(far), _lib.ptr(jitter), _lib.ptr(background),
-                                         bg_kind, _lib.ptr(z_in), float(cos_anneal), R, C.byref(o), _lib.ptr(ws),
-                                         ws.numel(), chunk, _lib.stream_ptr()), "avc_neus_render_fwd")
+    chunk = min(R, renderer.max_rays_per_chunk)
+    ws = renderer._workspace(chunk, keep=keep_ws)
+    o = NeusOutputs(**{k: out[k].data_ptr() for k in _lib._OUT_FIELDS})
+    _lib.check(L.avc_neus_render_fwd(C.byref(cfg), _lib.ptr(fp.flat), _lib.ptr(rays_o), _lib.ptr(rays_d),
+                                     _lib.ptr(near), _lib.ptr(far), _lib.ptr(jitter), _lib.ptr(background),
+                                     bg_kind, _lib.ptr(z_in), float(cos_anneal), R, C.byref(o), _lib.ptr(ws),
+                                     ws.numel(), chunk, _lib.stream_ptr()), "avc_neus_render_fwd")
+    return out, ws, chunk
+
+
+def render_backward_raw(renderer, rays_o, rays_d, background, bg_kind, cos_anneal, out, ws, chunk,
+                        cot: Dict[str, Optional[torch.Tensor]], grad: Optional[torch.Tensor] = None, flags: int = 0):
+    """One avc_neus_render_bwd call.  ``cot``: contiguous fp32 cotangents (missing / None = zero).
+    Returns the flat parameter gradient."""
+    L = _lib.lib()
+    fp: FlatParams = renderer._flat
+    c = NeusCotangents(**{k: (None if cot.get(k) is None else cot[k].data_ptr()) for k in _lib._COT_FIELDS})
+    o = NeusOutputs(**{k: out[k].data_ptr() for k in _lib._OUT_FIELDS})
+    if grad is None:
+        grad = torch.empty_like(fp.flat)
+    _lib.check(L.avc_neus_render_bwd(C.byref(fp.cfg), _lib.ptr(fp.flat), _lib.ptr(rays_o), _lib.ptr(rays_d),
+                                     _lib.ptr(background), bg_kind, float(cos_anneal), rays_o.shape[0], C.byref(o),
+                                     C.byref(c), _lib.ptr(grad), _lib.ptr(ws), ws.numel(), chunk, flags,
+                                     _lib.stream_ptr()), "avc_neus_render_bwd")
+    return grad
+
+
+class _RenderFn(torch.autograd.Function):
+    """Autograd seam.  ``hook`` is a dummy differentiable scalar that makes autograd call ``backward``; the
+    parameter gradients are handed to the modules' Parameters directly as views of ONE flat gradient vector
+    (accumulating into existing ``.grad`` like autograd would), so that neither 28 small copies nor 28
+    AccumulateGrad nodes are needed per step."""
+
+    @staticmethod
+    def forward(ctx, renderer, hook, rays_o, rays_d, near, far, jitter, background, bg_kind, cos_anneal, z_in):
+        need_grad = hook.requires_grad and torch.is_grad_enabled()
+        out, ws, chunk = render_forward_raw(renderer, rays_o, rays_d, near, far, jitter, background, bg_kind,
+                                            cos_anneal, z_in, keep_ws=need_grad)
         ctx.renderer, ctx.out, ctx.ws, ctx.chunk = renderer, out, ws, chunk
         ctx.rays = (rays_o, rays_d, background, bg_kind, float(cos_anneal))
-        ctx.flat_version = fp.flat._version
-        outs = tuple(out[k] for k in _OUT_KEYS) + (out["z_vals"],)
         ctx.mark_non_differentiable(out["mid_z_vals"], out["inside_sphere"], out["z_vals"])
-        return outs
+        return tuple(out[k] for k in _OUT_KEYS) + (out["z_vals"],)
 
     @staticmethod
     def backward(ctx, *gouts):
-        L = _lib.lib()
         renderer = ctx.renderer
         fp: FlatParams = renderer._flat
-        cfg = fp.cfg
         rays_o, rays_d, background, bg_kind, cos_anneal = ctx.rays
-        R = rays_o.shape[0]
-        g = dict(zip(_OUT_KEYS, gouts[:len(_OUT_KEYS)]))
-        keep = []
-
-        def cp(k):
-            t = g.get(k)
-            if t is None:
-                return None
-            t = t.contiguous().float()
-            keep.append(t)
-            return t.data_ptr()
-
-        cot = NeusCotangents(**{k: cp(k) for k in _lib._COT_FIELDS})
-        o = NeusOutputs(**{k: v.data_ptr() for k, v in ctx.out.items()})
-        grad = torch.empty_like(fp.flat)
-        _lib.check(L.avc_neus_render_bwd(C.byref(cfg), _lib.ptr(fp.flat), _lib.ptr(rays_o), _lib.ptr(rays_d),
-                                         _lib.ptr(background), bg_kind, cos_anneal, R, C.byref(o), C.byref(cot),
-                                         _lib.ptr(grad), _lib.ptr(ctx.ws), ctx.ws.numel(), ctx.chunk, 0,
-                                         _lib.stream_ptr()), "avc_neus_render_bwd")
+        cot = {}
+        for k, t in zip(_OUT_KEYS, gouts[:len(_OUT_KEYS)]):
+            if k in _lib._COT_FIELDS and t is not None:
+                cot[k] = t.contiguous().float()
+        grad = render_backward_raw(renderer, rays_o, rays_d, background, bg_kind, cos_anneal, ctx.out, ctx.ws,
+                                   ctx.chunk, cot)
         renderer.last_flat_grad = grad
-        return (None,) * 10 + tuple(fp.grad_views(grad))
+        for p, view in zip(fp.params(), fp.grad_views(grad)):
+            if p.requires_grad:
+                p.grad = view if p.grad is None else p.grad + view
+        return (None,) * 11
 
 
 class NeuSRenderer:
@@ -173,6 +191,7 @@ class NeuSRenderer:
             n_samples=self.n_samples, n_importance=self.n_importance, up_sample_steps=self.up_sample_steps,
             engine=int(engine))
         self._flat: Optional[FlatParams] = None
+        self._hook = torch.zeros((), requires_grad=True)
         self._ws_cache: Dict[int, torch.Tensor] = {}
         self.last_flat_grad: Optional[torch.Tensor] = None
         sdf_network._avc_binding = self
@@ -184,6 +203,10 @@ class NeuSRenderer:
         elif not self._flat.is_homed():
             self._flat.rehome()
         return self._flat
+
+    def _make_hook(self, dev):
+        self._hook = torch.zeros((), device=dev, requires_grad=True)
+        return self._hook
 
     def flat_params(self, device=None) -> FlatParams:
         if device is None:
@@ -244,8 +267,9 @@ class NeuSRenderer:
             else:
                 raise ValueError("background_rgb must be [1,3] or [R,1] (main.py:393-405)")
         z_in = self._prep(z_vals, (R, self.n_samples + self.n_importance)) if z_vals is not None else None
-        outs = _RenderFn.apply(self, rays_o, rays_d, near_t, far_t, jit, bg, bg_kind, float(cos_anneal_ratio), z_in,
-                               *fp.params())
+        hook = self._hook if self._hook.device == dev else self._make_hook(dev)
+        hook.requires_grad_(any(p.requires_grad for p in fp.params()))
+        outs = _RenderFn.apply(self, hook, rays_o, rays_d, near_t, far_t, jit, bg, bg_kind, float(cos_anneal_ratio), z_in)
         ret = dict(zip(_OUT_KEYS, outs[:len(_OUT_KEYS)]))
         ret["z_vals"] = outs[-1]
         return ret

@@ -1,0 +1,122 @@
+"""The appearance-optimisation train step of ``Runner.train_clip`` (AvatarGen/AppearanceGen/main.py:345-566)
+as a fused sequence of C-ABI calls -- no autograd graph, no eager PyTorch arithmetic on the hot path:
+
+    H2D(view) -> avc_neus_render_fwd -> avc_loss_stage_fwd -> avc_clip_loss_fwd (texture + shading canvases, B=2)
+             -> avc_clip_loss_bwd -> avc_loss_stage_bwd -> avc_neus_render_bwd
+             -> [all-reduce of the flat gradient over view-sharded ranks] -> avc_adam_step
+
+Multi-GPU: independent camera views shard one per rank; the only collective is one all-reduce(sum)
+of the flat fp32 gradient per step, scaled by 1/world inside the fused Adam.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib, losses
+from .renderer import NeuSRenderer, render_backward_raw, render_forward_raw
+from .workload import HostView
+
+
+class DeviceView:
+    """Device-resident copy of a HostView; ``upload`` refreshes it from (pinned) host memory."""
+
+    def __init__(self, hv: HostView, device):
+        self.device = torch.device(device)
+        self.H, self.W = hv.H, hv.W
+        mk = lambda t: None if t is None else torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        self.rays_o, self.rays_d = mk(hv.rays_o), mk(hv.rays_d)
+        self.near, self.far, self.jitter = mk(hv.near), mk(hv.far), mk(hv.jitter)
+        self.pix, self.in_mask = mk(hv.pix), mk(hv.in_mask)
+        self.true_rgb, self.mask = mk(hv.true_rgb), mk(hv.mask)
+        self.ray_background, self.canvas_background = mk(hv.ray_background), mk(hv.canvas_background)
+        self.upload(hv)
+
+    def upload(self, hv: HostView):
+        for name in ("rays_o", "rays_d", "near", "far", "jitter", "pix", "in_mask", "true_rgb", "mask",
+                     "ray_background", "canvas_background"):
+            src, dst = getattr(hv, name), getattr(self, name)
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self.bg_choice, self.light_dir, self.ambience = hv.bg_choice, hv.light_dir, hv.ambience
+
+
+class AppearanceTrainer:
+    def __init__(self, renderer: NeuSRenderer, clip_tower, text_emb: torch.Tensor, lr: float = 5e-4,
+                 igr_weight: float = 0.1, mask_weight: float = 0.5, clip_weight: float = 1.0,
+                 betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, device="cuda"):
+        self.renderer, self.clip = renderer, clip_tower
+        self.device = torch.device(device)
+        self.fp = renderer.flat_params(self.device)
+        self.exp_avg = torch.zeros_like(self.fp.flat)
+        self.exp_avg_sq = torch.zeros_like(self.fp.flat)
+        self.grad = torch.zeros_like(self.fp.flat)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.igr_weight, self.mask_weight, self.clip_weight = igr_weight, mask_weight, clip_weight
+        self.text = text_emb.detach().float().reshape(-1, clip_tower.cfg.out_dim).to(self.device)
+        if self.text.shape[0] == 1:
+            self.text = self.text.expand(2, -1)
+        self.text = self.text.contiguous()          # [2, 512]: texture prompt, no-texture prompt (main.py:500-508)
+        self.g_cos = torch.full((2,), -clip_weight, dtype=torch.float32, device=self.device)   # d(1-cos)*w / d cos
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.iter_step = 0
+        self._out = None
+        self._clip_ws = None
+        self.cos = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.emb = torch.zeros(2, clip_tower.cfg.out_dim, dtype=torch.float32, device=self.device)
+        self.scalars = None
+        self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self, dv: DeviceView, cos_anneal: float = 1.0) -> torch.Tensor:
+        """Everything up to (and including) the flat gradient; returns self.grad."""
+        L = _lib.lib()
+        r = self.renderer
+        bg = dv.ray_background if dv.bg_choice in (1, 2) else (torch.ones(3, device=self.device) if dv.bg_choice == 0 else None)
+        bg_kind = 2 if dv.bg_choice in (1, 2) else (1 if dv.bg_choice == 0 else 0)
+        jit = dv.jitter if r.perturb > 0 else None
+        out, ws, chunk = render_forward_raw(r, dv.rays_o, dv.rays_d, dv.near, dv.far, jit, bg, bg_kind, cos_anneal,
+                                            None, keep_ws=False, out=self._out)
+        self._out = out
+        si = losses.StepInputs(dv.pix, dv.in_mask, dv.true_rgb, dv.mask, dv.H, dv.W, dv.light_dir, dv.ambience,
+                               dv.bg_choice, dv.canvas_background, self.igr_weight, self.mask_weight, self.clip_weight)
+        canv, scal = losses.stage_forward(out, si)
+        self.scalars = scal
+        # CLIP on both canvases at once (main.py:509-526): B = 2
+        tower = self.clip
+        if self._clip_ws is None:
+            self._clip_ws = tower._workspace(2)
+        cws = self._clip_ws
+        _lib.check(L.avc_clip_loss_fwd(C.byref(tower.cfg), C.byref(tower.w), _lib.ptr(canv), dv.H, dv.W, 2, 0,
+                                       _lib.ptr(self.text), _lib.ptr(self.emb), _lib.ptr(self.cos), _lib.ptr(cws),
+                                       cws.numel(), _lib.stream_ptr()), "avc_clip_loss_fwd")
+        d_canv = torch.empty_like(canv)
+        _lib.check(L.avc_clip_loss_bwd(C.byref(tower.cfg), C.byref(tower.w), dv.H, dv.W, 2, 0, _lib.ptr(self.text),
+                                       _lib.ptr(self.g_cos), None, _lib.ptr(d_canv), _lib.ptr(cws), cws.numel(),
+                                       _lib.stream_ptr()), "avc_clip_loss_bwd")
+        cot = losses.stage_backward(out, si, d_canv, scal)
+        render_backward_raw(r, dv.rays_o, dv.rays_d, bg, bg_kind, cos_anneal, out, ws, chunk, cot, grad=self.grad)
+        return self.grad
+
+    def loss_value(self) -> torch.Tensor:
+        """Total loss of main.py:528-534 as a device scalar (one tiny kernel; read it with .item() to sync)."""
+        return self.scalars[losses.S_BASE] + ((1.0 - self.cos) * self.clip_weight).sum()
+
+    def optimizer_step(self, lr: Optional[float] = None):
+        if self.pg is not None and self.world > 1:
+            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        self.iter_step += 1
+        b1, b2 = self.betas
+        _lib.check(_lib.lib().avc_adam_step(_lib.ptr(self.fp.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),
+                                            _lib.ptr(self.exp_avg_sq), self.fp.n, float(self.lr if lr is None else lr),
+                                            b1, b2, self.eps, self.iter_step, 1.0 / self.world, _lib.stream_ptr()),
+                   "avc_adam_step")
+
+    def step(self, dv: DeviceView, lr: Optional[float] = None, cos_anneal: float = 1.0) -> torch.Tensor:
+        self.forward_backward(dv, cos_anneal)
+        self.optimizer_step(lr)
+        return self.loss_value()

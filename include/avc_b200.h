@@ -206,6 +206,45 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* w, int32_
                       float* d_canvases, void* workspace, size_t workspace_bytes, avc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Shading + canvas scatter + non-CLIP losses of Runner.train_clip (main.py:417-497, 528-534) with
+ * use_silhouettes / add_no_texture / texture_cast_light = True (every shipped train_clip conf).
+ * Rays are the True pixels of the dilated mask; pix[r] is the flat canvas index (y*W + x) of ray r.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct avc_loss_inputs {
+  /* render outputs (NeuSRenderer.render dict) */
+  const float* color_fine;       /* [R,3] */
+  const float* extra_color_fine; /* [R,3] */
+  const float* gradients;        /* [R,S,3] */
+  const float* weights;          /* [R,S] */
+  const float* weight_sum;       /* [R] */
+  const float* gradient_error;   /* [1] */
+  /* per step */
+  const int32_t* pix;            /* [R] canvas index of each ray */
+  const uint8_t* in_mask;        /* [H*W] 1 where a ray exists (the dilated mask, dataset.py:255-256) */
+  const float* true_rgb;         /* [H*W,3] template render resized to the canvas (main.py:376) */
+  const float* mask;             /* [H*W] 0/1 (main.py:377-380, 407-410) */
+  const float* background;       /* NULL, or [H*W] grey levels for bg_choice 1/2 (main.py:394-405) */
+  int32_t bg_choice;             /* 0 white, 1/2 per-pixel grey, 3 black (main.py:387-415) */
+  float light_dir[3];            /* sphere_coord(theta+U, phi+U) of main.py:433 (un-normalised) */
+  float ambience;                /* main.py:440 */
+  float igr_weight, mask_weight, clip_weight;  /* conf train.* */
+  int32_t R, S, H, W;
+} avc_loss_inputs;
+
+/* scalars written by the forward: [0] color_loss, [1] eikonal, [2] mask_loss (BCE), [3] psnr,
+ * [4] base_loss = color + igr*eik + mask_w*bce, [5..7] internal sums (l1, bce, sq), [8] mask_sum */
+#define AVC_LOSS_SCALARS 16
+/* Forward: fills canvases[2][H][W][3] (0: texture_shading, 1: rand_shading_rgb; main.py:466-473)
+ * and scalars[AVC_LOSS_SCALARS]. */
+int avc_loss_stage_fwd(const avc_loss_inputs* in, float* canvases, float* scalars, avc_stream_t stream);
+/* Backward: d_canvases[2][H][W][3] = d loss / d canvases (from the CLIP backward) plus the direct
+ * loss terms -> cotangents of the render outputs (struct avc_neus_cotangents, written in full:
+ * color_fine, extra_color_fine, gradients, weights, weight_sum, gradient_error must be non-NULL
+ * writable buffers; s_val, cdf_fine, weight_max are ignored). */
+int avc_loss_stage_bwd(const avc_loss_inputs* in, const float* d_canvases, const float* scalars,
+                       const avc_neus_cotangents* cot_out, avc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused Adam over the flat parameter vector (torch.optim.Adam defaults, main.py:145,536-538):
  * p -= lr * mhat / (sqrt(vhat) + eps); `step` is the 1-based step count; grad_scale multiplies g
  * first (1/world_size after the gradient all-reduce).

@@ -1,0 +1,70 @@
+"""Fused train step (render -> shading/losses -> CLIP x2 -> backward -> Adam) against the CPU oracle step."""
+import numpy as np
+import pytest
+import torch
+
+import util_neus as U
+from oracle import clip_vit as cv
+from oracle.train_step import OracleTrainer
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case, n_rays, H, bg_choice, seed=0):
+    from avatarclip_b200.clip_vit import ClipImageTower
+    from avatarclip_b200.trainer import AppearanceTrainer, DeviceView
+    from avatarclip_b200.workload import make_view
+    sdf_kw, col_kw, ren_kw, _ = U.CASES[case]
+    sconf, cconf, rconf = U.confs_from_kw(sdf_kw, col_kw, ren_kw)
+    sp, cp = U.synth_state(sdf_kw, col_kw, seed)
+    clip_sd = cv.random_vit_state(seed=seed)
+    text = torch.randn(2, 512, generator=torch.Generator().manual_seed(seed + 5))
+    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda")
+    tower = ClipImageTower(clip_sd, device="cuda")
+    tr = AppearanceTrainer(ren, tower, text, lr=5e-4)
+    orc = OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text, lr=5e-4)
+    hv = make_view(3, n_rays=n_rays, H=H, W=H, seed=seed, bg_choice=bg_choice)
+    return tr, orc, hv, DeviceView(hv, "cuda"), (sdf, col, var)
+
+
+@pytest.mark.parametrize("case,n_rays,H,bg", [("tiny", 120, 64, 3), ("shipped", 96, 80, 1), ("tiny", 150, 72, 0)])
+def test_fused_step_matches_oracle(case, n_rays, H, bg):
+    tr, orc, hv, dv, mods = _setup(case, n_rays, H, bg)
+    # ---- loss and gradient
+    grad = tr.forward_backward(dv).clone()
+    loss_p = tr.loss_value().item()
+    total, aux = orc.loss(hv)
+    gs = torch.autograd.grad(total, [v for _, v in orc.named_params()], allow_unused=True)
+    loss_o = total.item()
+    print(f"loss product {loss_p:.6f} oracle {loss_o:.6f}; cos product {tr.cos.tolist()} oracle {aux['cos'].tolist()}")
+    assert abs(loss_p - loss_o) / abs(loss_o) < 1e-3
+    views = dict(zip([n for n, _ in [("sdf." + k, v) for k, v in mods[0].named_parameters()]
+                      + [("col." + k, v) for k, v in mods[1].named_parameters()]
+                      + [("var." + k, v) for k, v in mods[2].named_parameters()]], [None] * 999))
+    fp = tr.fp
+    named = {}
+    for (p, o, m) in fp.slots:
+        for pre, mod in (("sdf.", mods[0]), ("col.", mods[1]), ("var.", mods[2])):
+            for k, q in mod.named_parameters():
+                if q is p:
+                    named[pre + k] = grad[o:o + m].view(p.shape).cpu()
+    worst = 0.0
+    gnorm_o = torch.cat([g.reshape(-1) for g in gs if g is not None]).norm().item()
+    diff2 = 0.0
+    for (k, v), g in zip(orc.named_params(), gs):
+        g = torch.zeros_like(v) if g is None else g
+        diff2 += (named[k] - g).double().pow(2).sum().item()
+        worst = max(worst, U.rel_to_max(named[k], g))
+    rel_l2 = diff2 ** 0.5 / gnorm_o
+    print(f"flat-gradient rel-L2 err {rel_l2:.3e}; worst per-tensor rel-to-max {worst:.3e}")
+    assert rel_l2 < 2e-2
+    # ---- one optimiser step: parameters move identically (Adam normalises, so compare the update direction)
+    before = {k: v.detach().clone() for k, v in orc.named_params()}
+    flat_before = tr.fp.flat.clone()
+    tr.optimizer_step()
+    orc.opt.zero_grad()
+    total.backward()
+    orc.opt.step()
+    upd_p = (tr.fp.flat - flat_before)
+    assert torch.isfinite(upd_p).all()
+    assert abs(upd_p.abs().max().item() - 5e-4) < 1e-5     # first Adam step moves every coordinate by ~lr
