@@ -1,0 +1,314 @@
+// avc_gemm_tc.cuh -- tcgen05 (5th-gen tensor core) GEMM tiles for sm_100a with TMA-fed operands and
+// TMEM accumulators; engine 1 of the NeuS MLP contractions.
+//
+// Precision: the NeuS SDF trunk cannot run on single-pass 16-bit tensor-core math (SURVEY.md Appendix C:
+// inv_s ~ 500 amplifies SDF error; bf16 gives 2.6e-2 RGB error, TF32 3e-3).  Operands are therefore kept as
+// TWO-TERM bf16 splits  x = hi + lo  (hi = bf16(x), lo = bf16(x - hi), ~16 mantissa bits) and every product is
+// three MMAs  hi*hi + hi*lo + lo*hi  accumulated in fp32 in TMEM (the dropped lo*lo term is ~2^-16 relative).
+//
+//   gemm_tc_nt : C[m,n] = sum_k A[m,k] B[n,k]     A:[M,lda] B:[N,ldb], both K-contiguous (K-major operands)
+//   gemm_tc_tn : C[i,j] += sum_p A[p,i] B[p,j]    reduction over rows (weight gradients; MN-major operands)
+//
+// Kernel shape (both): 192 threads = warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer,
+// warps 2-5 epilogue (TMEM lane quarter = warp_id % 4).  Tile 128 x BN, K step 64 (one 128-byte swizzle atom),
+// multi-stage shared-memory ring with full/empty mbarriers, accumulator hand-off through tcgen05.commit.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "avc_common.cuh"
+
+namespace avc {
+namespace tc {
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must trap (CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 / fp16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+// | layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, a_major @15, b_major @16
+// (0 = K-major, 1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] with row pitch ld (elements); box = box_cols x box_rows, 128-byte swizzle.
+static inline int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return AVC_E_BADCFG;
+  if (((uintptr_t)base & 15u) || (ld * 2) % 16) return AVC_E_ALIGN;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : AVC_E_BADCFG;
+}
+
+struct SplitPtr {            // two-term bf16 split of an fp32 matrix, both [rows][ld]
+  const __nv_bfloat16* hi;
+  const __nv_bfloat16* lo;
+  int ld;
+};
+
+constexpr int kBM = 128, kBK = 64;
+constexpr int kTcThreads = 192;
+
+template <int BN, int NPROD>
+struct TcCfg {
+  static constexpr int A_BYTES = kBM * kBK * 2;                    // one (hi or lo) A slab: 16 KB
+  static constexpr int B_BYTES = BN * kBK * 2;
+  static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
+  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "tile too large for shared memory");
+};
+
+// ------------------------------------------------------------------------------------------------ NT kernel
+// Epilogue: epi(row, col, float4) for col % 4 == 0, row < M, col < N.
+template <int BN, int NPROD, typename Epi>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                  const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                  int M, int N, int K, Epi epi) {
+  using Cfg = TcCfg<BN, NPROD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int nk = (K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
+    if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        mbar_wait(empty0 + 8 * s, ((kb / Cfg::STAGES) & 1) ^ 1);
+        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+        tma_load_2d(st, &mapAhi, kb * kBK, m0, full0 + 8 * s);
+        tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES, &mapBhi, kb * kBK, n0, full0 + 8 * s);
+        if (NPROD == 3) {
+          tma_load_2d(st + Cfg::A_BYTES, &mapAlo, kb * kBK, m0, full0 + 8 * s);
+          tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, full0 + 8 * s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < kBK / 16; ++k4) {
+          // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B
+          const uint64_t dah = make_smem_desc(a_hi + k4 * 32, 0, 1024);
+          const uint64_t dbh = make_smem_desc(b_hi + k4 * 32, 0, 1024);
+          umma_f16(tmem_base, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+          if (NPROD == 3) {
+            const uint64_t dal = make_smem_desc(a_lo + k4 * 32, 0, 1024);
+            const uint64_t dbl = make_smem_desc(b_lo + k4 * 32, 0, 1024);
+            umma_f16(tmem_base, dah, dbl, idesc, 1u);
+            umma_f16(tmem_base, dal, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(empty0 + 8 * s);      // frees this smem stage once the MMAs above have read it
+      }
+      umma_commit(tfull);                 // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      if (row < M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          int col = n0 + c * 32 + j * 4;
+          if (col < N)
+            epi(row, col, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int NPROD, typename Epi>
+static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
+                                       const Epi& epi) {
+  using Cfg = TcCfg<BN, NPROD>;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  AVC_TRY(make_map_bf16(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
+  AVC_TRY(make_map_bf16(&mBh, B.hi, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
+  if (NPROD == 3) {
+    AVC_TRY(make_map_bf16(&mAl, A.lo, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
+    AVC_TRY(make_map_bf16(&mBl, B.lo, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
+  } else {
+    mAl = mAh; mBl = mBh;
+  }
+  auto kern = gemm_tc_nt_kernel<BN, NPROD, Epi>;
+  static bool attr_set = false;    // per template instantiation
+  if (!attr_set) {
+    AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(M, kBM), ceil_div(N, BN));
+  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+// N <= 64 -> BN 64, N <= 128 -> BN 128, else BN 256 (tiles in y)
+template <int NPROD, typename Epi>
+static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
+                                    const Epi& epi) {
+  if (M <= 0 || N <= 0) return 0;
+  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, Epi>(st, M, N, K, A, B, epi);
+  if (N <= 128) return launch_gemm_tc_nt_bn<128, NPROD, Epi>(st, M, N, K, A, B, epi);
+  return launch_gemm_tc_nt_bn<256, NPROD, Epi>(st, M, N, K, A, B, epi);
+}
+
+// ------------------------------------------------------------------------------------------------ split helper
+// fp32 [rows][ld_src] -> bf16 hi/lo [rows][ld_dst] (columns >= cols zero-filled up to ld_dst)
+__global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int cols, int ld_src,
+                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ld_dst) return;
+  int64_t r = i / ld_dst;
+  int c = (int)(i - r * ld_dst);
+  float v = c < cols ? src[(size_t)r * ld_src + c] : 0.f;
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+}  // namespace tc
+}  // namespace avc

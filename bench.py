@@ -49,6 +49,19 @@ def algorithmic_flops_per_step():
     return mlp, clip
 
 
+def host_cores() -> int:
+    """Usable host cores: the cgroup CPU quota when there is one (the GPU boxes expose 128 logical CPUs but
+    grant a 16-CPU quota; 128 threads then run ~50x slower than 16), else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return n
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -302,7 +315,7 @@ def cpu_baseline(sp, cp, clip_sd, text, view, sample_rays=128):
     """Oracle ('port') step timed on this box's host cores.  The render part runs on `sample_rays` of the 512 rays
     and is scaled linearly; CLIP + loss stage + Adam run in full."""
     import oracle.neus as on
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     orc = oracle_trainer(sp, cp, clip_sd, text)
     v = subsample_view(view, sample_rays)
     # time the render forward alone to split fwd_all
@@ -339,7 +352,7 @@ def run_reference(args):
     import util_neus as U
     from oracle import clip_vit as cv
     from avatarclip_b200.workload import make_view
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     sp, cp = U.synth_state(SDF_KW, COL_KW, seed=0)
     clip_sd = cv.random_vit_state(seed=0)
     text = torch.randn(2, 512, generator=torch.Generator().manual_seed(5))

@@ -253,6 +253,14 @@ int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                   avc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Self-test of the tcgen05 GEMM tiles (engine 1): C[M][N] = A[M][K] . B[N][K]^T, fp32 in/out, operands
+ * split into bf16 (hi, lo) pairs; nprod = 1 (hi*hi only) or 3 (hi*hi + hi*lo + lo*hi).
+ * workspace >= 4 * (M + N) * round_up(K, 8) + 1024 bytes.
+ * ------------------------------------------------------------------------------------------ */
+int avc_tc_gemm_nt_test(const float* A, const float* B, int64_t M, int32_t N, int32_t K, int32_t nprod,
+                        float* C, void* workspace, size_t workspace_bytes, avc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

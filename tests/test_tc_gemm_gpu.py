@@ -1,0 +1,41 @@
+"""tcgen05 GEMM tiles (engine 1) against an fp64 matmul: single bf16 product and the two-term split."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(M, N, K, nprod, seed=0):
+    from avatarclip_b200 import _lib
+    L = _lib.lib()
+    L.avc_tc_gemm_nt_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    L.avc_tc_gemm_nt_test.restype = C.c_int
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(M, K, generator=g).cuda()
+    B = (torch.randn(N, K, generator=g) * 0.1).cuda()
+    Cm = torch.full((M, N), float("nan"), device="cuda")
+    ws = torch.empty(4 * (M + N) * ((K + 7) // 8 * 8) + 8192, dtype=torch.uint8, device="cuda")
+    _lib.check(L.avc_tc_gemm_nt_test(A.data_ptr(), B.data_ptr(), M, N, K, nprod, Cm.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _lib.stream_ptr()), "avc_tc_gemm_nt_test")
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().t())
+    err = (Cm.double() - ref).abs().max().item() / ref.abs().max().item()
+    return err
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 256, 256), (1000, 217, 256), (300, 39, 256), (4096, 256, 40),
+                                   (513, 128, 320)])
+def test_tc_gemm_split3(M, N, K):
+    err = _run(M, N, K, 3)
+    print(M, N, K, "split-3 rel-to-max err", err)
+    assert err < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (1000, 217, 256)])
+def test_tc_gemm_single(M, N, K):
+    err = _run(M, N, K, 1)
+    print(M, N, K, "single-bf16 rel-to-max err", err)
+    assert err < 2e-2

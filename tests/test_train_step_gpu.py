@@ -34,7 +34,7 @@ def test_fused_step_matches_oracle(case, n_rays, H, bg):
     grad = tr.forward_backward(dv).clone()
     loss_p = tr.loss_value().item()
     total, aux = orc.loss(hv)
-    gs = torch.autograd.grad(total, [v for _, v in orc.named_params()], allow_unused=True)
+    gs = torch.autograd.grad(total, [v for _, v in orc.named_params()], allow_unused=True, retain_graph=True)
     loss_o = total.item()
     print(f"loss product {loss_p:.6f} oracle {loss_o:.6f}; cos product {tr.cos.tolist()} oracle {aux['cos'].tolist()}")
     assert abs(loss_p - loss_o) / abs(loss_o) < 1e-3
