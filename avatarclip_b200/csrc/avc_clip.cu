@@ -16,7 +16,7 @@ using namespace avc;
 
 namespace {
 
-constexpr int kT = 50;   // tokens are derived from cfg at run time; kT only documents ViT-B/32
+
 
 // ------------------------------------------------------------------------------------------------
 // fp16 tensor-core GEMM  C[M,N] = A[M,K] . W[N,K]^T  (mma.sync m16n8k16, fp32 accumulate).

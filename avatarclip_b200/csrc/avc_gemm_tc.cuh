@@ -296,9 +296,167 @@ static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, co
   return launch_gemm_tc_nt_bn<256, NPROD, Epi>(st, M, N, K, A, B, epi);
 }
 
+// ------------------------------------------------------------------------------------------------ TN kernel
+// C[i*ldc + j] += sum_{p in slice} A[p,i] * B[p,j]   (i < N1, j < N2): weight gradients.  Both operands are read
+// "MN-major": the reduction index p is the row of the global arrays.  TMA boxes are 64 (i or j) x 64 (p); in shared
+// memory one box is an MN atom block [64 p][128 B] (SWIZZLE_128B); a 128-wide M tile is 2 blocks, a BN-wide N tile
+// BN/64 blocks.  Descriptor: SBO = 1024 B (8 p-rows), LBO = 8192 B (next 64-wide block), a K step of 16 p-rows
+// is +2048 B.  Split over p across blockIdx.z; partial tiles meet in fp32 red.global.add.
+template <int BN, int NPROD>
+struct TcTnCfg {
+  static constexpr int BLK = kBK * 128;                             // one 64 x 64 bf16 block: 8 KB
+  static constexpr int A_BYTES = (kBM / 64) * BLK;                  // 16 KB
+  static constexpr int B_BYTES = (BN / 64) * BLK;
+  static constexpr int NOP = (NPROD == 3) ? 2 : 1;
+  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "tile too large for shared memory");
+};
+
+template <int BN, int NPROD>
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                  const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                  int P, int N1, int N2, int rows_per_split, float* __restrict__ C, int ldc) {
+  using Cfg = TcTnCfg<BN, NPROD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * kBM, j0 = blockIdx.y * BN;
+  const int p_begin = blockIdx.z * rows_per_split;
+  const int p_end = min(P, p_begin + rows_per_split);
+  const int nk = (p_end - p_begin + kBK - 1) / kBK;     // host guarantees rows_per_split % 64 == 0 and nk >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        mbar_wait(empty0 + 8 * s, ((kb / Cfg::STAGES) & 1) ^ 1);
+        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+        const int p0 = p_begin + kb * kBK;
+        mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+        // rows beyond p_end inside the last box belong to the next split: they must not be counted twice, so the
+        // tensor maps are built with `rows = P` and the host makes every split a multiple of 64 rows.
+#pragma unroll
+        for (int a = 0; a < kBM / 64; ++a) {
+          tma_load_2d(st + a * Cfg::BLK, &mapAhi, i0 + 64 * a, p0, full0 + 8 * s);
+          if (NPROD == 3) tma_load_2d(st + Cfg::A_BYTES + a * Cfg::BLK, &mapAlo, i0 + 64 * a, p0, full0 + 8 * s);
+        }
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) {
+          tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + b * Cfg::BLK, &mapBhi, j0 + 64 * b, p0, full0 + 8 * s);
+          if (NPROD == 3)
+            tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES + b * Cfg::BLK, &mapBlo, j0 + 64 * b, p0, full0 + 8 * s);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % Cfg::STAGES;
+        mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < kBK / 16; ++k4) {
+          const uint64_t dah = make_smem_desc(a_hi + k4 * 2048, Cfg::BLK, 1024);
+          const uint64_t dbh = make_smem_desc(b_hi + k4 * 2048, Cfg::BLK, 1024);
+          umma_f16(tmem_base, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+          if (NPROD == 3) {
+            const uint64_t dal = make_smem_desc(a_lo + k4 * 2048, Cfg::BLK, 1024);
+            const uint64_t dbl = make_smem_desc(b_lo + k4 * 2048, Cfg::BLK, 1024);
+            umma_f16(tmem_base, dah, dbl, idesc, 1u);
+            umma_f16(tmem_base, dal, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(empty0 + 8 * s);
+      }
+      umma_commit(tfull);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int gi = i0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      if (gi < N1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int gj = j0 + c * 32 + j;
+          if (gj < N2) atomicAdd(C + (size_t)gi * ldc + gj, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// A: [P][N1] (ld A.ld), B: [P][N2] (ld B.ld); C[N1][ldc] += A^T B.
+template <int NPROD>
+static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, const SplitPtr& A, const SplitPtr& B,
+                                    float* C, int ldc) {
+  if (P <= 0 || N1 <= 0 || N2 <= 0) return 0;
+  CUtensorMap mAh, mAl, mBh, mBl;
+  AVC_TRY(make_map_bf16(&mAh, A.hi, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
+  AVC_TRY(make_map_bf16(&mBh, B.hi, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
+  if (NPROD == 3) {
+    AVC_TRY(make_map_bf16(&mAl, A.lo, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
+    AVC_TRY(make_map_bf16(&mBl, B.lo, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
+  } else {
+    mAl = mAh; mBl = mBh;
+  }
+  const int t1 = ceil_div(N1, kBM);
+  auto go = [&](auto kern, int BN, int smem) -> int {
+    static bool attr_set = false;
+    (void)attr_set;
+    AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int t2 = ceil_div(N2, BN);
+    int splits = (148 + t1 * t2 - 1) / (t1 * t2);
+    int rows = (int)round_up(ceil_div(P, splits), kBK);
+    splits = ceil_div(P, rows);
+    dim3 grid(t1, t2, splits);
+    kern<<<grid, kTcThreads, smem, st>>>(mAh, mAl, mBh, mBl, (int)P, N1, N2, rows, C, ldc);
+    AVC_LAUNCH_TRY();
+    return 0;
+  };
+  if (N2 <= 64) return go(gemm_tc_tn_kernel<64, NPROD>, 64, TcTnCfg<64, NPROD>::SMEM_BYTES);
+  if (N2 <= 128) return go(gemm_tc_tn_kernel<128, NPROD>, 128, TcTnCfg<128, NPROD>::SMEM_BYTES);
+  return go(gemm_tc_tn_kernel<256, NPROD>, 256, TcTnCfg<256, NPROD>::SMEM_BYTES);
+}
+
 // ------------------------------------------------------------------------------------------------ split helper
 // fp32 [rows][ld_src] -> bf16 hi/lo [rows][ld_dst] (columns >= cols zero-filled up to ld_dst)
-__global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int cols, int ld_src,
+static __global__ void k_split_bf16(const float* __restrict__ src, int64_t rows, int cols, int ld_src,
                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ld_dst) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * ld_dst) return;

@@ -14,6 +14,7 @@
 
 #include "avc_common.cuh"
 #include "avc_gemm_simt.cuh"
+#include "avc_gemm_tc.cuh"
 #include "avc_neus_kernels.cuh"
 #include "avc_neus_plan.cuh"
 
@@ -22,6 +23,31 @@ using namespace avc;
 namespace {
 
 inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// -------------------------------------------------------------------------------- engine dispatch
+// engine 0: fp32 FFMA tiles on the fp32 buffers; engine 1: tcgen05 tiles on the two-term bf16 copies.
+// B operands are addressed by their offset in the packed-weight buffer (same offset in the bf16 split).
+inline Split16 with_ld(Split16 s, int ld) { s.ld = ld; return s; }
+
+template <typename Epi>
+int gemm_nt(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int N, int K, const float* A, int lda,
+            const Split16& A16, int64_t pk_off, int ldb, const Epi& epi) {
+  if (pl.cfg.engine == 1) {
+    tc::SplitPtr a{A16.hi, A16.lo, lda}, b{w.pk_hi + pk_off, w.pk_lo + pk_off, ldb};
+    return tc::launch_gemm_tc_nt<3, Epi>(st, M, N, K, a, b, epi);
+  }
+  return launch_gemm_nt(st, M, N, (int)round_up(K, 4), A, lda, w.pack + pk_off, ldb, epi);
+}
+
+inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t P, int N1, int N2, const float* A,
+                   int lda, const Split16& A16, const float* B, int ldb, const Split16& B16, float* C, int ldc) {
+  (void)w;
+  if (pl.cfg.engine == 1) {
+    tc::SplitPtr a{A16.hi, A16.lo, lda}, b{B16.hi, B16.lo, ldb};
+    return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, ldc);
+  }
+  return launch_gemm_tn(st, P, N1, N2, A, lda, B, ldb, C, ldc);
+}
 
 // -------------------------------------------------------------------------------- packing
 int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStream_t st) {
@@ -87,16 +113,31 @@ int zero_pack(const NeusPlan& pl, float* pack, cudaStream_t st) {
   return 0;
 }
 
+// zero + pack (+ bf16 split for the tcgen05 engine)
+int prepare_weights(const NeusPlan& pl, const NeusWs& w, const float* params, cudaStream_t st) {
+  AVC_TRY(zero_pack(pl, w.pack, st));
+  AVC_TRY(pack_weights(pl, params, w.pack, st));
+  if (pl.cfg.engine == 1) {
+    tc::k_split_bf16<<<blocks_for(pl.pack_floats, 256), 256, 0, st>>>(w.pack, 1, (int)pl.pack_floats,
+                                                                      (int)pl.pack_floats, w.pk_hi, w.pk_lo,
+                                                                      (int)pl.pack_floats);
+    AVC_LAUNCH_TRY();
+  }
+  return 0;
+}
+
 EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
   EncodeTargets t;
   memset(&t, 0, sizeof(t));
   t.in0 = w.in[0]; t.ld0 = pl.sdf[0].Kp;
+  t.in0_16 = w.in16[0];
   for (int l = 1; l <= pl.L; ++l) {
     if (!pl.sdf[l].skip) continue;
     if (t.n_skip >= 4) break;
     t.skip_ptr[t.n_skip] = w.in[l];
     t.skip_ld[t.n_skip] = pl.sdf[l].Kp;
     t.skip_col[t.n_skip] = pl.sdf[l].K - pl.E;
+    t.skip16[t.n_skip] = w.in16[l];
     ++t.n_skip;
   }
   return t;
@@ -116,7 +157,8 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
     e.OUT = w.in[l + 1]; e.ldo = pl.sdf[l + 1].Kp;
     e.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
     e.N = d.N;
-    AVC_TRY(launch_gemm_nt(st, Pn, d.N, d.Kp, w.in[l], d.Kp, pack + d.pk_W, d.Kp, e));
+    e.o16 = w.in16[l + 1];
+    AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, e));
   }
   const LinDim& dl = pl.sdf[pl.L];
   OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale};
@@ -124,8 +166,8 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
                                                            pack + pl.pk_bsdf, Pn, os);
   AVC_LAUNCH_TRY();
   if (want_feat) {
-    EpiBias e{pack + dl.pk_b, w.feat, pl.Fp, pl.F};
-    AVC_TRY(launch_gemm_nt(st, Pn, pl.F, dl.Kp, w.in[pl.L], dl.Kp, pack + dl.pk_W, dl.Kp, e));
+    EpiBias e{pack + dl.pk_b, w.feat, pl.Fp, pl.F, w.feat16};
+    AVC_TRY(gemm_nt(pl, w, st, Pn, pl.F, dl.K, w.in[pl.L], dl.Kp, w.in16[pl.L], dl.pk_W, dl.Kp, e));
   }
   return 0;
 }
@@ -206,7 +248,8 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
     const LinDim& dp = pl.sdf[pl.L - 1];
     int64_t tot = P * (int64_t)(dp.Np > pl.EP ? dp.Np : pl.EP);
     k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
-                                                        w.z[pl.L - 1], dp.N, dp.Np, P, w.qt[pl.L - 1], w.ge);
+                                                        w.z[pl.L - 1], dp.N, dp.Np, P, w.qt[pl.L - 1], w.ge,
+                                                        w.qt16[pl.L - 1]);
     AVC_LAUNCH_TRY();
     for (int l = pl.L - 1; l >= 1; --l) {
       const LinDim& d = pl.sdf[l];
@@ -214,11 +257,12 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
       EpiChain e;
       e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
       e.Zprev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
-      AVC_TRY(launch_gemm_nt(st, P, d.K, d.Np, w.qt[l], d.Np, pack + d.pk_WT, d.Np, e));
+      e.q16 = w.qt16[l - 1];
+      AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
     }
     const LinDim& d0 = pl.sdf[0];
     EpiGe eg{w.ge, pl.EP, pl.E};
-    AVC_TRY(launch_gemm_nt(st, P, pl.E, d0.Np, w.qt[0], d0.Np, pack + d0.pk_WT, d0.Np, eg));
+    AVC_TRY(gemm_nt(pl, w, st, P, pl.E, d0.N, w.qt[0], d0.Np, w.qt16[0], d0.pk_WT, d0.Np, eg));
     k_normal<<<blocks_for(P, 128), 128, 0, st>>>(w.ge, pl.EP, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P, w.cin,
                                                  write_outputs ? io.out.gradients : nullptr);
     AVC_LAUNCH_TRY();
@@ -226,12 +270,12 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   // ---- colour net
   {
     const LinDim& c0 = pl.col[0];
-    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, w.ch[1], pl.Hc};
-    AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Fp, w.feat, pl.Fp, pack + c0.pk_W, pl.Fp, e0));
+    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, w.ch[1], pl.Hc, w.ch16[1]};
+    AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
     for (int l = 1; l < pl.Lc; ++l) {
       const LinDim& c = pl.col[l];
-      EpiRelu e{pack + c.pk_b, w.ch[l + 1], pl.Hc};
-      AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, pack + c.pk_W, pl.Hc, e));
+      EpiRelu e{pack + c.pk_b, w.ch[l + 1], pl.Hc, w.ch16[l + 1]};
+      AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, w.ch16[l], c.pk_W, pl.Hc, e));
     }
     OutHeads oh{w.rgb6};
     k_thin_nt<6, OutHeads><<<blocks_for(P, 8), 256, 0, st>>>(w.ch[pl.Lc], pl.Hc, pl.Hc, pack + pl.pk_W6, pl.Hc,
@@ -293,7 +337,8 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const LinDim& dx = pl.extra;
     AVC_TRY(thin_tn<3>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b));
     AVC_TRY(thin_tn<3>(st, w.y6bar + 3, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dx.off_v, pl.Hc, 1, wbar + dx.off_b));
-    k_heads_dgrad<<<blocks_for(P * pl.Hc, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0]);
+    k_heads_dgrad<<<blocks_for(P * pl.Hc, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0],
+                                                              w.cbar16[0]);
     AVC_LAUNCH_TRY();
   }
   // ---- colour hidden linears l = Lc-1 .. 0 ; cbar_l lives in w.cbar[cur]
@@ -303,17 +348,17 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     float* cb = w.cbar[cur];
     AVC_TRY(colsum(st, cb, pl.Hc, pl.Hc, P, 1.f, wbar + c.off_b));
     if (l > 0) {
-      AVC_TRY(launch_gemm_tn(st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.ch[l], pl.Hc, wbar + c.off_v, c.K));
-      EpiDgradRelu e{w.ch[l], w.cbar[cur ^ 1], pl.Hc};
-      AVC_TRY(launch_gemm_nt(st, P, pl.Hc, pl.Hc, cb, pl.Hc, pack + c.pk_WT, pl.Hc, e));
+      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], w.ch[l], pl.Hc, w.ch16[l], wbar + c.off_v, c.K));
+      EpiDgradRelu e{w.ch[l], w.cbar[cur ^ 1], pl.Hc, w.cbar16[cur ^ 1]};
+      AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, e));
       cur ^= 1;
     } else {
       // lin0 input = [x(3), n(3), feat(F)]: dW[:, 6:] += cbar^T feat ; dW[:, :6] += cbar^T cin6
-      AVC_TRY(launch_gemm_tn(st, P, pl.Hc, pl.F, cb, pl.Hc, w.feat, pl.Fp, wbar + c.off_v + 6, c.K));
+      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.F, cb, pl.Hc, w.cbar16[cur], w.feat, pl.Fp, w.feat16, wbar + c.off_v + 6, c.K));
       AVC_TRY(thin_tn<6>(st, w.cin, 8, 1.f, cb, pl.Hc, pl.Hc, P, wbar + c.off_v, 1, c.K, nullptr));
       // featbar = cbar . W0[:, 6:]
-      EpiStore es{w.featbar, pl.Fp, pl.F};
-      AVC_TRY(launch_gemm_nt(st, P, pl.F, pl.Hc, cb, pl.Hc, pack + c.pk_WT, pl.Hc, es));
+      EpiStore es{w.featbar, pl.Fp, pl.F, w.featbar16};
+      AVC_TRY(gemm_nt(pl, w, st, P, pl.F, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, es));
       // nbar += cbar . W0[:, 3:6]   (d/d points is discarded: pts is a leaf, models/fields.py:97)
       OutNbarAdd on{w.nbar};
       k_thin_nt<6, OutNbarAdd><<<blocks_for(P, 8), 256, 0, st>>>(cb, pl.Hc, pl.Hc, pack + pl.pk_c0xT, pl.Hc, nullptr,
@@ -327,7 +372,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
   {
     const LinDim& d0 = pl.sdf[0];
     k_dge<<<blocks_for(P, 128), 128, 0, st>>>(w.cin, w.nbar, pl.EP, pl.E, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P,
-                                              w.ubar[0], d0.Kp, w.gebar);
+                                              w.ubar[0], d0.Kp, w.gebar, with_ld(w.ubar16[0], d0.Kp));
     AVC_LAUNCH_TRY();
   }
   for (int l = 0; l <= pl.L; ++l) {
@@ -338,15 +383,17 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
       AVC_TRY(colsum(st, ub, d.Kp, d.K, P, 1.f, wbar + d.off_v));
       break;
     }
-    AVC_TRY(launch_gemm_tn(st, P, d.N, d.K, w.qt[l], d.Np, ub, d.Kp, wbar + d.off_v, d.K));
+    const Split16 ub16 = with_ld(w.ubar16[ucur], d.Kp);
+    AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.qt[l], d.Np, w.qt16[l], ub, d.Kp, ub16, wbar + d.off_v, d.K));
     const LinDim& dn = pl.sdf[l + 1];
     EpiChainBwd e;
     e.N = d.N; e.Np = d.Np; e.Z = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
     e.UNEXT = w.ubar[ucur ^ 1]; e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
-    AVC_TRY(launch_gemm_nt(st, P, d.N, d.Kp, ub, d.Kp, pack + d.pk_W, d.Kp, e));
+    e.u16 = with_ld(w.ubar16[ucur ^ 1], dn.Kp);
+    AVC_TRY(gemm_nt(pl, w, st, P, d.N, d.K, ub, d.Kp, ub16, d.pk_W, d.Kp, e));
     if (dn.skip) {
       k_fill_gebar<<<blocks_for(P * pl.E, 256), 256, 0, st>>>(w.gebar, pl.EP, pl.E, P, w.ubar[ucur ^ 1], dn.Kp,
-                                                              dn.K - pl.E);
+                                                              dn.K - pl.E, with_ld(w.ubar16[ucur ^ 1], dn.Kp));
       AVC_LAUNCH_TRY();
     }
     ucur ^= 1;
@@ -358,18 +405,20 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const float inv_scale = 1.0f / pl.cfg.sdf_scale;
     // last linear: row 0 (sdf) via thin ops, rows 1.. (features) via the GEMM tiles
     AVC_TRY(thin_tn<1>(st, w.sdfbar, 1, inv_scale, w.in[pl.L], dL.Kp, dL.K, P, wbar + dL.off_v, 0, 1, wbar + dL.off_b));
-    AVC_TRY(launch_gemm_tn(st, P, pl.F, dL.K, w.featbar, pl.Fp, w.in[pl.L], dL.Kp, wbar + dL.off_v + dL.K, dL.K));
+    AVC_TRY(gemm_tn(pl, w, st, P, pl.F, dL.K, w.featbar, pl.Fp, w.featbar16, w.in[pl.L], dL.Kp, w.in16[pl.L],
+                    wbar + dL.off_v + dL.K, dL.K));
     AVC_TRY(colsum(st, w.featbar, pl.Fp, pl.F, P, 1.f, wbar + dL.off_b + 1));
     const LinDim& dp = pl.sdf[pl.L - 1];
     EpiDgrad e;
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = dL.skip ? kSqrtHalf : 1.f;
     e.Zprev = w.z[pl.L - 1]; e.ZBARprev = w.zbar[pl.L - 1];
     e.sdfbar = w.sdfbar; e.wsdf = pack + pl.pk_wsdf; e.sdf_inv_scale = inv_scale;
-    AVC_TRY(launch_gemm_nt(st, P, dp.N, pl.Fp, w.featbar, pl.Fp, pack + dL.pk_WT, pl.Fp, e));
+    e.z16 = w.zbar16[pl.L - 1];
+    AVC_TRY(gemm_nt(pl, w, st, P, dp.N, pl.F, w.featbar, pl.Fp, w.featbar16, dL.pk_WT, pl.Fp, e));
   }
   for (int l = pl.L - 1; l >= 0; --l) {
     const LinDim& d = pl.sdf[l];
-    AVC_TRY(launch_gemm_tn(st, P, d.N, d.K, w.zbar[l], d.Np, w.in[l], d.Kp, wbar + d.off_v, d.K));
+    AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.zbar[l], d.Np, w.zbar16[l], w.in[l], d.Kp, w.in16[l], wbar + d.off_v, d.K));
     AVC_TRY(colsum(st, w.zbar[l], d.Np, d.N, P, 1.f, wbar + d.off_b));
     if (l == 0) break;
     const LinDim& dp = pl.sdf[l - 1];
@@ -377,7 +426,8 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = d.skip ? kSqrtHalf : 1.f;
     e.Zprev = w.z[l - 1]; e.ZBARprev = w.zbar[l - 1];
     e.sdfbar = nullptr; e.wsdf = nullptr; e.sdf_inv_scale = 1.f;
-    AVC_TRY(launch_gemm_nt(st, P, dp.N, d.Np, w.zbar[l], d.Np, pack + d.pk_WT, d.Np, e));
+    e.z16 = w.zbar16[l - 1];
+    AVC_TRY(gemm_nt(pl, w, st, P, dp.N, d.N, w.zbar[l], d.Np, w.zbar16[l], d.pk_WT, d.Np, e));
   }
   return 0;
 }
@@ -479,7 +529,6 @@ int avc_neus_render_fwd(const avc_neus_cfg* cfg, const float* params, const floa
   if (R <= 0 || max_rays_per_chunk <= 0) return AVC_E_SIZE;
   NeusPlan pl;
   AVC_TRY(build_plan(cfg, &pl));
-  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
   AVC_TRY(check_ptr16(workspace)); AVC_TRY(check_ptr16(params)); AVC_TRY(check_ptr16(out->z_vals));
   const int64_t Rc_max = R < max_rays_per_chunk ? R : max_rays_per_chunk;
   NeusWs w;
@@ -487,8 +536,7 @@ int avc_neus_render_fwd(const avc_neus_cfg* cfg, const float* params, const floa
   if (w.bytes > workspace_bytes) return AVC_E_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
 
-  AVC_TRY(zero_pack(pl, w.pack, st));
-  AVC_TRY(pack_weights(pl, params, w.pack, st));
+  AVC_TRY(prepare_weights(pl, w, params, st));
   k_ctx_init<<<1, 32, 0, st>>>(params, pl.off_var, w.ctx, 1);
   AVC_LAUNCH_TRY();
 
@@ -526,7 +574,6 @@ int avc_neus_render_bwd(const avc_neus_cfg* cfg, const float* params, const floa
   if (R <= 0 || max_rays_per_chunk <= 0) return AVC_E_SIZE;
   NeusPlan pl;
   AVC_TRY(build_plan(cfg, &pl));
-  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
   AVC_TRY(check_ptr16(workspace)); AVC_TRY(check_ptr16(params)); AVC_TRY(check_ptr16(grad_params));
   const int64_t Rc_max = R < max_rays_per_chunk ? R : max_rays_per_chunk;
   NeusWs w;
@@ -547,10 +594,7 @@ int avc_neus_render_bwd(const avc_neus_cfg* cfg, const float* params, const floa
     k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, Rc, 1, w.ctx + CTX_EIK_DEN);
     AVC_LAUNCH_TRY();
   }
-  if (!single) {
-    AVC_TRY(zero_pack(pl, w.pack, st));
-    AVC_TRY(pack_weights(pl, params, w.pack, st));
-  }
+  if (!single) AVC_TRY(prepare_weights(pl, w, params, st));
   for (int64_t r0 = 0; r0 < R; r0 += Rc_max) {
     const int64_t Rc = (R - r0) < Rc_max ? (R - r0) : Rc_max;
     ChunkIO io;
@@ -574,7 +618,6 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
   if (P <= 0) return AVC_E_SIZE;
   NeusPlan pl;
   AVC_TRY(build_plan(cfg, &pl));
-  if (pl.cfg.engine != 0) return AVC_E_BADCFG;
   // the workspace is sized in rays; a chunk of Rc rays offers Rc * S point rows
   size_t one = 0;
   AVC_TRY(avc_neus_workspace_bytes(cfg, 1, &one));
@@ -590,8 +633,7 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
   carve_ws(pl, Rc, workspace, &w);
   if (w.bytes > workspace_bytes) return AVC_E_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
-  AVC_TRY(zero_pack(pl, w.pack, st));
-  AVC_TRY(pack_weights(pl, params, w.pack, st));
+  AVC_TRY(prepare_weights(pl, w, params, st));
   const int64_t cap = Rc * pl.S;
   EncodeTargets t = make_targets(pl, w);
   for (int64_t p0 = 0; p0 < P; p0 += cap) {

@@ -4,9 +4,31 @@
 //
 // Reference citations are relative to AvatarGen/AppearanceGen of hongfz16/AvatarCLIP.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "avc_common.cuh"
 
 namespace avc {
+
+// Optional second copy of an activation as a two-term bf16 split (hi + lo), the operand format of the
+// tcgen05 engine (avc_gemm_tc.cuh).  hi == nullptr: fp32 engine, nothing is written.
+struct Split16 {
+  __nv_bfloat16* hi; __nv_bfloat16* lo; int ld;
+};
+__device__ __forceinline__ void split16_put(const Split16& s, size_t row, int col, float v) {
+  if (!s.hi) return;
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  s.hi[row * s.ld + col] = h;
+  s.lo[row * s.ld + col] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+__device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int col, const float v[4]) {
+  if (!s.hi) return;
+  __nv_bfloat16 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { h[i] = __float2bfloat16_rn(v[i]); l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i])); }
+  *reinterpret_cast<uint2*>(s.hi + row * s.ld + col) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(s.lo + row * s.ld + col) = *reinterpret_cast<const uint2*>(l);
+}
 
 // =============================================================================================
 // Weight packing: W = g * v / ||v||_row  (torch.nn.utils.weight_norm, models/fields.py:65-66,142-143)
@@ -87,6 +109,7 @@ struct EncodeTargets {
   float* in0; int ld0;              // in[0]: [P][EP]  <- e (padding columns zeroed)
   int n_skip;                       // skip layers: in[l][:, K-E .. K) <- e / sqrt(2)
   float* skip_ptr[4]; int skip_ld[4]; int skip_col[4];
+  Split16 in0_16; Split16 skip16[4];   // tcgen05 engine copies (hi == nullptr: unused)
 };
 
 __device__ __forceinline__ void encode_point(float x0, float x1, float x2, float scale, int multires, int E, int EP,
@@ -95,7 +118,11 @@ __device__ __forceinline__ void encode_point(float x0, float x1, float x2, float
   float* r0 = t.in0 + (size_t)p * t.ld0;
   auto put = [&](int c, float v) {
     r0[c] = v;
-    for (int s = 0; s < t.n_skip; ++s) t.skip_ptr[s][(size_t)p * t.skip_ld[s] + t.skip_col[s] + c] = v * kSqrtHalf;
+    split16_put(t.in0_16, (size_t)p, c, v);
+    for (int s = 0; s < t.n_skip; ++s) {
+      t.skip_ptr[s][(size_t)p * t.skip_ld[s] + t.skip_col[s] + c] = v * kSqrtHalf;
+      split16_put(t.skip16[s], (size_t)p, t.skip_col[s] + c, v * kSqrtHalf);
+    }
   };
   put(0, y[0]); put(1, y[1]); put(2, y[2]);
   float f = 1.f;
@@ -109,7 +136,7 @@ __device__ __forceinline__ void encode_point(float x0, float x1, float x2, float
     }
     f *= 2.f;
   }
-  for (int c = E; c < EP; ++c) r0[c] = 0.f;
+  for (int c = E; c < EP; ++c) { r0[c] = 0.f; split16_put(t.in0_16, (size_t)p, c, 0.f); }
 }
 
 // Sampling passes: points in SAMPLE-MAJOR order p = j * Rc + r taken from z[j][r] (first nz rows).
@@ -396,7 +423,7 @@ k_colsum(const float* __restrict__ X, int ld, int NC, int64_t P, int rows_per_bl
 // u_L = row 0 of W_L (constant):  qt[L-1] = softplus'(z[L-1]) * ua_L ; ge initialised.
 __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL, int E, int EP,
                               const float* __restrict__ zprev, int Nprev, int Npp, int64_t P,
-                              float* __restrict__ qt, float* __restrict__ ge) {
+                              float* __restrict__ qt, float* __restrict__ ge, Split16 qt16) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t tot = P * (int64_t)Npp;
   if (i < tot) {
@@ -408,6 +435,7 @@ __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL,
       v = softplus100_d1(zprev[i]) * ua;
     }
     qt[i] = v;
+    split16_put(qt16, (size_t)p, c, v);
   }
   if (i < P * (int64_t)EP) {
     int64_t p = i / EP;
@@ -443,14 +471,15 @@ __global__ void k_normal(const float* __restrict__ ge, int EP, int multires, flo
 
 // gebar = D(y) nbar -> ubar0[p][EP] (padding zeroed) and gebar[p][EP].
 __global__ void k_dge(const float* __restrict__ cin, const float* __restrict__ nbar, int EP, int E, int multires,
-                      float scale, int64_t P, float* __restrict__ ubar0, int ldu, float* __restrict__ gebar) {
+                      float scale, int64_t P, float* __restrict__ ubar0, int ldu, float* __restrict__ gebar,
+                      Split16 u16) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float* c = cin + (size_t)p * 8;
   const float nb[3] = {nbar[p * 4 + 0], nbar[p * 4 + 1], nbar[p * 4 + 2]};
   float* u = ubar0 + (size_t)p * ldu;
   float* g = gebar + (size_t)p * EP;
-  auto put = [&](int col, float v) { u[col] = v; g[col] = v; };
+  auto put = [&](int col, float v) { u[col] = v; g[col] = v; split16_put(u16, (size_t)p, col, v); };
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     float y = c[a] * scale;
@@ -465,22 +494,24 @@ __global__ void k_dge(const float* __restrict__ cin, const float* __restrict__ n
     }
   }
   for (int col = E; col < EP; ++col) put(col, 0.f);
-  for (int col = EP; col < ldu; ++col) u[col] = 0.f;
+  for (int col = EP; col < ldu; ++col) { u[col] = 0.f; split16_put(u16, (size_t)p, col, 0.f); }
 }
 
 // ubar[p][col0 + e] = gebar[p][e] / sqrt(2)   (the encoding half of a skip layer's input adjoint)
 __global__ void k_fill_gebar(const float* __restrict__ gebar, int EP, int E, int64_t P, float* __restrict__ ubar,
-                             int ldu, int col0) {
+                             int ldu, int col0, Split16 u16) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * (int64_t)E) return;
   int64_t p = i / E;
   int e = (int)(i - p * E);
-  ubar[(size_t)p * ldu + col0 + e] = gebar[(size_t)p * EP + e] * kSqrtHalf;
+  float v = gebar[(size_t)p * EP + e] * kSqrtHalf;
+  ubar[(size_t)p * ldu + col0 + e] = v;
+  split16_put(u16, (size_t)p, col0 + e, v);
 }
 
 // cbar[p][c] = (sum_i y6bar[p][i] * W6[i][c]) * [h[p][c] > 0]   (heads dgrad + ReLU mask)
 __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __restrict__ W6, int Hc,
-                              const float* __restrict__ h, int64_t P, float* __restrict__ cbar) {
+                              const float* __restrict__ h, int64_t P, float* __restrict__ cbar, Split16 c16) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * (int64_t)Hc) return;
   int64_t p = i / Hc;
@@ -489,7 +520,9 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
   float acc = 0.f;
 #pragma unroll
   for (int k = 0; k < 6; ++k) acc = fmaf(y[k], W6[(size_t)k * Hc + c], acc);
-  cbar[i] = h[i] > 0.f ? acc : 0.f;
+  float v = h[i] > 0.f ? acc : 0.f;
+  cbar[i] = v;
+  split16_put(c16, (size_t)p, c, v);
 }
 
 // =============================================================================================
@@ -499,7 +532,7 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
 
 // value chain: z = acc + b ; Z[row] = z (padding zero) ; OUT[row][col] = softplus(z) * oscale (col < N)
 struct EpiValue {
-  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N;
+  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float zz[4], hh[4];
@@ -512,36 +545,40 @@ struct EpiValue {
     if (Z) *reinterpret_cast<float4*>(Z + (size_t)row * ldz + col) = make_float4(zz[0], zz[1], zz[2], zz[3]);
     if (col + 3 < N) {
       *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      split16_put4(o16, (size_t)row, col, hh);
     } else {
-      for (int i = 0; i < 4 && col + i < N; ++i) OUT[(size_t)row * ldo + col + i] = hh[i];
+      for (int i = 0; i < 4 && col + i < N; ++i) { OUT[(size_t)row * ldo + col + i] = hh[i]; split16_put(o16, (size_t)row, col + i, hh[i]); }
     }
   }
 };
 
 // out = acc + b (feature rows of the last SDF linear)
 struct EpiBias {
-  const float* bias; float* OUT; int ldo; int N;
+  const float* bias; float* OUT; int ldo; int N; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] + bias[col + i] : 0.f;
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(o16, (size_t)row, col, v);
   }
 };
 
 // gradient chain, layer l >= 1: u = acc (width K_l).  Columns < Nprev: ua = u * s, qt_prev = sp'(z_prev) * ua;
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
 struct EpiChain {
-  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E;
+  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
       if (c < Nprev) {
-        QTprev[(size_t)row * Npp + c] = softplus100_d1(Zprev[(size_t)row * Npp + c]) * v[i] * s;
+        float qv = softplus100_d1(Zprev[(size_t)row * Npp + c]) * v[i] * s;
+        QTprev[(size_t)row * Npp + c] = qv;
+        split16_put(q16, (size_t)row, c, qv);
       } else {
-        if (c < Npp) QTprev[(size_t)row * Npp + c] = 0.f;
+        if (c < Npp) { QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
         int e = c - Nprev;
         if (e < E) GE[(size_t)row * EP + e] += v[i] * kSqrtHalf;
       }
@@ -562,7 +599,7 @@ struct EpiGe {
 
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
 struct EpiColor0 {
-  const float* bias; const float* cin; const float* Wx; float* OUT; int ldo;
+  const float* bias; const float* cin; const float* Wx; float* OUT; int ldo; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
@@ -577,37 +614,41 @@ struct EpiColor0 {
       v[i] = fmaxf(z, 0.f);
     }
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(o16, (size_t)row, col, v);
   }
 };
 
 struct EpiRelu {
-  const float* bias; float* OUT; int ldo;
+  const float* bias; float* OUT; int ldo; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i] + bias[col + i], 0.f);
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(o16, (size_t)row, col, v);
   }
 };
 
 // colour dgrad: out = acc * [h > 0]
 struct EpiDgradRelu {
-  const float* Hm; float* OUT; int ld;
+  const float* Hm; float* OUT; int ld; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     const float4 h = *reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col);
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) =
-        make_float4(h.x > 0.f ? v[0] : 0.f, h.y > 0.f ? v[1] : 0.f, h.z > 0.f ? v[2] : 0.f, h.w > 0.f ? v[3] : 0.f);
+    v[0] = h.x > 0.f ? v[0] : 0.f; v[1] = h.y > 0.f ? v[1] : 0.f; v[2] = h.z > 0.f ? v[2] : 0.f; v[3] = h.w > 0.f ? v[3] : 0.f;
+    *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(o16, (size_t)row, col, v);
   }
 };
 
 struct EpiStore {
-  float* OUT; int ldo; int N;
+  float* OUT; int ldo; int N; Split16 o16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] : 0.f;
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(o16, (size_t)row, col, v);
   }
 };
 
@@ -615,7 +656,7 @@ struct EpiStore {
 //   ubar_next[row][col] = sp'(z_l) * qbar * s_next            (col < N_l)
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
-  int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next;
+  int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float zb[4];
@@ -624,7 +665,9 @@ struct EpiChainBwd {
       int c = col + i;
       if (c < N) {
         float s1 = softplus100_d1(Z[(size_t)row * Np + c]);
-        UNEXT[(size_t)row * ldu + c] = s1 * v[i] * s_next;
+        float uv = s1 * v[i] * s_next;
+        UNEXT[(size_t)row * ldu + c] = uv;
+        split16_put(u16, (size_t)row, c, uv);
         zb[i] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * v[i];
       } else {
         zb[i] = 0.f;
@@ -638,7 +681,7 @@ struct EpiChainBwd {
 //   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev)
 struct EpiDgrad {
   int Nprev, Npp; float s; const float* Zprev; float* ZBARprev; const float* sdfbar; const float* wsdf;
-  float sdf_inv_scale;
+  float sdf_inv_scale; Split16 z16;
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;
@@ -649,7 +692,9 @@ struct EpiDgrad {
         float ab = v[i];
         if (sdfbar) ab = fmaf(sb, wsdf[c], ab);
         size_t o = (size_t)row * Npp + c;
-        ZBARprev[o] = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+        float zv = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+        ZBARprev[o] = zv;
+        split16_put(z16, (size_t)row, c, zv);
       }
     }
   }

@@ -2,6 +2,7 @@
 // parameter layout (reference state-dict order), the packed-weight layout and the workspace layout.
 #pragma once
 #include "avc_common.cuh"
+#include "avc_neus_kernels.cuh"   // Split16
 
 namespace avc {
 
@@ -54,8 +55,9 @@ static inline int build_plan(const avc_neus_cfg* c, NeusPlan* p) {
   if (c->n_samples < 2 || c->n_importance < 0 || c->up_sample_steps < 1) return AVC_E_BADCFG;
   if (c->n_importance % c->up_sample_steps) return AVC_E_BADCFG;
   if (c->engine != 0 && c->engine != 1) return AVC_E_BADCFG;
+  if (c->engine == 1 && (c->sdf_d_hidden % 8 || c->col_d_hidden % 8 || (c->sdf_d_out - 1) % 8)) return AVC_E_BADCFG;
   p->E = 3 * (1 + 2 * c->sdf_multires);
-  p->EP = (int)round_up(p->E, 4);
+  p->EP = (int)round_up(p->E, 8);   // multiples of 8: bf16 rows stay 16-byte aligned for TMA
   p->H = c->sdf_d_hidden;
   p->L = c->sdf_n_layers;
   p->F = c->sdf_d_out - 1;
@@ -70,7 +72,7 @@ static inline int build_plan(const avc_neus_cfg* c, NeusPlan* p) {
   if ((c->sdf_skip_mask & 1u) || (c->sdf_skip_mask >> (p->L + 1))) return AVC_E_BADCFG;
 
   int64_t po = 0, pk = 0;
-  auto take_pk = [&](int64_t n) { int64_t r = pk; pk += round_up(n, 4); return r; };
+  auto take_pk = [&](int64_t n) { int64_t r = pk; pk += round_up(n, 8); return r; };
   // ---- SDF linears (models/fields.py:24-43)
   for (int l = 0; l <= p->L; ++l) {
     LinDim& d = p->sdf[l];
@@ -80,8 +82,8 @@ static inline int build_plan(const avc_neus_cfg* c, NeusPlan* p) {
     d.N = (l == p->L) ? c->sdf_d_out : (next_skip ? p->H - p->E : p->H);
     if (d.N <= 0) return AVC_E_BADCFG;
     if (d.skip && l == 0) return AVC_E_BADCFG;
-    d.Kp = (int)round_up(d.K, 4);
-    d.Np = (int)round_up(d.N, 4);
+    d.Kp = (int)round_up(d.K, 8);
+    d.Np = (int)round_up(d.N, 8);
     d.off_g = po; po += d.N;
     d.off_v = po; po += (int64_t)d.N * d.K;
     d.off_b = po; po += d.N;
@@ -103,8 +105,8 @@ static inline int build_plan(const avc_neus_cfg* c, NeusPlan* p) {
     d.skip = false;
     d.K = (l == 0) ? 6 + p->F : p->Hc;
     d.N = (l == p->Lc) ? 3 : p->Hc;
-    d.Kp = (int)round_up(d.K, 4);
-    d.Np = (int)round_up(d.N, 4);
+    d.Kp = (int)round_up(d.K, 8);
+    d.Np = (int)round_up(d.N, 8);
     d.off_g = po; po += d.N;
     d.off_v = po; po += (int64_t)d.N * d.K;
     d.off_b = po; po += d.N;
@@ -168,6 +170,10 @@ struct NeusWs {
   float* cbar[2];    // [P][Hc]
   float* ubar[2];    // [P][max(Kp)]
   float* zbar[kMaxLin];   // [P][Np_l], l < L
+  // tcgen05 engine: two-term bf16 copies of every GEMM operand (same leading dimensions); hi == nullptr otherwise
+  __nv_bfloat16 *pk_hi, *pk_lo;            // split of the whole packed-weight buffer (same offsets as `pack`)
+  Split16 in16[kMaxLin], qt16[kMaxLin], zbar16[kMaxLin], ch16[kMaxLin];
+  Split16 feat16, featbar16, cbar16[2], ubar16[2];
   size_t bytes;
   int64_t Rc, P;
 };
@@ -213,6 +219,28 @@ static inline void carve_ws(const NeusPlan& pl, int64_t Rc, void* base, NeusWs* 
   w->cbar[1] = c.take<float>(P * pl.Hc);
   w->ubar[0] = c.take<float>(P * maxK);
   w->ubar[1] = c.take<float>(P * maxK);
+  const Split16 none = {nullptr, nullptr, 0};
+  w->pk_hi = w->pk_lo = nullptr;
+  for (int l = 0; l < kMaxLin; ++l) w->in16[l] = w->qt16[l] = w->zbar16[l] = w->ch16[l] = none;
+  w->feat16 = w->featbar16 = w->cbar16[0] = w->cbar16[1] = w->ubar16[0] = w->ubar16[1] = none;
+  if (pl.cfg.engine == 1) {
+    auto take16 = [&](int64_t rows, int ld) {
+      Split16 s;
+      s.hi = c.take<__nv_bfloat16>(rows * ld);
+      s.lo = c.take<__nv_bfloat16>(rows * ld);
+      s.ld = ld;
+      return s;
+    };
+    w->pk_hi = c.take<__nv_bfloat16>(pl.pack_floats);
+    w->pk_lo = c.take<__nv_bfloat16>(pl.pack_floats);
+    for (int l = 0; l <= pl.L; ++l) w->in16[l] = take16(P, pl.sdf[l].Kp);
+    for (int l = 0; l < pl.L; ++l) { w->qt16[l] = take16(P, pl.sdf[l].Np); w->zbar16[l] = take16(P, pl.sdf[l].Np); }
+    w->feat16 = take16(P, pl.Fp);
+    w->featbar16 = take16(P, pl.Fp);
+    for (int l = 1; l <= pl.Lc; ++l) w->ch16[l] = take16(P, pl.Hc);
+    w->cbar16[0] = take16(P, pl.Hc); w->cbar16[1] = take16(P, pl.Hc);
+    w->ubar16[0] = take16(P, maxK); w->ubar16[1] = take16(P, maxK);
+  }
   w->bytes = c.used();
 }
 

@@ -260,6 +260,10 @@ int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
  * ------------------------------------------------------------------------------------------ */
 int avc_tc_gemm_nt_test(const float* A, const float* B, int64_t M, int32_t N, int32_t K, int32_t nprod,
                         float* C, void* workspace, size_t workspace_bytes, avc_stream_t stream);
+/* Same for the reduction-over-rows tiles (weight gradients): C[N1][N2] += A[P][N1]^T . B[P][N2].
+ * workspace >= 4 * P * (round_up(N1,8) + round_up(N2,8)) + 2048 bytes. */
+int avc_tc_gemm_tn_test(const float* A, const float* B, int64_t P, int32_t N1, int32_t N2, int32_t nprod,
+                        float* C, void* workspace, size_t workspace_bytes, avc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -59,3 +59,17 @@ def test_sdf_query_matches_oracle():
     from oracle import neus
     want = neus.sdf_value(sp, sconf, pts)
     assert U.rel_to_max(got, want) < 1e-5
+
+
+@pytest.mark.parametrize("name,bg,anneal", [("tiny", "ray", 1.0), ("skiplast", "none", 0.3), ("shipped", "ray", 1.0),
+                                             ("b2", "white", 1.0)])
+def test_tcgen05_engine_matches_oracle(name, bg, anneal):
+    """engine 1: tcgen05 tiles with two-term bf16 split operands (3 MMAs per product).  The bar is the
+    north_star's: rendered outputs within 1e-3 relative; gradients are reported and held to 2e-2."""
+    rep = U.run_case_gpu_vs_oracle(name, bg_kind=bg, anneal=anneal, engine=1)
+    print({k: rep[k] for k in ("case", "worst_out", "worst_grad", "placement_frac_3e-3", "placement_max_dz",
+                               "full_render_frac_rays_1e-3")})
+    assert rep["worst_out"] < 1e-3, rep
+    assert rep["worst_grad"] < 2e-2, rep
+    assert rep["placement_frac_3e-3"] >= 0.97, rep
+    assert rep["full_render_frac_rays_1e-3"] >= 0.95, rep

@@ -39,3 +39,30 @@ def test_tc_gemm_single(M, N, K):
     err = _run(M, N, K, 1)
     print(M, N, K, "single-bf16 rel-to-max err", err)
     assert err < 2e-2
+
+
+def _run_tn(P, N1, N2, nprod, seed=0):
+    from avatarclip_b200 import _lib
+    L = _lib.lib()
+    L.avc_tc_gemm_tn_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+    L.avc_tc_gemm_tn_test.restype = C.c_int
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(P, N1, generator=g).cuda()
+    B = (torch.randn(P, N2, generator=g) * 0.1).cuda()
+    base = torch.randn(N1, N2, generator=g).cuda()
+    Cm = base.clone()
+    r8 = lambda n: (n + 7) // 8 * 8
+    ws = torch.empty(4 * P * (r8(N1) + r8(N2)) + 8192, dtype=torch.uint8, device="cuda")
+    _lib.check(L.avc_tc_gemm_tn_test(A.data_ptr(), B.data_ptr(), P, N1, N2, nprod, Cm.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _lib.stream_ptr()), "avc_tc_gemm_tn_test")
+    torch.cuda.synchronize()
+    ref = base.double() + A.double().t() @ B.double()
+    return (Cm.double() - ref).abs().max().item() / ref.abs().max().item()
+
+
+@pytest.mark.parametrize("P,N1,N2", [(64, 128, 64), (640, 256, 256), (5000, 217, 256), (3000, 257, 39), (9000, 40, 128)])
+def test_tc_gemm_tn_split3(P, N1, N2):
+    err = _run_tn(P, N1, N2, 3)
+    print(P, N1, N2, "TN split-3 rel-to-max err", err)
+    assert err < 3e-5
