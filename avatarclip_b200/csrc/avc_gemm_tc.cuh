@@ -123,6 +123,24 @@ static inline PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 tensor [rows][cols] with row pitch ld (elements); box = box_cols x box_rows, 128-byte swizzle.
+// Encoding a tensor map costs a few microseconds of host time and a step issues ~400 of them with a few dozen
+// distinct (pointer, shape) keys: keep a small direct-mapped cache (host-only, one host thread per device).
+struct MapCacheEntry { const void* base; uint64_t rows, cols, ld; uint32_t bc, br; CUtensorMap map; };
+static inline int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                uint32_t box_cols, uint32_t box_rows);
+static inline int make_map_bf16_cached(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                                       uint32_t box_cols, uint32_t box_rows) {
+  static MapCacheEntry cache[256];
+  uint64_t h = ((uintptr_t)base >> 8) * 0x9E3779B97F4A7C15ull ^ (rows * 31 + cols * 131 + ld * 7 + box_cols + 3 * box_rows);
+  MapCacheEntry& e = cache[(h >> 32) & 255];
+  if (e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.bc == box_cols && e.br == box_rows) {
+    *m = e.map;
+    return 0;
+  }
+  int r = make_map_bf16(m, base, rows, cols, ld, box_cols, box_rows);
+  if (r == 0) { e.base = base; e.rows = rows; e.cols = cols; e.ld = ld; e.bc = box_cols; e.br = box_rows; e.map = *m; }
+  return r;
+}
 static inline int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                                 uint32_t box_cols, uint32_t box_rows) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -154,12 +172,28 @@ struct TcCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;                 // per-warp 32x33 fp32 transpose buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
+// TMEM -> registers gives every thread one ROW (32 consecutive columns).  Writing that out directly would make each
+// warp store touch 32 different rows.  The 32x32 block is therefore transposed through a padded shared-memory tile so
+// that in the epilogue functor lane <-> column: every global access of the functor is one coalesced row segment.
+template <typename F>
+__device__ __forceinline__ void epilogue_block_transposed(float* stage /*[32][33]*/, const uint32_t (&r)[32], int lane,
+                                                          int row0, int nrows_valid, int col0, int ncols_valid, F&& f) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+  __syncwarp();
+  if (lane < ncols_valid) {
+    for (int i = 0; i < nrows_valid; ++i) f(row0 + i, col0 + lane, stage[i * 33 + lane]);
+  }
+  __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------ NT kernel
-// Epilogue: epi(row, col, float4) for col % 4 == 0, row < M, col < N.
+// Epilogue: epi.one(row, col, value) for row < M, col < N; consecutive lanes hold consecutive columns.
 template <int BN, int NPROD, typename Epi>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
@@ -170,6 +204,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
 
@@ -237,20 +272,18 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const int row = m0 + q * 32 + lane;
+    const int row0 = m0 + q * 32;
+    const int nrows = min(32, M - row0);
+    float* stage = epi_stage + (warp - 2) * 32 * 33;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = n0 + c * 32;
+      if (col0 >= N) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      if (row < M) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          int col = n0 + c * 32 + j * 4;
-          if (col < N)
-            epi(row, col, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-        }
-      }
+      if (nrows > 0)
+        epilogue_block_transposed(stage, r, lane, row0, nrows, col0, min(32, N - col0),
+                                  [&](int rr, int cc, float v) { epi.one(rr, cc, v); });
     }
   }
   tc_fence_before();
@@ -266,11 +299,11 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
                                        const Epi& epi) {
   using Cfg = TcCfg<BN, NPROD>;
   CUtensorMap mAh, mAl, mBh, mBl;
-  AVC_TRY(make_map_bf16(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
-  AVC_TRY(make_map_bf16(&mBh, B.hi, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
+  AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
+  AVC_TRY(make_map_bf16_cached(&mBh, B.hi, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
   if (NPROD == 3) {
-    AVC_TRY(make_map_bf16(&mAl, A.lo, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
-    AVC_TRY(make_map_bf16(&mBl, B.lo, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
+    AVC_TRY(make_map_bf16_cached(&mAl, A.lo, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
+    AVC_TRY(make_map_bf16_cached(&mBl, B.lo, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
   } else {
     mAl = mAh; mBl = mBh;
   }
@@ -310,7 +343,8 @@ struct TcTnCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
@@ -324,6 +358,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
 
@@ -399,18 +434,18 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const int q = warp & 3;
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const int gi = i0 + q * 32 + lane;
+    const int row0 = i0 + q * 32;
+    const int nrows = min(32, N1 - row0);
+    float* stage = epi_stage + (warp - 2) * 32 * 33;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
+      const int col0 = j0 + c * 32;
+      if (col0 >= N2) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      if (gi < N1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          int gj = j0 + c * 32 + j;
-          if (gj < N2) atomicAdd(C + (size_t)gi * ldc + gj, __uint_as_float(r[j]));
-        }
-      }
+      if (nrows > 0)
+        epilogue_block_transposed(stage, r, lane, row0, nrows, col0, min(32, N2 - col0),
+                                  [&](int rr, int cc, float v) { atomicAdd(C + (size_t)rr * ldc + cc, v); });
     }
   }
   tc_fence_before();
@@ -427,18 +462,16 @@ static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, 
                                     float* C, int ldc) {
   if (P <= 0 || N1 <= 0 || N2 <= 0) return 0;
   CUtensorMap mAh, mAl, mBh, mBl;
-  AVC_TRY(make_map_bf16(&mAh, A.hi, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
-  AVC_TRY(make_map_bf16(&mBh, B.hi, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
+  AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
+  AVC_TRY(make_map_bf16_cached(&mBh, B.hi, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
   if (NPROD == 3) {
-    AVC_TRY(make_map_bf16(&mAl, A.lo, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
-    AVC_TRY(make_map_bf16(&mBl, B.lo, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
+    AVC_TRY(make_map_bf16_cached(&mAl, A.lo, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
+    AVC_TRY(make_map_bf16_cached(&mBl, B.lo, (uint64_t)P, (uint64_t)N2, (uint64_t)B.ld, 64, kBK));
   } else {
     mAl = mAh; mBl = mBh;
   }
   const int t1 = ceil_div(N1, kBM);
   auto go = [&](auto kern, int BN, int smem) -> int {
-    static bool attr_set = false;
-    (void)attr_set;
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int t2 = ceil_div(N2, BN);
     int splits = (148 + t1 * t2 - 1) / (t1 * t2);

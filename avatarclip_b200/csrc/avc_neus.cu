@@ -299,14 +299,14 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
 template <int NI>
 int thin_tn(cudaStream_t st, const float* S, int lds, float s_scale, const float* Hm, int ldh, int NC, int64_t P,
             float* out, int si, int sc, float* bout) {
-  const int rows = 1024;
+  const int rows = 128;
   k_thin_tn<NI><<<blocks_for(P, rows), 256, 0, st>>>(S, lds, s_scale, Hm, ldh, NC, P, rows, out, si, sc, bout);
   AVC_LAUNCH_TRY();
   return 0;
 }
 
 int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float scale, float* out) {
-  const int rows = 512;
+  const int rows = 64;
   k_colsum<<<blocks_for(P, rows), 256, 0, st>>>(X, ld, NC, P, rows, scale, out);
   AVC_LAUNCH_TRY();
   return 0;

@@ -411,9 +411,14 @@ k_colsum(const float* __restrict__ X, int ld, int NC, int64_t P, int rows_per_bl
   const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t p1 = min(P, p0 + (int64_t)rows_per_block);
   for (int c = threadIdx.x; c < NC; c += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t p = p0; p < p1; ++p) acc += X[(size_t)p * ld + c];
-    atomicAdd(out + c, acc * scale);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int64_t p = p0;
+    for (; p + 3 < p1; p += 4) {
+      a0 += X[(size_t)p * ld + c]; a1 += X[(size_t)(p + 1) * ld + c];
+      a2 += X[(size_t)(p + 2) * ld + c]; a3 += X[(size_t)(p + 3) * ld + c];
+    }
+    for (; p < p1; ++p) a0 += X[(size_t)p * ld + c];
+    atomicAdd(out + c, (a0 + a1 + a2 + a3) * scale);
   }
 }
 
@@ -533,6 +538,14 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
 // value chain: z = acc + b ; Z[row] = z (padding zero) ; OUT[row][col] = softplus(z) * oscale (col < N)
 struct EpiValue {
   const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
+  // scalar form used by the tcgen05 epilogue (lane <-> column: coalesced rows)
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    float z = a + bias[col];
+    if (Z) Z[(size_t)row * ldz + col] = z;
+    float h = softplus100(z) * oscale;
+    OUT[(size_t)row * ldo + col] = h;
+    split16_put(o16, (size_t)row, col, h);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float zz[4], hh[4];
@@ -555,6 +568,11 @@ struct EpiValue {
 // out = acc + b (feature rows of the last SDF linear)
 struct EpiBias {
   const float* bias; float* OUT; int ldo; int N; Split16 o16;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    float v = a + bias[col];
+    OUT[(size_t)row * ldo + col] = v;
+    split16_put(o16, (size_t)row, col, v);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
@@ -568,6 +586,17 @@ struct EpiBias {
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
 struct EpiChain {
   int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16;
+  __device__ __forceinline__ void one(int row, int c, float a) const {
+    if (c < Nprev) {
+      float qv = softplus100_d1(Zprev[(size_t)row * Npp + c]) * a * s;
+      QTprev[(size_t)row * Npp + c] = qv;
+      split16_put(q16, (size_t)row, c, qv);
+    } else {
+      if (c < Npp) { QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
+      int e = c - Nprev;
+      if (e < E) GE[(size_t)row * EP + e] += a * kSqrtHalf;
+    }
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
@@ -589,6 +618,9 @@ struct EpiChain {
 // gradient chain, layer 0: ge += acc  (width E)
 struct EpiGe {
   float* GE; int EP; int E;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    if (col < E) GE[(size_t)row * EP + col] += a;
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
@@ -600,6 +632,18 @@ struct EpiGe {
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
 struct EpiColor0 {
   const float* bias; const float* cin; const float* Wx; float* OUT; int ldo; Split16 o16;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
+    const float4 c1 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4);
+    const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8);
+    const float4 w1 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8 + 4);
+    float z = a + bias[col];
+    z = fmaf(c0.x, w0.x, z); z = fmaf(c0.y, w0.y, z); z = fmaf(c0.z, w0.z, z);
+    z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
+    z = fmaxf(z, 0.f);
+    OUT[(size_t)row * ldo + col] = z;
+    split16_put(o16, (size_t)row, col, z);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
@@ -620,6 +664,11 @@ struct EpiColor0 {
 
 struct EpiRelu {
   const float* bias; float* OUT; int ldo; Split16 o16;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    float v = fmaxf(a + bias[col], 0.f);
+    OUT[(size_t)row * ldo + col] = v;
+    split16_put(o16, (size_t)row, col, v);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
@@ -632,6 +681,11 @@ struct EpiRelu {
 // colour dgrad: out = acc * [h > 0]
 struct EpiDgradRelu {
   const float* Hm; float* OUT; int ld; Split16 o16;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    float v = Hm[(size_t)row * ld + col] > 0.f ? a : 0.f;
+    OUT[(size_t)row * ld + col] = v;
+    split16_put(o16, (size_t)row, col, v);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     const float4 h = *reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col);
@@ -643,6 +697,10 @@ struct EpiDgradRelu {
 
 struct EpiStore {
   float* OUT; int ldo; int N; Split16 o16;
+  __device__ __forceinline__ void one(int row, int col, float a) const {
+    OUT[(size_t)row * ldo + col] = a;
+    split16_put(o16, (size_t)row, col, a);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
@@ -657,6 +715,13 @@ struct EpiStore {
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
   int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
+  __device__ __forceinline__ void one(int row, int c, float a) const {
+    float s1 = softplus100_d1(Z[(size_t)row * Np + c]);
+    float uv = s1 * a * s_next;
+    UNEXT[(size_t)row * ldu + c] = uv;
+    split16_put(u16, (size_t)row, c, uv);
+    ZBAR[(size_t)row * Np + c] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * a;
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float zb[4];
@@ -682,6 +747,15 @@ struct EpiChainBwd {
 struct EpiDgrad {
   int Nprev, Npp; float s; const float* Zprev; float* ZBARprev; const float* sdfbar; const float* wsdf;
   float sdf_inv_scale; Split16 z16;
+  __device__ __forceinline__ void one(int row, int c, float a) const {
+    if (c >= Nprev) return;
+    float ab = a;
+    if (sdfbar) ab = fmaf(sdfbar[row] * sdf_inv_scale, wsdf[c], ab);
+    size_t o = (size_t)row * Npp + c;
+    float zv = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+    ZBARprev[o] = zv;
+    split16_put(z16, (size_t)row, c, zv);
+  }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;

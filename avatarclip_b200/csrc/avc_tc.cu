@@ -6,10 +6,7 @@ using namespace avc;
 namespace {
 struct EpiPlainStore {
   float* C; int ldc; int N;
-  __device__ void operator()(int row, int col, float4 a) const {
-    float v[4] = {a.x, a.y, a.z, a.w};
-    for (int i = 0; i < 4 && col + i < N; ++i) C[(size_t)row * ldc + col + i] = v[i];
-  }
+  __device__ void one(int row, int col, float v) const { C[(size_t)row * ldc + col] = v; }
 };
 }  // namespace
 
