@@ -19,6 +19,7 @@
 #include "avc_common.cuh"
 
 namespace avc {
+struct EpiPre;   // avc_neus_kernels.cuh
 namespace tc {
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -163,7 +164,8 @@ struct SplitPtr {            // two-term bf16 split of an fp32 matrix, both [row
 };
 
 constexpr int kBM = 128, kBK = 64;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 
 template <int BN, int NPROD>
 struct TcCfg {
@@ -172,7 +174,7 @@ struct TcCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;                 // per-warp 32x33 fp32 transpose buffers
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose buffers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
@@ -276,14 +278,32 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const int nrows = min(32, M - row0);
     float* stage = epi_stage + (warp - 2) * 32 * 33;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {     // the two warps of a quarter interleave columns
       const int col0 = n0 + c * 32;
       if (col0 >= N) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      if (nrows > 0)
-        epilogue_block_transposed(stage, r, lane, row0, nrows, col0, min(32, N - col0),
-                                  [&](int rr, int cc, float v) { epi.one(rr, cc, v); });
+      if (nrows > 0) {
+        // transpose through shared memory (lane <-> column), then finish rows in batches of 8 with all the
+        // functor's global loads of a batch in flight together
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int ncols = min(32, N - col0);
+        if (lane < ncols) {
+          const int col = col0 + lane;
+          for (int i0 = 0; i0 < nrows; i0 += 8) {
+            decltype(epi.load(0, 0)) pre[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u < nrows) pre[u] = epi.load(row0 + i0 + u, col);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i0 + u < nrows) epi.one(row0 + i0 + u, col, stage[(i0 + u) * 33 + lane], pre[u]);
+          }
+        }
+        __syncwarp();
+      }
     }
   }
   tc_fence_before();
@@ -343,7 +363,7 @@ struct TcTnCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int EPI_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
@@ -438,7 +458,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const int nrows = min(32, N1 - row0);
     float* stage = epi_stage + (warp - 2) * 32 * 33;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {
       const int col0 = j0 + c * 32;
       if (col0 >= N2) break;
       uint32_t r[32];

@@ -30,6 +30,10 @@ __device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int c
   *reinterpret_cast<uint2*>(s.lo + row * s.ld + col) = *reinterpret_cast<const uint2*>(l);
 }
 
+// Values an epilogue functor needs from global memory for one output element.  The tcgen05 epilogue issues the
+// `load`s of several rows back to back before finishing any of them (memory-level parallelism).
+struct EpiPre { float a, b, c; };
+
 // =============================================================================================
 // Weight packing: W = g * v / ||v||_row  (torch.nn.utils.weight_norm, models/fields.py:65-66,142-143)
 // One block per output row.  Destinations: up to two column segments, each written row-major
@@ -539,11 +543,12 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
 struct EpiValue {
   const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
   // scalar form used by the tcgen05 epilogue (lane <-> column: coalesced rows)
-  __device__ __forceinline__ void one(int row, int col, float a) const {
-    float z = a + bias[col];
+  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
+    float z = a + p.a;
     if (Z) Z[(size_t)row * ldz + col] = z;
     float h = softplus100(z) * oscale;
-    OUT[(size_t)row * ldo + col] = h;
+    if (OUT) OUT[(size_t)row * ldo + col] = h;
     split16_put(o16, (size_t)row, col, h);
   }
   __device__ void operator()(int row, int col, float4 a) const {
@@ -568,8 +573,9 @@ struct EpiValue {
 // out = acc + b (feature rows of the last SDF linear)
 struct EpiBias {
   const float* bias; float* OUT; int ldo; int N; Split16 o16;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
-    float v = a + bias[col];
+  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
+    float v = a + p.a;
     OUT[(size_t)row * ldo + col] = v;
     split16_put(o16, (size_t)row, col, v);
   }
@@ -586,15 +592,21 @@ struct EpiBias {
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
 struct EpiChain {
   int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16;
-  __device__ __forceinline__ void one(int row, int c, float a) const {
+  __device__ __forceinline__ EpiPre load(int row, int c) const {
+    EpiPre p = {0.f, 0.f, 0.f};
+    if (c < Nprev) p.a = Zprev[(size_t)row * Npp + c];
+    else if (c - Nprev < E) p.b = GE[(size_t)row * EP + (c - Nprev)];
+    return p;
+  }
+  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
     if (c < Nprev) {
-      float qv = softplus100_d1(Zprev[(size_t)row * Npp + c]) * a * s;
+      float qv = softplus100_d1(p.a) * a * s;
       QTprev[(size_t)row * Npp + c] = qv;
       split16_put(q16, (size_t)row, c, qv);
     } else {
       if (c < Npp) { QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
       int e = c - Nprev;
-      if (e < E) GE[(size_t)row * EP + e] += a * kSqrtHalf;
+      if (e < E) GE[(size_t)row * EP + e] = p.b + a * kSqrtHalf;
     }
   }
   __device__ void operator()(int row, int col, float4 a) const {
@@ -618,8 +630,11 @@ struct EpiChain {
 // gradient chain, layer 0: ge += acc  (width E)
 struct EpiGe {
   float* GE; int EP; int E;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
-    if (col < E) GE[(size_t)row * EP + col] += a;
+  __device__ __forceinline__ EpiPre load(int row, int col) const {
+    return {col < E ? GE[(size_t)row * EP + col] : 0.f, 0.f, 0.f};
+  }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
+    if (col < E) GE[(size_t)row * EP + col] = p.a + a;
   }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
@@ -632,12 +647,13 @@ struct EpiGe {
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
 struct EpiColor0 {
   const float* bias; const float* cin; const float* Wx; float* OUT; int ldo; Split16 o16;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
+  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
     const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
     const float4 c1 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4);
     const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8);
     const float4 w1 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8 + 4);
-    float z = a + bias[col];
+    float z = a + p.a;
     z = fmaf(c0.x, w0.x, z); z = fmaf(c0.y, w0.y, z); z = fmaf(c0.z, w0.z, z);
     z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
     z = fmaxf(z, 0.f);
@@ -664,8 +680,9 @@ struct EpiColor0 {
 
 struct EpiRelu {
   const float* bias; float* OUT; int ldo; Split16 o16;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
-    float v = fmaxf(a + bias[col], 0.f);
+  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
+    float v = fmaxf(a + p.a, 0.f);
     OUT[(size_t)row * ldo + col] = v;
     split16_put(o16, (size_t)row, col, v);
   }
@@ -681,8 +698,9 @@ struct EpiRelu {
 // colour dgrad: out = acc * [h > 0]
 struct EpiDgradRelu {
   const float* Hm; float* OUT; int ld; Split16 o16;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
-    float v = Hm[(size_t)row * ld + col] > 0.f ? a : 0.f;
+  __device__ __forceinline__ EpiPre load(int row, int col) const { return {Hm[(size_t)row * ld + col], 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
+    float v = p.a > 0.f ? a : 0.f;
     OUT[(size_t)row * ld + col] = v;
     split16_put(o16, (size_t)row, col, v);
   }
@@ -697,7 +715,8 @@ struct EpiDgradRelu {
 
 struct EpiStore {
   float* OUT; int ldo; int N; Split16 o16;
-  __device__ __forceinline__ void one(int row, int col, float a) const {
+  __device__ __forceinline__ EpiPre load(int, int) const { return {0.f, 0.f, 0.f}; }
+  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre&) const {
     OUT[(size_t)row * ldo + col] = a;
     split16_put(o16, (size_t)row, col, a);
   }
@@ -715,12 +734,15 @@ struct EpiStore {
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
   int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
-  __device__ __forceinline__ void one(int row, int c, float a) const {
-    float s1 = softplus100_d1(Z[(size_t)row * Np + c]);
+  __device__ __forceinline__ EpiPre load(int row, int c) const {
+    return {Z[(size_t)row * Np + c], QT[(size_t)row * Np + c], 0.f};
+  }
+  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
+    float s1 = softplus100_d1(p.a);
     float uv = s1 * a * s_next;
     UNEXT[(size_t)row * ldu + c] = uv;
     split16_put(u16, (size_t)row, c, uv);
-    ZBAR[(size_t)row * Np + c] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * a;
+    ZBAR[(size_t)row * Np + c] = kBeta * (1.f - s1) * p.b * a;
   }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
@@ -747,12 +769,19 @@ struct EpiChainBwd {
 struct EpiDgrad {
   int Nprev, Npp; float s; const float* Zprev; float* ZBARprev; const float* sdfbar; const float* wsdf;
   float sdf_inv_scale; Split16 z16;
-  __device__ __forceinline__ void one(int row, int c, float a) const {
+  __device__ __forceinline__ EpiPre load(int row, int c) const {
+    EpiPre p = {0.f, 0.f, 0.f};
+    if (c < Nprev) {
+      size_t o = (size_t)row * Npp + c;
+      p.a = Zprev[o]; p.b = ZBARprev[o];
+      if (sdfbar) p.c = sdfbar[row] * sdf_inv_scale * wsdf[c];
+    }
+    return p;
+  }
+  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
     if (c >= Nprev) return;
-    float ab = a;
-    if (sdfbar) ab = fmaf(sdfbar[row] * sdf_inv_scale, wsdf[c], ab);
     size_t o = (size_t)row * Npp + c;
-    float zv = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+    float zv = fmaf(softplus100_d1(p.a), (a + p.c) * s, p.b);
     ZBARprev[o] = zv;
     split16_put(z16, (size_t)row, c, zv);
   }

@@ -6,7 +6,9 @@ using namespace avc;
 namespace {
 struct EpiPlainStore {
   float* C; int ldc; int N;
-  __device__ void one(int row, int col, float v) const { C[(size_t)row * ldc + col] = v; }
+  struct Pre {};
+  __device__ Pre load(int, int) const { return {}; }
+  __device__ void one(int row, int col, float v, const Pre&) const { C[(size_t)row * ldc + col] = v; }
 };
 }  // namespace
 
