@@ -284,22 +284,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
       if (nrows > 0) {
-        // transpose through shared memory (lane <-> column), then finish rows in batches of 8 with all the
-        // functor's global loads of a batch in flight together
+        // transpose through shared memory, then every lane finishes 4 consecutive columns of one row: a warp pass
+        // covers 4 rows x 32 columns, so the functor's float4 accesses are whole 128-byte row segments
 #pragma unroll
         for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
         __syncwarp();
-        const int ncols = min(32, N - col0);
-        if (lane < ncols) {
-          const int col = col0 + lane;
-          for (int i0 = 0; i0 < nrows; i0 += 8) {
-            decltype(epi.load(0, 0)) pre[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (i0 + u < nrows) pre[u] = epi.load(row0 + i0 + u, col);
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              if (i0 + u < nrows) epi.one(row0 + i0 + u, col, stage[(i0 + u) * 33 + lane], pre[u]);
+        const int cg = (lane & 7) * 4;
+        if (col0 + cg < N) {
+#pragma unroll 2
+          for (int i = lane >> 3; i < nrows; i += 4) {
+            const float* sp = stage + i * 33 + cg;
+            epi(row0 + i, col0 + cg, make_float4(sp[0], sp[1], sp[2], sp[3]));
           }
         }
         __syncwarp();

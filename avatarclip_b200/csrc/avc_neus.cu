@@ -154,7 +154,8 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
     EpiValue e;
     e.bias = pack + d.pk_b;
     e.Z = stash ? w.z[l] : nullptr; e.ldz = d.Np;
-    e.OUT = w.in[l + 1]; e.ldo = pl.sdf[l + 1].Kp;
+    // tcgen05 engine: the fp32 copy of a hidden activation is only read by the thin sdf head (layer L)
+    e.OUT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.in[l + 1]; e.ldo = pl.sdf[l + 1].Kp;
     e.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
     e.N = d.N;
     e.o16 = w.in16[l + 1];

@@ -34,6 +34,14 @@ __device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int c
 // `load`s of several rows back to back before finishing any of them (memory-level parallelism).
 struct EpiPre { float a, b, c; };
 
+// softplus' with SFU exp/div: backward-only epilogues (2 ulp-level error on a gradient factor)
+__device__ __forceinline__ float softplus100_d1_fast(float z) {
+  float bz = z * kBeta;
+  if (bz > kThresh) return 1.0f;
+  float e = __expf(bz);
+  return __fdividef(e, e + 1.0f);
+}
+
 // =============================================================================================
 // Weight packing: W = g * v / ||v||_row  (torch.nn.utils.weight_norm, models/fields.py:65-66,142-143)
 // One block per output row.  Destinations: up to two column segments, each written row-major
@@ -562,10 +570,13 @@ struct EpiValue {
     }
     if (Z) *reinterpret_cast<float4*>(Z + (size_t)row * ldz + col) = make_float4(zz[0], zz[1], zz[2], zz[3]);
     if (col + 3 < N) {
-      *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(hh[0], hh[1], hh[2], hh[3]);
       split16_put4(o16, (size_t)row, col, hh);
     } else {
-      for (int i = 0; i < 4 && col + i < N; ++i) { OUT[(size_t)row * ldo + col + i] = hh[i]; split16_put(o16, (size_t)row, col + i, hh[i]); }
+      for (int i = 0; i < 4 && col + i < N; ++i) {
+        if (OUT) OUT[(size_t)row * ldo + col + i] = hh[i];
+        split16_put(o16, (size_t)row, col + i, hh[i]);
+      }
     }
   }
 };
@@ -611,6 +622,15 @@ struct EpiChain {
   }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
+    if (col + 3 < Nprev) {        // fast path: whole group inside the hidden part
+      const size_t o = (size_t)row * Npp + col;
+      const float4 z = *reinterpret_cast<const float4*>(Zprev + o);
+      float q[4] = {softplus100_d1(z.x) * v[0] * s, softplus100_d1(z.y) * v[1] * s, softplus100_d1(z.z) * v[2] * s,
+                    softplus100_d1(z.w) * v[3] * s};
+      *reinterpret_cast<float4*>(QTprev + o) = make_float4(q[0], q[1], q[2], q[3]);
+      split16_put4(q16, (size_t)row, col, q);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
@@ -746,12 +766,29 @@ struct EpiChainBwd {
   }
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
+    if (col + 3 < N) {
+      const size_t o = (size_t)row * Np + col;
+      const float4 z = *reinterpret_cast<const float4*>(Z + o);
+      const float4 qt = *reinterpret_cast<const float4*>(QT + o);
+      const float zz[4] = {z.x, z.y, z.z, z.w}, qq[4] = {qt.x, qt.y, qt.z, qt.w};
+      float u[4], zb[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float s1 = softplus100_d1_fast(zz[i]);
+        u[i] = s1 * v[i] * s_next;
+        zb[i] = kBeta * (1.f - s1) * qq[i] * v[i];
+      }
+      *reinterpret_cast<float4*>(UNEXT + (size_t)row * ldu + col) = make_float4(u[0], u[1], u[2], u[3]);
+      split16_put4(u16, (size_t)row, col, u);
+      *reinterpret_cast<float4*>(ZBAR + o) = make_float4(zb[0], zb[1], zb[2], zb[3]);
+      return;
+    }
     float zb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
       if (c < N) {
-        float s1 = softplus100_d1(Z[(size_t)row * Np + c]);
+        float s1 = softplus100_d1_fast(Z[(size_t)row * Np + c]);
         float uv = s1 * v[i] * s_next;
         UNEXT[(size_t)row * ldu + c] = uv;
         split16_put(u16, (size_t)row, c, uv);
@@ -788,6 +825,22 @@ struct EpiDgrad {
   __device__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
     float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;
+    if (col + 3 < Nprev) {
+      const size_t o = (size_t)row * Npp + col;
+      const float4 z = *reinterpret_cast<const float4*>(Zprev + o);
+      const float4 zb = *reinterpret_cast<const float4*>(ZBARprev + o);
+      const float zz[4] = {z.x, z.y, z.z, z.w}, zo[4] = {zb.x, zb.y, zb.z, zb.w};
+      float r[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float ab = v[i];
+        if (sdfbar) ab = fmaf(sb, wsdf[col + i], ab);
+        r[i] = fmaf(softplus100_d1_fast(zz[i]), ab * s, zo[i]);
+      }
+      *reinterpret_cast<float4*>(ZBARprev + o) = make_float4(r[0], r[1], r[2], r[3]);
+      split16_put4(z16, (size_t)row, col, r);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
@@ -795,7 +848,7 @@ struct EpiDgrad {
         float ab = v[i];
         if (sdfbar) ab = fmaf(sb, wsdf[c], ab);
         size_t o = (size_t)row * Npp + c;
-        float zv = fmaf(softplus100_d1(Zprev[o]), ab * s, ZBARprev[o]);
+        float zv = fmaf(softplus100_d1_fast(Zprev[o]), ab * s, ZBARprev[o]);
         ZBARprev[o] = zv;
         split16_put(z16, (size_t)row, c, zv);
       }

@@ -6,9 +6,10 @@ using namespace avc;
 namespace {
 struct EpiPlainStore {
   float* C; int ldc; int N;
-  struct Pre {};
-  __device__ Pre load(int, int) const { return {}; }
-  __device__ void one(int row, int col, float v, const Pre&) const { C[(size_t)row * ldc + col] = v; }
+  __device__ void operator()(int row, int col, float4 a) const {
+    float v[4] = {a.x, a.y, a.z, a.w};
+    for (int i = 0; i < 4 && col + i < N; ++i) C[(size_t)row * ldc + col + i] = v[i];
+  }
 };
 }  // namespace
 
