@@ -164,10 +164,8 @@ struct SplitPtr {            // two-term bf16 split of an fp32 matrix, both [row
 };
 
 constexpr int kBM = 128, kBK = 64;
-constexpr int kEpiWarps = 8;        // TN kernel: warps 2-9 (two per TMEM lane quarter), smem-transposed atomics
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-constexpr int kNtEpiWarps = 16;     // NT kernel: warps 2-17 (four per quarter): the epilogue is latency bound, occupancy hides it
-constexpr int kNtThreads = 64 + 32 * kNtEpiWarps;
+constexpr int kTcThreads = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 
 template <int BN, int NPROD>
 struct TcCfg {
@@ -176,7 +174,8 @@ struct TcCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
@@ -198,7 +197,7 @@ __device__ __forceinline__ void epilogue_block_transposed(float* stage /*[32][33
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Epilogue: epi.one(row, col, value) for row < M, col < N; consecutive lanes hold consecutive columns.
 template <int BN, int NPROD, typename Epi>
-__global__ void __launch_bounds__(kNtThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                   int M, int N, int K, Epi epi) {
@@ -275,23 +274,30 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const int q = warp & 3;               // TMEM lane quarter this warp may access
     mbar_wait(tfull, 0);
     tc_fence_after();
-    // lane <-> accumulator row; each thread finishes its 32 consecutive columns as 8 independent float4 groups
-    // (whole 16-byte pieces of one row: sector-efficient stores, 8-way instruction-level parallelism)
-    const int row = m0 + q * 32 + lane;
+    const int row0 = m0 + q * 32;
+    const int nrows = min(32, M - row0);
+    float* stage = epi_stage + (warp - 2) * 32 * 33;
 #pragma unroll 1
-    for (int c = (warp - 2) >> 2; c < BN / 32; c += kNtEpiWarps / 4) {
+    for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {     // the two warps of a quarter interleave columns
       const int col0 = n0 + c * 32;
       if (col0 >= N) break;
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      if (row < M) {
+      if (nrows > 0) {
+        // transpose through shared memory, then every lane finishes 4 consecutive columns of one row: a warp pass
+        // covers 4 rows x 32 columns, so the functor's float4 accesses are whole 128-byte row segments
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = col0 + 4 * j;
-          if (col < N)
-            epi(row, col, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int cg = (lane & 7) * 4;
+        if (col0 + cg < N) {
+#pragma unroll 2
+          for (int i = lane >> 3; i < nrows; i += 4) {
+            const float* sp = stage + i * 33 + cg;
+            epi(row0 + i, col0 + cg, make_float4(sp[0], sp[1], sp[2], sp[3]));
+          }
         }
+        __syncwarp();
       }
     }
   }
@@ -323,7 +329,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
     attr_set = true;
   }
   dim3 grid(ceil_div(M, kBM), ceil_div(N, BN));
-  kern<<<grid, kNtThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
+  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
   AVC_LAUNCH_TRY();
   return 0;
 }
