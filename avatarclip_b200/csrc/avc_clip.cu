@@ -351,7 +351,7 @@ k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __h
 constexpr int AT = 64;   // max tokens
 constexpr int AD = 64;   // head dim
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
   extern __shared__ float sm[];
   float* q = sm;                  // [T][AD+1]
@@ -375,7 +375,7 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int a = warp; a < T; a += 4) {
+  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, S[a * (AT + 1) + c]);
 #pragma unroll
@@ -396,7 +396,7 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
 }
 
 // backward: recompute P; dqkv[M][3W] fp32 from dO[M][W] fp32
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
                 float* __restrict__ dqkv) {
   extern __shared__ float sm[];
@@ -428,7 +428,7 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int a = warp; a < T; a += 4) {
+  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, Pm[a * (AT + 1) + c]);
 #pragma unroll
@@ -493,8 +493,14 @@ k_head_fwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__
   }
   __syncthreads();
   for (int o = threadIdx.x; o < OD; o += blockDim.x) {
-    float a = 0.f;
-    for (int c = 0; c < Wd; ++c) a = fmaf(y[c], proj[(size_t)c * OD + o], a);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 8 loads in flight per thread
+    int c = 0;
+    for (; c + 7 < Wd; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(y[c + u], proj[(size_t)(c + u) * OD + o], acc[u]);
+    }
+    float a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+    for (; c < Wd; ++c) a = fmaf(y[c], proj[(size_t)c * OD + o], a);
     e[o] = a;
     emb[(size_t)b * OD + o] = a;
   }
@@ -545,10 +551,11 @@ k_head_bwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__
     de[o] = d;
   }
   __syncthreads();
-  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+  for (int cc = threadIdx.x >> 5; cc < Wd; cc += (blockDim.x >> 5)) {   // one warp per row of proj: coalesced
     float s = 0.f;
-    for (int o = 0; o < OD; ++o) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
-    dy[cc] = s;
+    for (int o = threadIdx.x & 31; o < OD; o += 32) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) dy[cc] = s;
   }
   __syncthreads();
   // LayerNorm backward on the cls row
@@ -724,7 +731,7 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     AVC_LAUNCH_TRY();
     { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e)); }
-    k_attention<<<B * cfg->heads, 128, attn_fwd_smem, st>>>(qkv, T, Wd, cfg->heads, w.o16);
+    k_attention<<<B * cfg->heads, 512, attn_fwd_smem, st>>>(qkv, T, Wd, cfg->heads, w.o16);
     AVC_LAUNCH_TRY();
     { EpiResidual e{w.x, Wd, lw.b_out};
       AVC_TRY(gemm16(st, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 2, e)); }
@@ -786,7 +793,7 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     AVC_LAUNCH_TRY();
     { EpiStoreUnscale e{w.dO, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_out_t, Wd, M, Wd, Wd, 1, e)); }
-    k_attention_bwd<<<B * cfg->heads, 128, attn_bwd_smem, st>>>(qkv, w.dO, T, Wd, cfg->heads, w.dqkv);
+    k_attention_bwd<<<B * cfg->heads, 512, attn_bwd_smem, st>>>(qkv, w.dO, T, Wd, cfg->heads, w.dqkv);
     AVC_LAUNCH_TRY();
     k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, nullptr);
     AVC_LAUNCH_TRY();

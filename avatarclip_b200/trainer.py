@@ -16,7 +16,7 @@ from typing import Dict, Optional
 
 import torch
 
-from . import _lib, losses
+from . import _lib, dist as avc_dist, losses
 from .renderer import NeuSRenderer, render_backward_raw, render_forward_raw
 from .workload import HostView
 
@@ -107,8 +107,7 @@ class AppearanceTrainer:
         return self.scalars[losses.S_BASE] + ((1.0 - self.cos) * self.clip_weight).sum()
 
     def optimizer_step(self, lr: Optional[float] = None):
-        if self.pg is not None and self.world > 1:
-            torch.distributed.all_reduce(self.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+        avc_dist.allreduce_sum_(self.grad, self.pg)      # the step's only collective (NCCL over NVLink)
         self.iter_step += 1
         b1, b2 = self.betas
         _lib.check(_lib.lib().avc_adam_step(_lib.ptr(self.fp.flat), _lib.ptr(self.grad), _lib.ptr(self.exp_avg),

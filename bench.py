@@ -391,7 +391,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--engine", type=int, default=int(os.environ.get("AVC_ENGINE", "0")))
+    ap.add_argument("--engine", type=int, default=int(os.environ.get("AVC_ENGINE", "1")),
+                    help="MLP contraction engine: 1 = tcgen05 split-bf16 tiles (default), 0 = fp32 FFMA tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rays", type=int, default=64)
     args = ap.parse_args()

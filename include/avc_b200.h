@@ -254,6 +254,19 @@ int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   avc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * SMPL linear-blend skinning: my_lbs(v_shaped, pose, v_template, shapedirs, posedirs, J_regressor, parents,
+ * lbs_weights, pose2rot) of models/utils.py:176-224 (batch 1; v_template / shapedirs are unused by the reference
+ * function and therefore absent here).  pose: [n_joints*3] axis-angle when pose2rot != 0, else [n_joints][3][3]
+ * rotation matrices.  posedirs: [(n_joints-1)*9][V*3].  lbs_weights: [V][n_joints].  n_joints <= 32.
+ * Outputs: verts_out [V][3], joints_out [n_joints][3] (J_transformed).
+ * ------------------------------------------------------------------------------------------ */
+int avc_lbs_workspace_bytes(int32_t n_joints, size_t* bytes);
+int avc_lbs_fwd(const float* v_shaped, const float* pose, int32_t pose2rot, const float* J_regressor,
+                const int32_t* parents, const float* posedirs, const float* lbs_weights, int32_t V,
+                int32_t n_joints, float* verts_out, float* joints_out, void* workspace,
+                size_t workspace_bytes, avc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self-test of the tcgen05 GEMM tiles (engine 1): C[M][N] = A[M][K] . B[N][K]^T, fp32 in/out, operands
  * split into bf16 (hi, lo) pairs; nprod = 1 (hi*hi only) or 3 (hi*hi + hi*lo + lo*hi).
  * workspace >= 4 * (M + N) * round_up(K, 8) + 1024 bytes.

@@ -51,3 +51,12 @@ def test_sample_placement_matches_reference(name):
     dz = (z - b["z_vals"]).abs().max(dim=1)[0]
     assert (dz < 1e-4).float().mean().item() >= 0.95
     assert torch.all(z[:, 1:] >= z[:, :-1])
+
+
+def test_lbs_restatement_matches_reference_golden():
+    """oracle.lbs.my_lbs vs the vector recorded from the reference's own my_lbs (oracle/pin_lbs.py)."""
+    from oracle import lbs
+    g = torch.load(os.path.join(GOLDEN, "lbs_small.pt"), map_location="cpu", weights_only=False)
+    v, j = lbs.my_lbs(**g["inputs"])
+    assert (v - g["verts"]).abs().max().item() < 1e-6
+    assert (j - g["joints"]).abs().max().item() < 1e-6
