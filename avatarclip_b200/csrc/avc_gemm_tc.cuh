@@ -89,6 +89,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
 // | layout type [61,64) (2 = SWIZZLE_128B).
@@ -164,8 +175,10 @@ struct SplitPtr {            // two-term bf16 split of an fp32 matrix, both [row
 };
 
 constexpr int kBM = 128, kBK = 64;
-constexpr int kTcThreads = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int kTcThreads = 320;   // TN kernel: warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
+constexpr int kNtEpiWarps = 16;   // NT kernel: warps 2-17 (four per quarter): the epilogue is issue/latency bound
+constexpr int kNtThreads = 64 + 32 * kNtEpiWarps;
 
 template <int BN, int NPROD>
 struct TcCfg {
@@ -174,7 +187,7 @@ struct TcCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;         // per-warp 32x33 fp32 transpose buffers
+  static constexpr int EPI_BYTES = kNtEpiWarps * 32 * 16 * 4;       // per-warp 32x16 fp32 transpose buffers (XOR-swizzled)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
@@ -197,7 +210,7 @@ __device__ __forceinline__ void epilogue_block_transposed(float* stage /*[32][33
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Epilogue: epi.one(row, col, value) for row < M, col < N; consecutive lanes hold consecutive columns.
 template <int BN, int NPROD, typename Epi>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kNtThreads, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                   int M, int N, int K, Epi epi) {
@@ -276,25 +289,27 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     tc_fence_after();
     const int row0 = m0 + q * 32;
     const int nrows = min(32, M - row0);
-    float* stage = epi_stage + (warp - 2) * 32 * 33;
+    float* stage = epi_stage + (warp - 2) * 32 * 16;
+    // the four warps of a TMEM lane quarter interleave 16-column sub-blocks; every sub-block is transposed through a
+    // padded shared-memory tile so that one warp pass covers 8 rows x 16 columns: the functor's float4 accesses are
+    // 64-byte row segments (whole sectors), 4 passes per sub-block
 #pragma unroll 1
-    for (int c = (warp - 2) >> 2; c < BN / 32; c += kEpiWarps / 4) {     // the two warps of a quarter interleave columns
-      const int col0 = n0 + c * 32;
+    for (int c = (warp - 2) >> 2; c < BN / 16; c += kNtEpiWarps / 4) {
+      const int col0 = n0 + c * 16;
       if (col0 >= N) break;
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
       if (nrows > 0) {
-        // transpose through shared memory, then every lane finishes 4 consecutive columns of one row: a warp pass
-        // covers 4 rows x 32 columns, so the functor's float4 accesses are whole 128-byte row segments
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j) stage[lane * 16 + (j ^ ((lane >> 1) & 15))] = __uint_as_float(r[j]);   // conflict-free
         __syncwarp();
-        const int cg = (lane & 7) * 4;
+        const int cg = (lane & 3) * 4;
         if (col0 + cg < N) {
 #pragma unroll 2
-          for (int i = lane >> 3; i < nrows; i += 4) {
-            const float* sp = stage + i * 33 + cg;
-            epi(row0 + i, col0 + cg, make_float4(sp[0], sp[1], sp[2], sp[3]));
+          for (int i = lane >> 2; i < nrows; i += 8) {
+            const float* sp = stage + i * 16;
+            const int sw = (i >> 1) & 15;
+            epi(row0 + i, col0 + cg, make_float4(sp[cg ^ sw], sp[(cg + 1) ^ sw], sp[(cg + 2) ^ sw], sp[(cg + 3) ^ sw]));
           }
         }
         __syncwarp();
@@ -329,7 +344,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
     attr_set = true;
   }
   dim3 grid(ceil_div(M, kBM), ceil_div(N, BN));
-  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
+  kern<<<grid, kNtThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
   AVC_LAUNCH_TRY();
   return 0;
 }

@@ -159,6 +159,7 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
     e.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
     e.N = d.N;
     e.o16 = w.in16[l + 1];
+    e.fast = pl.cfg.engine == 1;
     AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, e));
   }
   const LinDim& dl = pl.sdf[pl.L];
@@ -259,6 +260,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
       e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
       e.Zprev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
       e.q16 = w.qt16[l - 1];
+      e.fast = pl.cfg.engine == 1;
       AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
     }
     const LinDim& d0 = pl.sdf[0];

@@ -34,7 +34,13 @@ __device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int c
 // `load`s of several rows back to back before finishing any of them (memory-level parallelism).
 struct EpiPre { float a, b, c; };
 
-// softplus' with SFU exp/div: backward-only epilogues (2 ulp-level error on a gradient factor)
+// SFU (ex2/lg2.approx based) softplus for the tcgen05 engine's epilogues, which are instruction-issue bound:
+// |error| <~ 1e-8 absolute on softplus (value / 100), ~2 ulp on softplus'.  The fp32 engine keeps libm accuracy.
+__device__ __forceinline__ float softplus100_fast(float z) {
+  float bz = z * kBeta;
+  return bz > kThresh ? z : __logf(1.0f + __expf(bz)) * (1.0f / kBeta);
+}
+// softplus' with SFU exp/div
 __device__ __forceinline__ float softplus100_d1_fast(float z) {
   float bz = z * kBeta;
   if (bz > kThresh) return 1.0f;
@@ -549,7 +555,7 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
 
 // value chain: z = acc + b ; Z[row] = z (padding zero) ; OUT[row][col] = softplus(z) * oscale (col < N)
 struct EpiValue {
-  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
+  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16; int fast;
   // scalar form used by the tcgen05 epilogue (lane <-> column: coalesced rows)
   __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
   __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
@@ -566,7 +572,7 @@ struct EpiValue {
     for (int i = 0; i < 4; ++i) {
       bool ok = col + i < N;
       zz[i] = ok ? v[i] + bias[col + i] : 0.f;
-      hh[i] = softplus100(zz[i]) * oscale;
+      hh[i] = (fast ? softplus100_fast(zz[i]) : softplus100(zz[i])) * oscale;
     }
     if (Z) *reinterpret_cast<float4*>(Z + (size_t)row * ldz + col) = make_float4(zz[0], zz[1], zz[2], zz[3]);
     if (col + 3 < N) {
@@ -602,7 +608,7 @@ struct EpiBias {
 // gradient chain, layer l >= 1: u = acc (width K_l).  Columns < Nprev: ua = u * s, qt_prev = sp'(z_prev) * ua;
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
 struct EpiChain {
-  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16;
+  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16; int fast;
   __device__ __forceinline__ EpiPre load(int row, int c) const {
     EpiPre p = {0.f, 0.f, 0.f};
     if (c < Nprev) p.a = Zprev[(size_t)row * Npp + c];
@@ -625,8 +631,14 @@ struct EpiChain {
     if (col + 3 < Nprev) {        // fast path: whole group inside the hidden part
       const size_t o = (size_t)row * Npp + col;
       const float4 z = *reinterpret_cast<const float4*>(Zprev + o);
-      float q[4] = {softplus100_d1(z.x) * v[0] * s, softplus100_d1(z.y) * v[1] * s, softplus100_d1(z.z) * v[2] * s,
-                    softplus100_d1(z.w) * v[3] * s};
+      float q[4];
+      if (fast) {
+        q[0] = softplus100_d1_fast(z.x) * v[0] * s; q[1] = softplus100_d1_fast(z.y) * v[1] * s;
+        q[2] = softplus100_d1_fast(z.z) * v[2] * s; q[3] = softplus100_d1_fast(z.w) * v[3] * s;
+      } else {
+        q[0] = softplus100_d1(z.x) * v[0] * s; q[1] = softplus100_d1(z.y) * v[1] * s;
+        q[2] = softplus100_d1(z.z) * v[2] * s; q[3] = softplus100_d1(z.w) * v[3] * s;
+      }
       *reinterpret_cast<float4*>(QTprev + o) = make_float4(q[0], q[1], q[2], q[3]);
       split16_put4(q16, (size_t)row, col, q);
       return;
