@@ -209,6 +209,13 @@ __device__ __forceinline__ void epilogue_block_transposed(float* stage /*[32][33
 
 // ------------------------------------------------------------------------------------------------ NT kernel
 // Epilogue: epi.one(row, col, value) for row < M, col < N; consecutive lanes hold consecutive columns.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: gridDim.x CTAs (<= one per SM) walk the output tiles t = blockIdx.x, +gridDim.x, ...  The accumulator
+// is double buffered in TMEM (2 x BN columns) so the epilogue of tile i runs while the TMA/MMA warps already work
+// on tile i+1:  tfull[b] (MMA -> epilogue, tcgen05.commit)  /  tempty[b] (epilogue -> MMA, one arrive per warp).
 template <int BN, int NPROD, typename Epi>
 __global__ void __launch_bounds__(kNtThreads, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
@@ -218,23 +225,25 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
   float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull0 = empty0 + 8 * Cfg::STAGES,
+                 tempty0 = tfull0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int ntiles = ((M + kBM - 1) / kBM) * tiles_n;
   const int nk = (K + kBK - 1) / kBK;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
     if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, kNtEpiWarps); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -242,16 +251,20 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        mbar_wait(empty0 + 8 * s, ((kb / Cfg::STAGES) & 1) ^ 1);
-        const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
-        tma_load_2d(st, &mapAhi, kb * kBK, m0, full0 + 8 * s);
-        tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES, &mapBhi, kb * kBK, n0, full0 + 8 * s);
-        if (NPROD == 3) {
-          tma_load_2d(st + Cfg::A_BYTES, &mapAlo, kb * kBK, m0, full0 + 8 * s);
-          tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, full0 + 8 * s);
+      int it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          mbar_wait(empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
+          const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
+          tma_load_2d(st, &mapAhi, kb * kBK, m0, full0 + 8 * s);
+          tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES, &mapBhi, kb * kBK, n0, full0 + 8 * s);
+          if (NPROD == 3) {
+            tma_load_2d(st + Cfg::A_BYTES, &mapAlo, kb * kBK, m0, full0 + 8 * s);
+            tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, full0 + 8 * s);
+          }
         }
       }
     }
@@ -259,68 +272,83 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1;
+        mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
-        const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % Cfg::STAGES;
+          mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+          const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
-        for (int k4 = 0; k4 < kBK / 16; ++k4) {
-          // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B
-          const uint64_t dah = make_smem_desc(a_hi + k4 * 32, 0, 1024);
-          const uint64_t dbh = make_smem_desc(b_hi + k4 * 32, 0, 1024);
-          umma_f16(tmem_base, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
-          if (NPROD == 3) {
-            const uint64_t dal = make_smem_desc(a_lo + k4 * 32, 0, 1024);
-            const uint64_t dbl = make_smem_desc(b_lo + k4 * 32, 0, 1024);
-            umma_f16(tmem_base, dah, dbl, idesc, 1u);
-            umma_f16(tmem_base, dal, dbh, idesc, 1u);
+          for (int k4 = 0; k4 < kBK / 16; ++k4) {
+            // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B
+            const uint64_t dah = make_smem_desc(a_hi + k4 * 32, 0, 1024);
+            const uint64_t dbh = make_smem_desc(b_hi + k4 * 32, 0, 1024);
+            umma_f16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+            if (NPROD == 3) {
+              const uint64_t dal = make_smem_desc(a_lo + k4 * 32, 0, 1024);
+              const uint64_t dbl = make_smem_desc(b_lo + k4 * 32, 0, 1024);
+              umma_f16(d_tmem, dah, dbl, idesc, 1u);
+              umma_f16(d_tmem, dal, dbh, idesc, 1u);
+            }
           }
+          umma_commit(empty0 + 8 * s);      // frees this smem stage once the MMAs above have read it
         }
-        umma_commit(empty0 + 8 * s);      // frees this smem stage once the MMAs above have read it
+        umma_commit(tfull0 + 8 * buf);      // accumulator complete
       }
-      umma_commit(tfull);                 // accumulator complete
     }
     __syncwarp();
   } else {
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-    const int row0 = m0 + q * 32;
-    const int nrows = min(32, M - row0);
     float* stage = epi_stage + (warp - 2) * 32 * 16;
-    // the four warps of a TMEM lane quarter interleave 16-column sub-blocks; every sub-block is transposed through a
-    // padded shared-memory tile so that one warp pass covers 8 rows x 16 columns: the functor's float4 accesses are
-    // 64-byte row segments (whole sectors), 4 passes per sub-block
+    int lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      const uint32_t buf = lt & 1;
+      mbar_wait(tfull0 + 8 * buf, (lt >> 1) & 1);
+      tc_fence_after();
+      const int row0 = m0 + q * 32;
+      const int nrows = min(32, M - row0);
+      // the four warps of a TMEM lane quarter interleave 16-column sub-blocks; every sub-block is transposed through a
+      // swizzled shared-memory tile so that one warp pass covers 8 rows x 16 columns: the functor's float4 accesses
+      // are 64-byte row segments (whole sectors), 4 passes per sub-block
 #pragma unroll 1
-    for (int c = (warp - 2) >> 2; c < BN / 16; c += kNtEpiWarps / 4) {
-      const int col0 = n0 + c * 16;
-      if (col0 >= N) break;
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
-      if (nrows > 0) {
+      for (int c = (warp - 2) >> 2; c < BN / 16; c += kNtEpiWarps / 4) {
+        const int col0 = n0 + c * 16;
+        if (col0 >= N) break;
+        uint32_t r[16];
+        tmem_ld16(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
+        if (nrows > 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) stage[lane * 16 + (j ^ ((lane >> 1) & 15))] = __uint_as_float(r[j]);   // conflict-free
-        __syncwarp();
-        const int cg = (lane & 3) * 4;
-        if (col0 + cg < N) {
+          for (int j = 0; j < 16; ++j) stage[lane * 16 + (j ^ ((lane >> 1) & 15))] = __uint_as_float(r[j]);   // conflict-free
+          __syncwarp();
+          const int cg = (lane & 3) * 4;
+          if (col0 + cg < N) {
 #pragma unroll 2
-          for (int i = lane >> 2; i < nrows; i += 8) {
-            const float* sp = stage + i * 16;
-            const int sw = (i >> 1) & 15;
-            epi(row0 + i, col0 + cg, make_float4(sp[cg ^ sw], sp[(cg + 1) ^ sw], sp[(cg + 2) ^ sw], sp[(cg + 3) ^ sw]));
+            for (int i = lane >> 2; i < nrows; i += 8) {
+              const float* sp = stage + i * 16;
+              const int sw = (i >> 1) & 15;
+              epi(row0 + i, col0 + cg, make_float4(sp[cg ^ sw], sp[(cg + 1) ^ sw], sp[(cg + 2) ^ sw], sp[(cg + 3) ^ sw]));
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * buf);    // this warp no longer reads accumulator `buf`
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -343,7 +371,14 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid(ceil_div(M, kBM), ceil_div(N, BN));
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    AVC_CUDA_TRY(cudaGetDevice(&dev));
+    AVC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ntiles = ceil_div(M, kBM) * ceil_div(N, BN);
+  dim3 grid(ntiles < num_sms ? ntiles : num_sms);      // persistent: at most one CTA per SM
   kern<<<grid, kNtThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
   AVC_LAUNCH_TRY();
   return 0;
