@@ -23,7 +23,8 @@ namespace {
 // CTA: 128 threads, tile 64 x 32, BK = 64, 3-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
 // Epilogue functor: epi(row, col, v0, v1, ksplit_index) for two consecutive columns.
 // ------------------------------------------------------------------------------------------------
-constexpr int GBM = 64, GBN = 32, GBK = 64, GST = 3, GPAD = 8;
+constexpr int GBM = 64, GBN = 32, GBK = 64, GST = 6, GPAD = 8;
+constexpr int G_SMEM = GST * (GBM + GBN) * (GBK + GPAD) * 2;   // 82,944 B of dynamic shared memory
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -38,8 +39,10 @@ template <typename Epi>
 __global__ void __launch_bounds__(128)
 k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
          int k_per_split, Epi epi) {
-  __shared__ __align__(16) __half sA[GST][GBM][GBK + GPAD];
-  __shared__ __align__(16) __half sW[GST][GBN][GBK + GPAD];
+  extern __shared__ __align__(16) unsigned char g_smem[];
+  __half (*sA)[GBM][GBK + GPAD] = reinterpret_cast<__half (*)[GBM][GBK + GPAD]>(g_smem);
+  __half (*sW)[GBN][GBK + GPAD] =
+      reinterpret_cast<__half (*)[GBN][GBK + GPAD]>(g_smem + (size_t)GST * GBM * (GBK + GPAD) * 2);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM;
   const int kb = blockIdx.z * k_per_split;
@@ -124,19 +127,24 @@ int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw,
   int kper = (int)round_up(ceil_div(K, ksplit), GBK);
   ksplit = ceil_div(K, kper);
   dim3 grid(N / GBN, ceil_div(M, GBM), ksplit);
-  k_gemm16<Epi><<<grid, 128, 0, st>>>(A, lda, Wt, ldw, M, N, K, kper, epi);
+  static bool attr_set = false;      // per epilogue instantiation
+  if (!attr_set) {
+    AVC_CUDA_TRY(cudaFuncSetAttribute(k_gemm16<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    attr_set = true;
+  }
+  k_gemm16<Epi><<<grid, 128, G_SMEM, st>>>(A, lda, Wt, ldw, M, N, K, kper, epi);
   AVC_LAUNCH_TRY();
   return 0;
 }
 
 // ---- epilogues -----------------------------------------------------------------------------------
-struct EpiPatch {   // token row b*T + 1 + p  <-  acc + positional_embedding[1+p]
-  float* x; const float* pos; int T, Wd, np;
+struct EpiPatch {   // token row b*T + 1 + p  +=  acc   (rows pre-initialised with the positional embedding; split-K)
+  float* x; int T, Wd, np;
   __device__ void operator()(int row, int col, float v0, float v1, int) const {
     int b = row / np, p = row - b * np;
     size_t o = ((size_t)b * T + 1 + p) * Wd + col;
-    x[o] = v0 + pos[(size_t)(1 + p) * Wd + col];
-    x[o + 1] = v1 + pos[(size_t)(1 + p) * Wd + col + 1];
+    atomicAdd(x + o, v0);
+    atomicAdd(x + o + 1, v1);
   }
 };
 struct EpiBiasStore {   // out = acc + b
@@ -259,12 +267,13 @@ __global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W,
   add(ty.i1, tx.i1, ty.l * tx.l);
 }
 
+// token buffer initialisation: row 0 = class_embedding + pos[0], rows 1.. = pos[t] (the patch GEMM adds onto them)
 __global__ void k_cls_rows(const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
                            float* __restrict__ x) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * Wd) return;
-  int b = i / Wd, c = i - b * Wd;
-  x[(size_t)b * T * Wd + c] = cls[c] + pos[c];
+  if (i >= B * T * Wd) return;
+  int c = i % Wd, t = (i / Wd) % T;
+  x[i] = pos[(size_t)t * Wd + c] + (t == 0 ? cls[c] : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,55 +468,67 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
 // ------------------------------------------------------------------------------------------------
 // Head: ln_post(x[b,0]) @ proj -> emb ; cosine with the text embedding.  One CTA per image.
 // ------------------------------------------------------------------------------------------------
+// ln_post(x[b,0]) @ proj: grid (B, OD/64); every CTA recomputes the (cheap) LayerNorm of the cls row and produces 64
+// outputs, each from 4 partial dots over a quarter of the 768 inputs.
 __global__ void __launch_bounds__(256)
-k_head_fwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
-           const float* __restrict__ proj, int OD, const float* __restrict__ text, float* __restrict__ emb,
-           float* __restrict__ cos_out, float* __restrict__ ynorm) {
+k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
+            const float* __restrict__ proj, int OD, float* __restrict__ emb, float* __restrict__ ynorm) {
   extern __shared__ float sm[];
-  float* y = sm;             // [Wd]
-  float* e = y + Wd;         // [OD]
-  __shared__ float red[3][8];
+  float* y = sm;               // [Wd]
+  float* part = y + Wd;        // [4][64]
+  __shared__ float red[8];
   const int b = blockIdx.x;
   const float* xr = x + (size_t)b * T * Wd;
   float s = 0.f;
   for (int c = threadIdx.x; c < Wd; c += blockDim.x) s += xr[c];
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   float mean = 0.f;
-  for (int i = 0; i < 8; ++i) mean += red[0][i];
+  for (int i = 0; i < 8; ++i) mean += red[i];
   mean /= (float)Wd;
   float v = 0.f;
   for (int c = threadIdx.x; c < Wd; c += blockDim.x) { float d = xr[c] - mean; v += d * d; }
   v = warp_sum(v);
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = v;
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float var = 0.f;
-  for (int i = 0; i < 8; ++i) var += red[0][i];
+  for (int i = 0; i < 8; ++i) var += red[i];
   float rstd = rsqrtf(var / (float)Wd + 1e-5f);
   for (int c = threadIdx.x; c < Wd; c += blockDim.x) {
     float yy = (xr[c] - mean) * rstd * g[c] + bta[c];
     y[c] = yy;
-    ynorm[(size_t)b * Wd + c] = yy;
+    if (blockIdx.y == 0) ynorm[(size_t)b * Wd + c] = yy;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // 8 loads in flight per thread
-    int c = 0;
-    for (; c + 7 < Wd; c += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) acc[u] = fmaf(y[c + u], proj[(size_t)(c + u) * OD + o], acc[u]);
+  const int ol = threadIdx.x & 63, pt = threadIdx.x >> 6;
+  const int o = blockIdx.y * 64 + ol;
+  const int c0 = pt * (Wd / 4), c1 = c0 + Wd / 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (o < OD) {
+    int c = c0;
+    for (; c + 3 < c1; c += 4) {
+      a0 = fmaf(y[c], proj[(size_t)c * OD + o], a0);
+      a1 = fmaf(y[c + 1], proj[(size_t)(c + 1) * OD + o], a1);
+      a2 = fmaf(y[c + 2], proj[(size_t)(c + 2) * OD + o], a2);
+      a3 = fmaf(y[c + 3], proj[(size_t)(c + 3) * OD + o], a3);
     }
-    float a = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-    for (; c < Wd; ++c) a = fmaf(y[c], proj[(size_t)c * OD + o], a);
-    e[o] = a;
-    emb[(size_t)b * OD + o] = a;
+    for (; c < c1; ++c) a0 = fmaf(y[c], proj[(size_t)c * OD + o], a0);
   }
+  part[pt * 64 + ol] = (a0 + a1) + (a2 + a3);
   __syncthreads();
+  if (pt == 0 && o < OD) emb[(size_t)b * OD + o] = (part[ol] + part[64 + ol]) + (part[128 + ol] + part[192 + ol]);
+}
+
+// cosine(emb[b], text[b]); torch.cosine_similarity: x.y / max(||x|| * ||y||, 1e-8)
+__global__ void __launch_bounds__(256)
+k_cosine(const float* __restrict__ emb, const float* __restrict__ text, int OD, float* __restrict__ cos_out) {
+  __shared__ float red[3][8];
+  const int b = blockIdx.x;
   float ee = 0.f, tt = 0.f, et = 0.f;
   for (int o = threadIdx.x; o < OD; o += blockDim.x) {
-    float a = e[o], t = text[(size_t)b * OD + o];
+    float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
     ee += a * a; tt += t * t; et += a * t;
   }
   ee = warp_sum(ee); tt = warp_sum(tt); et = warp_sum(et);
@@ -516,7 +537,6 @@ k_head_fwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__
   if (threadIdx.x == 0) {
     float a = 0.f, t = 0.f, c = 0.f;
     for (int i = 0; i < 8; ++i) { a += red[0][i]; t += red[1][i]; c += red[2][i]; }
-    // torch.cosine_similarity: x.y / max(||x|| * ||y||, eps), eps = 1e-8
     cos_out[b] = c / fmaxf(sqrtf(a) * sqrtf(t), 1e-8f);
   }
 }
@@ -713,11 +733,11 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
 
   int64_t npx = (int64_t)B * 3 * IS * IS;
   k_preprocess<<<(int)((npx + 255) / 256), 256, 0, st>>>(canvases, H, W, B, IS, cfg->patch, w.a0, input_mode);
-  k_cls_rows<<<(B * Wd + 255) / 256, 256, 0, st>>>(wt->cls, wt->pos, B, T, Wd, w.tok_pre);
+  k_cls_rows<<<(B * T * Wd + 255) / 256, 256, 0, st>>>(wt->cls, wt->pos, B, T, Wd, w.tok_pre);
   AVC_LAUNCH_TRY();
   {
-    EpiPatch e{w.tok_pre, wt->pos, T, Wd, np};
-    AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 1, e));
+    EpiPatch e{w.tok_pre, T, Wd, np};
+    AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 4, e));
   }
   k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr);
   AVC_LAUNCH_TRY();
@@ -743,9 +763,10 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
       AVC_TRY(gemm16(st, w.g16, cfg->mlp, (const __half*)lw.w_proj, cfg->mlp, M, Wd, cfg->mlp, 4, e)); }
   }
   AVC_CUDA_TRY(cudaMemcpyAsync(w.x_final, w.x, sizeof(float) * (size_t)M * Wd, cudaMemcpyDeviceToDevice, st));
-  k_head_fwd<<<B, 256, (Wd + cfg->out_dim) * sizeof(float), st>>>(w.x_final, T, Wd, wt->ln_post_g, wt->ln_post_b,
-                                                                 wt->proj, cfg->out_dim, text_emb, w.emb, cos_out,
-                                                                 w.ynorm);
+  if (Wd % 4) return AVC_E_BADCFG;
+  k_head_proj<<<dim3(B, (cfg->out_dim + 63) / 64), 256, (Wd + 256) * sizeof(float), st>>>(
+      w.x_final, T, Wd, wt->ln_post_g, wt->ln_post_b, wt->proj, cfg->out_dim, w.emb, w.ynorm);
+  k_cosine<<<B, 256, 0, st>>>(w.emb, text_emb, cfg->out_dim, cos_out);
   AVC_LAUNCH_TRY();
   AVC_CUDA_TRY(cudaMemcpyAsync(emb_out, w.emb, sizeof(float) * (size_t)B * cfg->out_dim, cudaMemcpyDeviceToDevice, st));
   return 0;

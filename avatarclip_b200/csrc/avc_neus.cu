@@ -177,7 +177,7 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
 // -------------------------------------------------------------------------------- placement
 int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, const float* rays_d, const float* near,
                   const float* far, const float* jitter, int Rc, float* z_out_raymajor, cudaStream_t st) {
-  const int T = 128;
+  const int T = 32;     // one thread per ray, long serial loops: small CTAs spread the rays over many SMs
   k_coarse_z<<<blocks_for(Rc, T), T, 0, st>>>(near, far, jitter, pl.n0, Rc, w.zA);
   AVC_LAUNCH_TRY();
   if (pl.cfg.n_importance == 0) {
@@ -187,7 +187,7 @@ int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, cons
   }
   EncodeTargets t = make_targets(pl, w);
   int64_t Pn = (int64_t)pl.n0 * Rc;
-  k_encode_samples<<<blocks_for(Pn, 128), 128, 0, st>>>(rays_o, rays_d, w.zA, pl.n0, Rc, pl.cfg.sdf_scale,
+  k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.zA, pl.n0, Rc, pl.cfg.sdf_scale,
                                                         pl.cfg.sdf_multires, pl.E, pl.EP, t);
   AVC_LAUNCH_TRY();
   AVC_TRY(value_chain(pl, w, Pn, false, false, w.sA, st));
@@ -200,7 +200,7 @@ int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, cons
     AVC_LAUNCH_TRY();
     if (!last) {
       Pn = (int64_t)pl.per * Rc;
-      k_encode_samples<<<blocks_for(Pn, 128), 128, 0, st>>>(rays_o, rays_d, w.newZ, pl.per, Rc, pl.cfg.sdf_scale,
+      k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.newZ, pl.per, Rc, pl.cfg.sdf_scale,
                                                             pl.cfg.sdf_multires, pl.E, pl.EP, t);
       AVC_LAUNCH_TRY();
       AVC_TRY(value_chain(pl, w, Pn, false, false, w.newS, st));
@@ -238,7 +238,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   const int64_t P = io.Rc * pl.S;
   const float* pack = w.pack;
   EncodeTargets t = make_targets(pl, w);
-  k_encode_fine<<<blocks_for(P, 128), 128, 0, st>>>(io.rays_o, io.rays_d, io.out.z_vals, pl.S, io.Rc,
+  k_encode_fine<<<blocks_for(P * 8, 256), 256, 0, st>>>(io.rays_o, io.rays_d, io.out.z_vals, pl.S, io.Rc,
                                                     2.0f / (float)pl.n0, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
                                                     pl.EP, w.cin, write_outputs ? io.out.mid_z_vals : nullptr,
                                                     write_outputs ? io.out.inside_sphere : nullptr, t);
@@ -391,7 +391,9 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const LinDim& dn = pl.sdf[l + 1];
     EpiChainBwd e;
     e.N = d.N; e.Np = d.Np; e.Z = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
-    e.UNEXT = w.ubar[ucur ^ 1]; e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
+    // tcgen05 engine: the fp32 copy of ubar_{l+1} is only read by the column sum at the last linear
+    e.UNEXT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.ubar[ucur ^ 1];
+    e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
     e.u16 = with_ld(w.ubar16[ucur ^ 1], dn.Kp);
     AVC_TRY(gemm_nt(pl, w, st, P, d.N, d.K, ub, d.Kp, ub16, d.pk_W, d.Kp, e));
     if (dn.skip) {
@@ -641,7 +643,7 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
   EncodeTargets t = make_targets(pl, w);
   for (int64_t p0 = 0; p0 < P; p0 += cap) {
     int64_t n = (P - p0) < cap ? (P - p0) : cap;
-    k_encode_points<<<blocks_for(n, 128), 128, 0, st>>>(pts + p0 * 3, n, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
+    k_encode_points<<<blocks_for(n * 8, 256), 256, 0, st>>>(pts + p0 * 3, n, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
                                                         pl.EP, t);
     AVC_LAUNCH_TRY();
     AVC_TRY(value_chain(pl, w, n, false, false, sdf_out + p0, st));

@@ -130,8 +130,11 @@ struct EncodeTargets {
   Split16 in0_16; Split16 skip16[4];   // tcgen05 engine copies (hi == nullptr: unused)
 };
 
-__device__ __forceinline__ void encode_point(float x0, float x1, float x2, float scale, int multires, int E, int EP,
-                                             int64_t p, const EncodeTargets& t) {
+// One point is encoded by 8 cooperating lanes (group g = lane & 7): g = 0 writes the identity columns and the zero
+// padding, g = 1.. write one frequency each (sin xyz, cos xyz; frequencies beyond 7 wrap around), so that the 8 lanes
+// of a point cover its whole 160-byte row with adjacent pieces (coalesced) instead of one thread writing 40 floats.
+__device__ __forceinline__ void encode_group(float x0, float x1, float x2, float scale, int multires, int E, int EP,
+                                             int64_t p, int g, const EncodeTargets& t) {
   const float y[3] = {x0 * scale, x1 * scale, x2 * scale};
   float* r0 = t.in0 + (size_t)p * t.ld0;
   auto put = [&](int c, float v) {
@@ -142,9 +145,12 @@ __device__ __forceinline__ void encode_point(float x0, float x1, float x2, float
       split16_put(t.skip16[s], (size_t)p, t.skip_col[s] + c, v * kSqrtHalf);
     }
   };
-  put(0, y[0]); put(1, y[1]); put(2, y[2]);
-  float f = 1.f;
-  for (int k = 0; k < multires; ++k) {
+  if (g == 0) {
+    put(0, y[0]); put(1, y[1]); put(2, y[2]);
+    for (int c = E; c < EP; ++c) { r0[c] = 0.f; split16_put(t.in0_16, (size_t)p, c, 0.f); }
+  }
+  for (int k = g - 1; k >= 0 && k < multires; k += 7) {
+    const float f = (float)(1 << k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float sn, cs;
@@ -152,16 +158,15 @@ __device__ __forceinline__ void encode_point(float x0, float x1, float x2, float
       put(3 + 6 * k + c, sn);
       put(6 + 6 * k + c, cs);
     }
-    f *= 2.f;
   }
-  for (int c = E; c < EP; ++c) { r0[c] = 0.f; split16_put(t.in0_16, (size_t)p, c, 0.f); }
 }
 
 // Sampling passes: points in SAMPLE-MAJOR order p = j * Rc + r taken from z[j][r] (first nz rows).
 __global__ void k_encode_samples(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                  const float* __restrict__ z, int nz, int Rc, float scale, int multires, int E, int EP,
                                  EncodeTargets t) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = id >> 3;
   if (p >= (int64_t)nz * Rc) return;
   int r = (int)(p % Rc);
   float zz = z[p];
@@ -169,15 +174,16 @@ __global__ void k_encode_samples(const float* __restrict__ rays_o, const float* 
   float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], zz));
   float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], zz));
   float x2 = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], zz));
-  encode_point(x0, x1, x2, scale, multires, E, EP, p, t);
+  encode_group(x0, x1, x2, scale, multires, E, EP, p, (int)(id & 7), t);
 }
 
 // Arbitrary query points [P][3] (SDFNetwork.sdf for extract_fields).
 __global__ void k_encode_points(const float* __restrict__ pts, int64_t P, float scale, int multires, int E, int EP,
                                 EncodeTargets t) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = id >> 3;
   if (p >= P) return;
-  encode_point(pts[p * 3 + 0], pts[p * 3 + 1], pts[p * 3 + 2], scale, multires, E, EP, p, t);
+  encode_group(pts[p * 3 + 0], pts[p * 3 + 1], pts[p * 3 + 2], scale, multires, E, EP, p, (int)(id & 7), t);
 }
 
 // Fine pass (render_core, renderer.py:208-219): ray-major p = r * S + j.  Section midpoints, dists,
@@ -186,8 +192,10 @@ __global__ void k_encode_fine(const float* __restrict__ rays_o, const float* __r
                               const float* __restrict__ z_vals, int S, int64_t Rc, float sample_dist,
                               float scale, int multires, int E, int EP, float* __restrict__ cin,
                               float* __restrict__ mid_z_out, float* __restrict__ inside_out, EncodeTargets t) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t p = id >> 3;
   if (p >= Rc * S) return;
+  const int g = (int)(id & 7);
   int64_t r = p / S;
   int j = (int)(p - r * S);
   float z0 = z_vals[p];
@@ -196,15 +204,17 @@ __global__ void k_encode_fine(const float* __restrict__ rays_o, const float* __r
   float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], mid));
   float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], mid));
   float x2 = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], mid));
-  float4* c = reinterpret_cast<float4*>(cin + (size_t)p * 8);
-  c[0] = make_float4(x0, x1, x2, 0.f);
-  c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (mid_z_out) mid_z_out[p] = mid;
-  if (inside_out) {
-    float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
-    inside_out[p] = nrm < 1.0f ? 1.f : 0.f;
+  if (g == 7) {       // the lane without a frequency of its own (multires <= 6) writes the per-point extras
+    float4* c = reinterpret_cast<float4*>(cin + (size_t)p * 8);
+    c[0] = make_float4(x0, x1, x2, 0.f);
+    c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mid_z_out) mid_z_out[p] = mid;
+    if (inside_out) {
+      float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
+      inside_out[p] = nrm < 1.0f ? 1.f : 0.f;
+    }
   }
-  encode_point(x0, x1, x2, scale, multires, E, EP, p, t);
+  encode_group(x0, x1, x2, scale, multires, E, EP, p, g, t);
 }
 
 // =============================================================================================
@@ -772,7 +782,7 @@ struct EpiChainBwd {
   __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
     float s1 = softplus100_d1(p.a);
     float uv = s1 * a * s_next;
-    UNEXT[(size_t)row * ldu + c] = uv;
+    if (UNEXT) UNEXT[(size_t)row * ldu + c] = uv;
     split16_put(u16, (size_t)row, c, uv);
     ZBAR[(size_t)row * Np + c] = kBeta * (1.f - s1) * p.b * a;
   }
@@ -790,7 +800,7 @@ struct EpiChainBwd {
         u[i] = s1 * v[i] * s_next;
         zb[i] = kBeta * (1.f - s1) * qq[i] * v[i];
       }
-      *reinterpret_cast<float4*>(UNEXT + (size_t)row * ldu + col) = make_float4(u[0], u[1], u[2], u[3]);
+      if (UNEXT) *reinterpret_cast<float4*>(UNEXT + (size_t)row * ldu + col) = make_float4(u[0], u[1], u[2], u[3]);
       split16_put4(u16, (size_t)row, col, u);
       *reinterpret_cast<float4*>(ZBAR + o) = make_float4(zb[0], zb[1], zb[2], zb[3]);
       return;
@@ -802,7 +812,7 @@ struct EpiChainBwd {
       if (c < N) {
         float s1 = softplus100_d1_fast(Z[(size_t)row * Np + c]);
         float uv = s1 * v[i] * s_next;
-        UNEXT[(size_t)row * ldu + c] = uv;
+        if (UNEXT) UNEXT[(size_t)row * ldu + c] = uv;
         split16_put(u16, (size_t)row, c, uv);
         zb[i] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * v[i];
       } else {

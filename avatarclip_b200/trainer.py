@@ -70,22 +70,33 @@ class AppearanceTrainer:
         self.emb = torch.zeros(2, clip_tower.cfg.out_dim, dtype=torch.float32, device=self.device)
         self.scalars = None
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.phase_events = None      # set to [] to record a CUDA event after every phase of the next step
 
     # ------------------------------------------------------------------------------------------
     def forward_backward(self, dv: DeviceView, cos_anneal: float = 1.0) -> torch.Tensor:
         """Everything up to (and including) the flat gradient; returns self.grad."""
         L = _lib.lib()
         r = self.renderer
+
+        def mark(name):
+            if self.phase_events is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                self.phase_events.append((name, e))
+
+        mark("start")
         bg = dv.ray_background if dv.bg_choice in (1, 2) else (torch.ones(3, device=self.device) if dv.bg_choice == 0 else None)
         bg_kind = 2 if dv.bg_choice in (1, 2) else (1 if dv.bg_choice == 0 else 0)
         jit = dv.jitter if r.perturb > 0 else None
         out, ws, chunk = render_forward_raw(r, dv.rays_o, dv.rays_d, dv.near, dv.far, jit, bg, bg_kind, cos_anneal,
                                             None, keep_ws=False, out=self._out)
         self._out = out
+        mark("render_fwd")
         si = losses.StepInputs(dv.pix, dv.in_mask, dv.true_rgb, dv.mask, dv.H, dv.W, dv.light_dir, dv.ambience,
                                dv.bg_choice, dv.canvas_background, self.igr_weight, self.mask_weight, self.clip_weight)
         canv, scal = losses.stage_forward(out, si)
         self.scalars = scal
+        mark("loss_stage_fwd")
         # CLIP on both canvases at once (main.py:509-526): B = 2
         tower = self.clip
         if self._clip_ws is None:
@@ -94,12 +105,16 @@ class AppearanceTrainer:
         _lib.check(L.avc_clip_loss_fwd(C.byref(tower.cfg), C.byref(tower.w), _lib.ptr(canv), dv.H, dv.W, 2, 0,
                                        _lib.ptr(self.text), _lib.ptr(self.emb), _lib.ptr(self.cos), _lib.ptr(cws),
                                        cws.numel(), _lib.stream_ptr()), "avc_clip_loss_fwd")
+        mark("clip_fwd")
         d_canv = torch.empty_like(canv)
         _lib.check(L.avc_clip_loss_bwd(C.byref(tower.cfg), C.byref(tower.w), dv.H, dv.W, 2, 0, _lib.ptr(self.text),
                                        _lib.ptr(self.g_cos), None, _lib.ptr(d_canv), _lib.ptr(cws), cws.numel(),
                                        _lib.stream_ptr()), "avc_clip_loss_bwd")
+        mark("clip_bwd")
         cot = losses.stage_backward(out, si, d_canv, scal)
+        mark("loss_stage_bwd")
         render_backward_raw(r, dv.rays_o, dv.rays_d, bg, bg_kind, cos_anneal, out, ws, chunk, cot, grad=self.grad)
+        mark("render_bwd")
         return self.grad
 
     def loss_value(self) -> torch.Tensor:
@@ -114,6 +129,10 @@ class AppearanceTrainer:
                                             _lib.ptr(self.exp_avg_sq), self.fp.n, float(self.lr if lr is None else lr),
                                             b1, b2, self.eps, self.iter_step, 1.0 / self.world, _lib.stream_ptr()),
                    "avc_adam_step")
+        if self.phase_events is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.phase_events.append(("allreduce_adam", e))
 
     def step(self, dv: DeviceView, lr: Optional[float] = None, cos_anneal: float = 1.0) -> torch.Tensor:
         self.forward_backward(dv, cos_anneal)

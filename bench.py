@@ -214,6 +214,17 @@ def run_native(args):
         tot_render += e[0].elapsed_time(e[1]) + e[2].elapsed_time(e[3])
     ms_render = tot_render / min(K, 5)
 
+    # per-phase device times (CUDA events between the C-ABI calls), averaged over a few extra steps
+    phases = {}
+    for i in range(5):
+        tr.phase_events = []
+        tr.step(resident[i % n_views])
+        torch.cuda.synchronize()
+        evs = tr.phase_events
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / 5.0
+    tr.phase_events = None
+
     # ---------------- end-to-end timing: pinned-host inputs copied every step, loss read back every step
     barrier()
     ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -256,6 +267,7 @@ def run_native(args):
                                   "avc_neus_render_fwd + avc_neus_render_bwd; peak = " + peak_src,
                          "dominant_kernel": dom, "ms_render_fwd_bwd": ms_render},
             "last_loss": last,
+            "phases_ms": {k: round(v, 4) for k, v in phases.items()},
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(sp, cp, clip_sd, text, views[0], sample_rays=args.cpu_sample_rays)
