@@ -304,7 +304,8 @@ k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict_
 // dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))
 __global__ void __launch_bounds__(256)
 k_layernorm_bwd(const float* __restrict__ x, const float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
-                float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx) {
+                float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx,
+                __half* __restrict__ dx16, float* __restrict__ dx_scale) {
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -323,10 +324,22 @@ k_layernorm_bwd(const float* __restrict__ x, const float* __restrict__ dy, int M
   }
   a = warp_sum(a) / (float)Wd; bq = warp_sum(bq) / (float)Wd;
   float* o = dx + (size_t)row * row_stride_dx;
+  float mx = 0.f;
   for (int c = lane; c < Wd; c += 32) {
     float xh = (xr[c] - mean) * rstd;
     float r = rstd * (dr[c] * g[c] - a - xh * bq);
-    o[c] = accumulate ? o[c] + r : r;
+    r = accumulate ? o[c] + r : r;
+    o[c] = r;
+    mx = fmaxf(mx, fabsf(r));
+  }
+  if (dx16) {      // fused k_to_half_rowscaled of the updated row (operand of the next input-gradient GEMM)
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+    float sc = 1.f;
+    if (mx > 0.f && isfinite(mx)) { int e; frexpf(mx, &e); sc = ldexpf(1.f, 1 - e); }
+    __syncwarp();
+    for (int c = lane; c < Wd; c += 32) dx16[(size_t)row * Wd + c] = __float2half_rn(o[c] * sc);
+    if (lane == 0) dx_scale[row] = sc;
   }
 }
 
@@ -359,27 +372,35 @@ k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __h
 // ------------------------------------------------------------------------------------------------
 constexpr int AT = 64;   // max tokens
 constexpr int AD = 64;   // head dim
+constexpr int AP = AD + 4;   // shared-memory row pitch: 16-byte aligned rows, LDS.128 conflict-free across 8 rows
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+}
 
 __global__ void __launch_bounds__(512)
 k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
-  extern __shared__ float sm[];
-  float* q = sm;                  // [T][AD+1]
-  float* k = q + AT * (AD + 1);
-  float* v = k + AT * (AD + 1);
-  float* S = v + AT * (AD + 1);   // [T][AT+1]
+  extern __shared__ __align__(16) float sm[];
+  float* q = sm;                  // [T][AP]
+  float* k = q + AT * AP;
+  float* v = k + AT * AP;
+  float* S = v + AT * AP;         // [T][AT+1]
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
-    int t = i / AD, d = i % AD;
+  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
     const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
-    q[t * (AD + 1) + d] = r[0]; k[t * (AD + 1) + d] = r[Wd]; v[t * (AD + 1) + d] = r[2 * Wd];
+    *reinterpret_cast<float4*>(q + t * AP + d) = *reinterpret_cast<const float4*>(r);
+    *reinterpret_cast<float4*>(k + t * AP + d) = *reinterpret_cast<const float4*>(r + Wd);
+    *reinterpret_cast<float4*>(v + t * AP + d) = *reinterpret_cast<const float4*>(r + 2 * Wd);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
     int a = i / T, c = i % T;
     float s = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < AD; ++d) s = fmaf(q[a * (AD + 1) + d], k[c * (AD + 1) + d], s);
+#pragma unroll
+    for (int d = 0; d < AD; d += 4)
+      s = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), s);
     S[a * (AT + 1) + c] = s * 0.125f;          // 1/sqrt(64)
   }
   __syncthreads();
@@ -396,11 +417,18 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
     for (int c = lane; c < T; c += 32) S[a * (AT + 1) + c] *= inv;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
-    int a = i / AD, d = i % AD;
-    float o = 0.f;
-    for (int c = 0; c < T; ++c) o = fmaf(S[a * (AT + 1) + c], v[c * (AD + 1) + d], o);
-    o16[((size_t)b * T + a) * Wd + h * AD + d] = __float2half_rn(o);
+  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+    int a = i / (AD / 4), d = (i % (AD / 4)) * 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < T; ++c) {
+      const float p = S[a * (AT + 1) + c];
+      const float4 vv = *reinterpret_cast<const float4*>(v + c * AP + d);
+      o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
+    }
+    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
+    *reinterpret_cast<uint2*>(o16 + ((size_t)b * T + a) * Wd + h * AD + d) = pk;
   }
 }
 
@@ -408,29 +436,32 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
 __global__ void __launch_bounds__(512)
 k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
                 float* __restrict__ dqkv) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* q = sm;
-  float* k = q + AT * (AD + 1);
-  float* v = k + AT * (AD + 1);
-  float* dO_s = v + AT * (AD + 1);
-  float* Pm = dO_s + AT * (AD + 1);     // [T][AT+1]
+  float* k = q + AT * AP;
+  float* v = k + AT * AP;
+  float* dO_s = v + AT * AP;
+  float* Pm = dO_s + AT * AP;           // [T][AT+1]
   float* dS = Pm + AT * (AT + 1);
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
-    int t = i / AD, d = i % AD;
+  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
     const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
-    q[t * (AD + 1) + d] = r[0]; k[t * (AD + 1) + d] = r[Wd]; v[t * (AD + 1) + d] = r[2 * Wd];
-    dO_s[t * (AD + 1) + d] = dO[((size_t)b * T + t) * Wd + h * AD + d];
+    *reinterpret_cast<float4*>(q + t * AP + d) = *reinterpret_cast<const float4*>(r);
+    *reinterpret_cast<float4*>(k + t * AP + d) = *reinterpret_cast<const float4*>(r + Wd);
+    *reinterpret_cast<float4*>(v + t * AP + d) = *reinterpret_cast<const float4*>(r + 2 * Wd);
+    *reinterpret_cast<float4*>(dO_s + t * AP + d) =
+        *reinterpret_cast<const float4*>(dO + ((size_t)b * T + t) * Wd + h * AD + d);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
     int a = i / T, c = i % T;
     float s = 0.f, dp = 0.f;
-#pragma unroll 16
-    for (int d = 0; d < AD; ++d) {
-      s = fmaf(q[a * (AD + 1) + d], k[c * (AD + 1) + d], s);
-      dp = fmaf(dO_s[a * (AD + 1) + d], v[c * (AD + 1) + d], dp);
+#pragma unroll
+    for (int d = 0; d < AD; d += 4) {
+      s = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), s);
+      dp = dot4(*reinterpret_cast<const float4*>(dO_s + a * AP + d), *reinterpret_cast<const float4*>(v + c * AP + d), dp);
     }
     Pm[a * (AT + 1) + c] = s * 0.125f;
     dS[a * (AT + 1) + c] = dp;               // dP for now
@@ -452,16 +483,22 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
   }
   __syncthreads();
   float* dbase = dqkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * AD; i += blockDim.x) {
-    int t = i / AD, d = i % AD;
-    float dq = 0.f, dk = 0.f, dv = 0.f;
+  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
+    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
     for (int c = 0; c < T; ++c) {
-      dq = fmaf(dS[t * (AT + 1) + c], k[c * (AD + 1) + d], dq);       // dQ[t] = sum_c dS[t][c] K[c]
-      dk = fmaf(dS[c * (AT + 1) + t], q[c * (AD + 1) + d], dk);       // dK[t] = sum_c dS[c][t] Q[c]
-      dv = fmaf(Pm[c * (AT + 1) + t], dO_s[c * (AD + 1) + d], dv);    // dV[t] = sum_c P[c][t] dO[c]
+      const float s_tc = dS[t * (AT + 1) + c], s_ct = dS[c * (AT + 1) + t], p_ct = Pm[c * (AT + 1) + t];
+      const float4 kc = *reinterpret_cast<const float4*>(k + c * AP + d);
+      const float4 qc = *reinterpret_cast<const float4*>(q + c * AP + d);
+      const float4 oc = *reinterpret_cast<const float4*>(dO_s + c * AP + d);
+      dq.x = fmaf(s_tc, kc.x, dq.x); dq.y = fmaf(s_tc, kc.y, dq.y); dq.z = fmaf(s_tc, kc.z, dq.z); dq.w = fmaf(s_tc, kc.w, dq.w);
+      dk.x = fmaf(s_ct, qc.x, dk.x); dk.y = fmaf(s_ct, qc.y, dk.y); dk.z = fmaf(s_ct, qc.z, dk.z); dk.w = fmaf(s_ct, qc.w, dk.w);
+      dv.x = fmaf(p_ct, oc.x, dv.x); dv.y = fmaf(p_ct, oc.y, dv.y); dv.z = fmaf(p_ct, oc.z, dv.z); dv.w = fmaf(p_ct, oc.w, dv.w);
     }
     float* r = dbase + (size_t)t * 3 * Wd + h * AD + d;
-    r[0] = dq; r[Wd] = dk; r[2 * Wd] = dv;
+    *reinterpret_cast<float4*>(r) = dq;
+    *reinterpret_cast<float4*>(r + Wd) = dk;
+    *reinterpret_cast<float4*>(r + 2 * Wd) = dv;
   }
 }
 
@@ -541,14 +578,13 @@ k_cosine(const float* __restrict__ emb, const float* __restrict__ text, int OD, 
   }
 }
 
-// d cos / d emb -> through proj and ln_post -> dx rows (cls row gets the gradient, other rows zero)
+// d cos / d emb (+ g_emb) -> dy = proj . de, spread over (B, Wd/96) CTAs (one warp per row of proj: coalesced)
 __global__ void __launch_bounds__(256)
-k_head_bwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ proj,
-           int OD, const float* __restrict__ text, const float* __restrict__ emb, const float* __restrict__ g_cos,
-           const float* __restrict__ g_emb, float* __restrict__ dx) {
+k_head_bwd_dy(int Wd, const float* __restrict__ proj, int OD, const float* __restrict__ text,
+              const float* __restrict__ emb, const float* __restrict__ g_cos, const float* __restrict__ g_emb,
+              float* __restrict__ dy_out, int rows_per_cta) {
   extern __shared__ float sm[];
   float* de = sm;            // [OD]
-  float* dy = de + OD;       // [Wd]
   __shared__ float red[3][8];
   const int b = blockIdx.x;
   float ee = 0.f, tt = 0.f, et = 0.f;
@@ -571,19 +607,26 @@ k_head_bwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__
     de[o] = d;
   }
   __syncthreads();
-  for (int cc = threadIdx.x >> 5; cc < Wd; cc += (blockDim.x >> 5)) {   // one warp per row of proj: coalesced
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(Wd, r0 + rows_per_cta);
+  for (int cc = r0 + (threadIdx.x >> 5); cc < r1; cc += (blockDim.x >> 5)) {
     float s = 0.f;
     for (int o = threadIdx.x & 31; o < OD; o += 32) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) dy[cc] = s;
+    if ((threadIdx.x & 31) == 0) dy_out[(size_t)b * Wd + cc] = s;
   }
-  __syncthreads();
-  // LayerNorm backward on the cls row
+}
+
+// LayerNorm (ln_post) backward on the cls row; the other token rows receive no gradient from the head
+__global__ void __launch_bounds__(256)
+k_head_bwd_ln(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ dy_in,
+              float* __restrict__ dx) {
+  __shared__ float red[3][8];
+  const int b = blockIdx.x;
   const float* xr = x + (size_t)b * T * Wd;
+  const float* dy = dy_in + (size_t)b * Wd;
   float s = 0.f;
   for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) s += xr[cc];
   s = warp_sum(s);
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
   __syncthreads();
   float mean = 0.f;
@@ -604,7 +647,6 @@ k_head_bwd(const float* __restrict__ x, int T, int Wd, const float* __restrict__
     pa += dg; pb += dg * (xr[cc] - mean) * rstd;
   }
   pa = warp_sum(pa); pb = warp_sum(pb);
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) { red[1][threadIdx.x >> 5] = pa; red[2][threadIdx.x >> 5] = pb; }
   __syncthreads();
   float A = 0.f, Bq = 0.f;
@@ -727,8 +769,8 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
   if (w.bytes > workspace_bytes) return AVC_E_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
   const int Wd = cfg->width, M = B * T, IS = cfg->image_size;
-  const int attn_fwd_smem = (3 * AT * (AD + 1) + AT * (AT + 1)) * (int)sizeof(float);
-  const int attn_bwd_smem = (4 * AT * (AD + 1) + 2 * AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_fwd_smem = (3 * AT * AP + AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_bwd_smem = (4 * AT * AP + 2 * AT * (AT + 1)) * (int)sizeof(float);
   AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
 
   int64_t npx = (int64_t)B * 3 * IS * IS;
@@ -786,12 +828,16 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
   if (w.bytes > workspace_bytes) return AVC_E_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
   const int Wd = cfg->width, M = B * T, IS = cfg->image_size, mlp = cfg->mlp;
-  const int attn_fwd_smem = (3 * AT * (AD + 1) + AT * (AT + 1)) * (int)sizeof(float);
-  const int attn_bwd_smem = (4 * AT * (AD + 1) + 2 * AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_fwd_smem = (3 * AT * AP + AT * (AT + 1)) * (int)sizeof(float);
+  const int attn_bwd_smem = (4 * AT * AP + 2 * AT * (AT + 1)) * (int)sizeof(float);
   AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
 
-  k_head_bwd<<<B, 256, (Wd + cfg->out_dim) * sizeof(float), st>>>(w.x_final, T, Wd, wt->ln_post_g, wt->proj,
-                                                                 cfg->out_dim, text_emb, w.emb, g_cos, g_emb, w.dx);
+  {
+    const int rows = 96;
+    k_head_bwd_dy<<<dim3(B, ceil_div(Wd, rows)), 256, cfg->out_dim * sizeof(float), st>>>(
+        Wd, wt->proj, cfg->out_dim, text_emb, w.emb, g_cos, g_emb, w.dO, rows);      // w.dO[0 .. B*Wd) as scratch
+    k_head_bwd_ln<<<B, 256, 0, st>>>(w.x_final, T, Wd, wt->ln_post_g, w.dO, w.dx);
+  }
   AVC_LAUNCH_TRY();
   for (int l = cfg->layers - 1; l >= 0; --l) {
     const avc_clip_layer_weights& lw = wt->layer[l];
@@ -800,18 +846,18 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     const float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
     const float* fcp = w.fc_pre + (size_t)l * M * mlp;
     // ---- MLP branch: x_out = x_mid + c_proj(QuickGELU(c_fc(ln_2(x_mid))))
-    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
-    AVC_LAUNCH_TRY();
+    if (l == cfg->layers - 1) {     // later layers get this conversion fused into the previous LayerNorm backward
+      k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
+      AVC_LAUNCH_TRY();
+    }
     { EpiDfc e{fcp, w.d16b, mlp};
       AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_proj_t, Wd, M, mlp, Wd, 1, e)); }
     AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16b, mlp, (const __half*)lw.w_fc_t, mlp, M, Wd, mlp, 4, e)); }
-    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd);
+    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale);
     AVC_LAUNCH_TRY();
     // ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
-    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
-    AVC_LAUNCH_TRY();
     { EpiStoreUnscale e{w.dO, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_out_t, Wd, M, Wd, Wd, 1, e)); }
     k_attention_bwd<<<B * cfg->heads, 512, attn_bwd_smem, st>>>(qkv, w.dO, T, Wd, cfg->heads, w.dqkv);
@@ -821,11 +867,12 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, 3 * Wd, (const __half*)lw.w_qkv_t, 3 * Wd, M, Wd, 3 * Wd, 3, e)); }
-    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd);
+    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale);
     AVC_LAUNCH_TRY();
   }
   // ln_pre, patch embedding, pre-processing
-  k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, w.dx, M, Wd, wt->ln_pre_g, w.dtmp, 0, Wd, Wd, Wd);
+  k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, w.dx, M, Wd, wt->ln_pre_g, w.dtmp, 0, Wd, Wd, Wd, nullptr,
+                                                  nullptr);
   k_patch_row_map<<<ceil_div(B * np, 128), 128, 0, st>>>(B, T, w.rowmap);
   k_to_half_rowscaled<<<ceil_div(B * np, 8), 256, 0, st>>>(w.dtmp, B * np, Wd, Wd, w.d16a, w.scale, w.rowmap);
   AVC_LAUNCH_TRY();

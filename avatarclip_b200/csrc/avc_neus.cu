@@ -147,7 +147,7 @@ EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
 // in[0] (and the skip columns) must hold the encoding of Pn points.  stash: keep z[l].
 // Leaves in[L] ready; writes sdf[Pn] (thin) and, when want_feat, feat[Pn][Fp].
 int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, bool want_feat, float* sdf_out,
-                cudaStream_t st) {
+                cudaStream_t st, int sdf_nz = 0, int sdf_pitch = 0) {
   const float* pack = w.pack;
   for (int l = 0; l < pl.L; ++l) {
     const LinDim& d = pl.sdf[l];
@@ -163,7 +163,7 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
     AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, e));
   }
   const LinDim& dl = pl.sdf[pl.L];
-  OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale};
+  OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale, sdf_nz, sdf_pitch};
   k_thin_nt<1, OutSdf><<<blocks_for(Pn, 8), 256, 0, st>>>(w.in[pl.L], dl.Kp, dl.Kp, pack + pl.pk_wsdf, dl.Kp,
                                                            pack + pl.pk_bsdf, Pn, os);
   AVC_LAUNCH_TRY();
@@ -177,36 +177,36 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
 // -------------------------------------------------------------------------------- placement
 int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, const float* rays_d, const float* near,
                   const float* far, const float* jitter, int Rc, float* z_out_raymajor, cudaStream_t st) {
-  const int T = 32;     // one thread per ray, long serial loops: small CTAs spread the rays over many SMs
-  k_coarse_z<<<blocks_for(Rc, T), T, 0, st>>>(near, far, jitter, pl.n0, Rc, w.zA);
+  // ray-major buffers [Rc][S]; one warp per ray in the per-ray kernels
+  const int S = pl.S;
+  if (S > kPlaceMaxN || pl.per > kPlaceMaxNew) return AVC_E_BADCFG;
+  float* z0 = (pl.cfg.n_importance == 0) ? z_out_raymajor : w.zA;
+  k_coarse_z<<<blocks_for((int64_t)Rc * pl.n0, 256), 256, 0, st>>>(near, far, jitter, pl.n0, S, Rc, z0);
   AVC_LAUNCH_TRY();
-  if (pl.cfg.n_importance == 0) {
-    k_transpose_z<<<blocks_for((int64_t)pl.n0 * Rc, 256), 256, 0, st>>>(w.zA, pl.n0, Rc, z_out_raymajor);
-    AVC_LAUNCH_TRY();
-    return 0;
-  }
+  if (pl.cfg.n_importance == 0) return 0;
   EncodeTargets t = make_targets(pl, w);
   int64_t Pn = (int64_t)pl.n0 * Rc;
-  k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.zA, pl.n0, Rc, pl.cfg.sdf_scale,
-                                                        pl.cfg.sdf_multires, pl.E, pl.EP, t);
+  k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.zA, pl.n0, S, Rc, pl.cfg.sdf_scale,
+                                                            pl.cfg.sdf_multires, pl.E, pl.EP, t);
   AVC_LAUNCH_TRY();
-  AVC_TRY(value_chain(pl, w, Pn, false, false, w.sA, st));
+  AVC_TRY(value_chain(pl, w, Pn, false, false, w.sA, st, pl.n0, S));
   float *zc = w.zA, *sc = w.sA, *zn = w.zB, *sn = w.sB;
   int n = pl.n0;
   for (int i = 0; i < pl.steps; ++i) {
     const bool last = (i + 1 == pl.steps);
     float inv_s = 64.0f * (float)(1 << i);                                     // renderer.py:346
-    k_upsample<<<blocks_for(Rc, T), T, 0, st>>>(rays_o, rays_d, zc, sc, n, Rc, inv_s, pl.per, w.wS, w.newZ);
+    k_upsample<<<blocks_for(Rc, 8), 256, 0, st>>>(rays_o, rays_d, zc, sc, n, S, Rc, inv_s, pl.per, w.newZ);
     AVC_LAUNCH_TRY();
     if (!last) {
       Pn = (int64_t)pl.per * Rc;
-      k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.newZ, pl.per, Rc, pl.cfg.sdf_scale,
-                                                            pl.cfg.sdf_multires, pl.E, pl.EP, t);
+      k_encode_samples<<<blocks_for(Pn * 8, 256), 256, 0, st>>>(rays_o, rays_d, w.newZ, pl.per, pl.per, Rc,
+                                                                pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E, pl.EP, t);
       AVC_LAUNCH_TRY();
-      AVC_TRY(value_chain(pl, w, Pn, false, false, w.newS, st));
+      AVC_TRY(value_chain(pl, w, Pn, false, false, w.newS, st, 0, 0));   // newS is [Rc][per]: identity mapping
     }
-    k_merge<<<blocks_for(Rc, T), T, 0, st>>>(zc, sc, n, w.newZ, last ? nullptr : w.newS, pl.per, Rc, zn, sn,
-                                              last ? z_out_raymajor : nullptr);
+    // the last round writes the merged depths straight into the caller's z_vals [Rc][S]
+    k_merge<<<blocks_for(Rc, 8), 256, 0, st>>>(zc, sc, n, S, w.newZ, last ? nullptr : w.newS, pl.per, Rc,
+                                               last ? z_out_raymajor : zn, sn, S);
     AVC_LAUNCH_TRY();
     float* tz = zc; zc = zn; zn = tz;
     float* ts = sc; sc = sn; sn = ts;

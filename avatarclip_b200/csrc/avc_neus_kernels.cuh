@@ -161,15 +161,15 @@ __device__ __forceinline__ void encode_group(float x0, float x1, float x2, float
   }
 }
 
-// Sampling passes: points in SAMPLE-MAJOR order p = j * Rc + r taken from z[j][r] (first nz rows).
+// Sampling passes: points p = r * nz + j taken from z[r][j] (row pitch `pitch`).
 __global__ void k_encode_samples(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                 const float* __restrict__ z, int nz, int Rc, float scale, int multires, int E, int EP,
-                                 EncodeTargets t) {
+                                 const float* __restrict__ z, int nz, int pitch, int Rc, float scale, int multires, int E,
+                                 int EP, EncodeTargets t) {
   int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t p = id >> 3;
   if (p >= (int64_t)nz * Rc) return;
-  int r = (int)(p % Rc);
-  float zz = z[p];
+  int r = (int)(p / nz);
+  float zz = z[(size_t)r * pitch + (p - (int64_t)r * nz)];
   // renderer.py:337 / :182: pts = rays_o + rays_d * z  (separately rounded mul and add, as torch does)
   float x0 = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], zz));
   float x1 = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], zz));
@@ -229,19 +229,17 @@ __device__ __forceinline__ float torch_linspace(float start, float end, int n, i
   return (j < n / 2) ? __fadd_rn(start, __fmul_rn(step, (float)j)) : __fsub_rn(end, __fmul_rn(step, (float)(n - 1 - j)));
 }
 
+// Placement buffers are RAY-MAJOR [ray][pitch]; one warp per ray.
 __global__ void k_coarse_z(const float* __restrict__ near, const float* __restrict__ far,
-                           const float* __restrict__ jitter, int n, int Rc, float* __restrict__ z) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= Rc) return;
+                           const float* __restrict__ jitter, int n, int pitch, int Rc, float* __restrict__ z) {
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (int64_t)Rc * n) return;
+  int r = (int)(id / n), j = (int)(id % n);
   float nr = near[r], fr = far[r];
   float span = __fsub_rn(fr, nr);
-  float jit = 0.f;
-  if (jitter) jit = __fdiv_rn(__fmul_rn(jitter[r], 2.0f), (float)n);   // renderer.py:319
-  for (int j = 0; j < n; ++j) {
-    float zz = __fadd_rn(nr, __fmul_rn(span, torch_linspace(0.f, 1.f, n, j)));  // renderer.py:305-306
-    if (jitter) zz = __fadd_rn(zz, jit);
-    z[(size_t)j * Rc + r] = zz;
-  }
+  float zz = __fadd_rn(nr, __fmul_rn(span, torch_linspace(0.f, 1.f, n, j)));   // renderer.py:305-306
+  if (jitter) zz = __fadd_rn(zz, __fdiv_rn(__fmul_rn(jitter[r], 2.0f), (float)n));   // renderer.py:319
+  z[(size_t)r * pitch + j] = zz;
 }
 
 __device__ __forceinline__ float ray_radius(const float* o, const float* d, float z) {
@@ -251,96 +249,135 @@ __device__ __forceinline__ float ray_radius(const float* o, const float* d, floa
   return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x0, x0), __fmul_rn(x1, x1)), __fmul_rn(x2, x2)));
 }
 
+__device__ __forceinline__ float warp_excl_prod_f(float v, float* total) {
+  const int lane = threadIdx.x & 31;
+  float inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc *= t;
+  }
+  *total = __shfl_sync(0xffffffffu, inc, 31);
+  float ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  return lane == 0 ? 1.f : ex;
+}
+
+constexpr int kPlaceMaxN = 256;     // samples per ray handled by the placement kernels
+constexpr int kPlaceMaxNew = 64;    // new samples per round
+
 // up_sample (renderer.py:133-177) + sample_pdf(det=True) (:39-69).  n = current samples per ray.
-__global__ void k_upsample(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                           const float* __restrict__ z, const float* __restrict__ sdf, int n, int Rc,
-                           float inv_s, int per, float* __restrict__ wscr, float* __restrict__ newz) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per ray: section terms in blocks of 32 (neighbour values by shuffle), transmittance by a prefix-product
+// scan, cdf by a prefix-sum scan into shared memory, one inverse-CDF lookup (binary search) per new sample.
+__global__ void __launch_bounds__(256)
+k_upsample(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z,
+           const float* __restrict__ sdf, int n, int pitch, int Rc, float inv_s, int per, float* __restrict__ newz) {
+  __shared__ float s_z[8][kPlaceMaxN];
+  __shared__ float s_cdf[8][kPlaceMaxN];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + wib;
   if (r >= Rc) return;
+  float* sz = s_z[wib];
+  float* scdf = s_cdf[wib];
   const float o[3] = {rays_o[r * 3], rays_o[r * 3 + 1], rays_o[r * 3 + 2]};
   const float d[3] = {rays_d[r * 3], rays_d[r * 3 + 1], rays_d[r * 3 + 2]};
-  float z_prev = z[r], s_prev = sdf[r];
-  float rad_prev = ray_radius(o, d, z_prev);
-  float prev_cos = 0.f, T = 1.f, wsum = 0.f;
-  for (int j = 0; j + 1 < n; ++j) {
-    float z_next = z[(size_t)(j + 1) * Rc + r], s_next = sdf[(size_t)(j + 1) * Rc + r];
-    float rad_next = ray_radius(o, d, z_next);
-    float inside = (rad_prev < 1.0f || rad_next < 1.0f) ? 1.f : 0.f;
-    float mid_sdf = __fmul_rn(__fadd_rn(s_prev, s_next), 0.5f);
-    float dist = __fsub_rn(z_next, z_prev);
-    float cosv = __fdiv_rn(__fsub_rn(s_next, s_prev), __fadd_rn(dist, 1e-5f));
-    float cm = fminf(prev_cos, cosv);
-    prev_cos = cosv;
-    cm = fminf(fmaxf(cm, -1e3f), 0.0f) * inside;
-    float half = __fmul_rn(__fmul_rn(cm, dist), 0.5f);
-    float prev_esti = __fsub_rn(mid_sdf, half);
-    float next_esti = __fadd_rn(mid_sdf, half);
-    float pc = sigmoidf_acc(__fmul_rn(prev_esti, inv_s));
-    float nc = sigmoidf_acc(__fmul_rn(next_esti, inv_s));
-    float alpha = __fdiv_rn(__fadd_rn(__fsub_rn(pc, nc), 1e-5f), __fadd_rn(pc, 1e-5f));
-    float w = __fadd_rn(__fmul_rn(alpha, T), 1e-5f);          // weights + 1e-5 (renderer.py:41)
-    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f));
-    wscr[(size_t)j * Rc + r] = w;
-    wsum = __fadd_rn(wsum, w);
-    z_prev = z_next; s_prev = s_next; rad_prev = rad_next;
-  }
-  // inverse CDF with a two-pointer walk: cdf[0] = 0, cdf[k] = cdf[k-1] + pdf[k-1], k < n
-  int k = 1;
-  float c_km1 = 0.f;
-  float c_k = __fdiv_rn(wscr[r], wsum);
-  float ustart = 0.5f / (float)per, uend = 1.0f - 0.5f / (float)per;
-  for (int t = 0; t < per; ++t) {
-    float u = torch_linspace(ustart, uend, per, t);
-    while (k < n && c_k <= u) {       // searchsorted(right=True): count of entries <= u
-      c_km1 = c_k;
-      ++k;
-      if (k < n) c_k = __fadd_rn(c_km1, __fdiv_rn(wscr[(size_t)(k - 1) * Rc + r], wsum));
+  const float* zr = z + (size_t)r * pitch;
+  const float* sr = sdf + (size_t)r * pitch;
+  const int nsec = n - 1;
+  const int nb = (nsec + 31) >> 5;
+  float wreg[kPlaceMaxN / 32];
+  float carry_cos = 0.f, carry_T = 1.f, wsum = 0.f;
+  for (int j = lane; j < n; j += 32) sz[j] = zr[j];
+#pragma unroll
+  for (int b = 0; b < kPlaceMaxN / 32; ++b) {
+    wreg[b] = 0.f;
+    if (b >= nb) continue;
+    const int j = b * 32 + lane;
+    const bool ok = j < nsec;
+    float z0 = 0.f, z1 = 0.f, s0 = 0.f, s1 = 0.f;
+    if (ok) { z0 = zr[j]; z1 = zr[j + 1]; s0 = sr[j]; s1 = sr[j + 1]; }
+    const float dist = __fsub_rn(z1, z0);
+    float cosv = ok ? __fdiv_rn(__fsub_rn(s1, s0), __fadd_rn(dist, 1e-5f)) : 0.f;
+    float prev = __shfl_up_sync(0xffffffffu, cosv, 1);
+    if (lane == 0) prev = carry_cos;                              // prev_cos of the first section is 0 (:162)
+    carry_cos = __shfl_sync(0xffffffffu, cosv, 31);
+    float alpha = 0.f;
+    if (ok) {
+      float inside = (ray_radius(o, d, z0) < 1.0f || ray_radius(o, d, z1) < 1.0f) ? 1.f : 0.f;
+      float cm = fminf(fmaxf(fminf(prev, cosv), -1e3f), 0.0f) * inside;
+      float mid_sdf = __fmul_rn(__fadd_rn(s0, s1), 0.5f);
+      float half = __fmul_rn(__fmul_rn(cm, dist), 0.5f);
+      float pc = sigmoidf_acc(__fmul_rn(__fsub_rn(mid_sdf, half), inv_s));
+      float nc = sigmoidf_acc(__fmul_rn(__fadd_rn(mid_sdf, half), inv_s));
+      alpha = __fdiv_rn(__fadd_rn(__fsub_rn(pc, nc), 1e-5f), __fadd_rn(pc, 1e-5f));
     }
-    int below = k - 1;
-    int above = (k < n) ? k : n - 1;
-    float cb = c_km1, ca = (k < n) ? c_k : c_km1;
-    float zb = z[(size_t)below * Rc + r], za = z[(size_t)above * Rc + r];
+    float total;
+    float T = carry_T * warp_excl_prod_f(ok ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f) : 1.f, &total);
+    carry_T *= total;
+    float w = ok ? __fadd_rn(__fmul_rn(alpha, T), 1e-5f) : 0.f;    // weights + 1e-5 (renderer.py:41)
+    wreg[b] = w;
+    wsum += w;
+  }
+  wsum = warp_sum(wsum);
+  // cdf[0] = 0, cdf[j+1] = cdf[j] + w_j / sum
+  float carry = 0.f;
+  if (lane == 0) scdf[0] = 0.f;
+#pragma unroll
+  for (int b = 0; b < kPlaceMaxN / 32; ++b) {
+    if (b >= nb) continue;
+    const int j = b * 32 + lane;
+    float inc = __fdiv_rn(wreg[b], wsum);
+#pragma unroll
+    for (int of = 1; of < 32; of <<= 1) {
+      float t = __shfl_up_sync(0xffffffffu, inc, of);
+      if (lane >= of) inc += t;
+    }
+    if (j < nsec) scdf[j + 1] = carry + inc;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+  const float ustart = 0.5f / (float)per, uend = 1.0f - 0.5f / (float)per;
+  for (int t = lane; t < per; t += 32) {
+    const float u = torch_linspace(ustart, uend, per, t);
+    int lo = 0, hi = n;                       // searchsorted(right=True): number of cdf entries <= u
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (scdf[mid] <= u) lo = mid + 1; else hi = mid; }
+    const int below = max(lo - 1, 0), above = min(lo, n - 1);
+    const float cb = scdf[below], ca = scdf[above], zb = sz[below], za = sz[above];
     float denom = __fsub_rn(ca, cb);
     if (denom < 1e-5f) denom = 1.0f;
-    float tt = __fdiv_rn(__fsub_rn(u, cb), denom);
-    newz[(size_t)t * Rc + r] = __fadd_rn(zb, __fmul_rn(tt, __fsub_rn(za, zb)));
+    const float tt = __fdiv_rn(__fsub_rn(u, cb), denom);
+    newz[(size_t)r * per + t] = __fadd_rn(zb, __fmul_rn(tt, __fsub_rn(za, zb)));
   }
 }
 
-// cat_z_vals (renderer.py:179-193): merge two ascending lists (old entries first on ties).
-// When out_raymajor != NULL the merged depths are also written ray-major [r][n+per] (final round).
-__global__ void k_merge(const float* __restrict__ z, const float* __restrict__ sdf, int n,
-                        const float* __restrict__ newz, const float* __restrict__ news, int per, int Rc,
-                        float* __restrict__ zo, float* __restrict__ so, float* __restrict__ out_raymajor) {
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
+// cat_z_vals (renderer.py:179-193): merge two ascending lists (old entries first on ties) by rank computation:
+// rank(old i) = i + #{new < z_i}, rank(new t) = t + #{old <= newz_t}.  One warp per ray.
+__global__ void __launch_bounds__(256)
+k_merge(const float* __restrict__ z, const float* __restrict__ sdf, int n, int pitch, const float* __restrict__ newz,
+        const float* __restrict__ news, int per, int Rc, float* __restrict__ zo, float* __restrict__ so, int pitch_o) {
+  __shared__ float s_z[8][kPlaceMaxN];
+  __shared__ float s_n[8][kPlaceMaxNew];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + wib;
   if (r >= Rc) return;
-  int a = 0, b = 0;
-  float za = z[r], zb = newz[r];
-  for (int o = 0; o < n + per; ++o) {
-    bool take_a = (b >= per) || (a < n && za <= zb);
-    float zv, sv = 0.f;
-    if (take_a) {
-      zv = za;
-      if (news) sv = sdf[(size_t)a * Rc + r];
-      ++a;
-      if (a < n) za = z[(size_t)a * Rc + r];
-    } else {
-      zv = zb;
-      if (news) sv = news[(size_t)b * Rc + r];
-      ++b;
-      if (b < per) zb = newz[(size_t)b * Rc + r];
-    }
-    zo[(size_t)o * Rc + r] = zv;
-    if (news) so[(size_t)o * Rc + r] = sv;
-    if (out_raymajor) out_raymajor[(size_t)r * (n + per) + o] = zv;
+  float* sz = s_z[wib];
+  float* sn = s_n[wib];
+  for (int j = lane; j < n; j += 32) sz[j] = z[(size_t)r * pitch + j];
+  for (int t = lane; t < per; t += 32) sn[t] = newz[(size_t)r * per + t];
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const float v = sz[i];
+    int lo = 0, hi = per;                    // # new strictly less than v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sn[mid] < v) lo = mid + 1; else hi = mid; }
+    zo[(size_t)r * pitch_o + i + lo] = v;
+    if (news) so[(size_t)r * pitch_o + i + lo] = sdf[(size_t)r * pitch + i];
   }
-}
-
-__global__ void k_transpose_z(const float* __restrict__ z, int n, int Rc, float* __restrict__ out_raymajor) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)n * Rc) return;
-  int r = (int)(i / n), j = (int)(i % n);
-  out_raymajor[i] = z[(size_t)j * Rc + r];
+  for (int t = lane; t < per; t += 32) {
+    const float v = sn[t];
+    int lo = 0, hi = n;                      // # old less than or equal to v
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (sz[mid] <= v) lo = mid + 1; else hi = mid; }
+    zo[(size_t)r * pitch_o + t + lo] = v;
+    if (news) so[(size_t)r * pitch_o + t + lo] = news[(size_t)r * per + t];
+  }
 }
 
 // =============================================================================================
@@ -371,9 +408,12 @@ k_thin_nt(const float* __restrict__ A, int lda, int K, const float* __restrict__
   if (lane == 0) out(p, acc);
 }
 
-struct OutSdf {     // sdf = z_L[0] / scale   (models/fields.py:88)
-  float* sdf; float inv_scale;
-  __device__ void operator()(int64_t p, const float* v) const { sdf[p] = v[0] * inv_scale; }
+struct OutSdf {     // sdf = z_L[0] / scale   (models/fields.py:88); point p = r * nz + j is stored at [r][j] (row pitch)
+  float* sdf; float inv_scale; int nz; int pitch;
+  __device__ void operator()(int64_t p, const float* v) const {
+    int64_t o = nz > 0 ? (p / nz) * pitch + (p % nz) : p;
+    sdf[o] = v[0] * inv_scale;
+  }
 };
 struct OutHeads {   // sigmoid of both colour heads (models/fields.py:180-184) -> rgb6[p][8]
   float* rgb6;
