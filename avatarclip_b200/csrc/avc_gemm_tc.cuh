@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "avc_common.cuh"
 
 namespace avc {
@@ -390,8 +392,12 @@ static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, co
                                     const Epi& epi) {
   if (M <= 0 || N <= 0) return 0;
   if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, Epi>(st, M, N, K, A, B, epi);
-  if (N <= 128) return launch_gemm_tc_nt_bn<128, NPROD, Epi>(st, M, N, K, A, B, epi);
-  return launch_gemm_tc_nt_bn<256, NPROD, Epi>(st, M, N, K, A, B, epi);
+  // N > 128 is covered by several 128-wide tiles: with one 256-wide tile per 128 rows a 65536-row GEMM has 512 tiles
+  // = 3.46 waves over 148 persistent CTAs (13 % tail); 1024 tiles = 6.9 waves (1.4 % tail), 3 pipeline stages fit
+  static int wide = -1;       // AVC_TC_BN=256 selects one 256-wide tile per 128 rows instead (tuning knob)
+  if (wide < 0) { const char* e = getenv("AVC_TC_BN"); wide = (e && atoi(e) == 256) ? 1 : 0; }
+  if (wide && N > 128) return launch_gemm_tc_nt_bn<256, NPROD, Epi>(st, M, N, K, A, B, epi);
+  return launch_gemm_tc_nt_bn<128, NPROD, Epi>(st, M, N, K, A, B, epi);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel
@@ -408,8 +414,8 @@ struct TcTnCfg {
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+  static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;        // 33,792 B (a multiple of 1024: the ones tile stays aligned)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + BLK + 768;
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
@@ -417,13 +423,16 @@ template <int BN, int NPROD>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                  int P, int N1, int N2, int rows_per_split, float* __restrict__ C, int ldc) {
+                  int P, int N1, int N2, int rows_per_split, float* __restrict__ C, int ldc,
+                  float* __restrict__ colsum /* += sum_p A[p,i]; nullptr: off */) {
   using Cfg = TcTnCfg<BN, NPROD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
   float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  uint8_t* ones_tile = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::EPI_BYTES;   // 8 KB of bf16 1.0 (1024-B aligned)
+  const bool do_colsum = (colsum != nullptr) && (blockIdx.y == 0);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
 
@@ -439,7 +448,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     mbar_init(tfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);   // BN accumulator columns + 16 for the column sums (power of 2)
+  if (do_colsum) {   // any layout of an all-ones tile is the all-ones tile
+    for (int i = threadIdx.x; i < Cfg::BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3F803F80u;
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -472,6 +485,8 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+      constexpr uint32_t idesc1 = make_idesc_bf16(kBM, 16, 1, 1);
+      const uint32_t ones_addr = smem_u32(ones_tile);
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % Cfg::STAGES;
         mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
@@ -488,6 +503,11 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
             const uint64_t dbl = make_smem_desc(b_lo + k4 * 2048, Cfg::BLK, 1024);
             umma_f16(tmem_base, dah, dbl, idesc, 1u);
             umma_f16(tmem_base, dal, dbh, idesc, 1u);
+          }
+          if (do_colsum) {      // D2[128 x 16] += A^T . ones : every column of D2 is the column sum of A
+            const uint64_t dones = make_smem_desc(ones_addr, Cfg::BLK, 1024);
+            umma_f16(tmem_base + BN, dah, dones, idesc1, (kb | k4) ? 1u : 0u);
+            if (NPROD == 3) umma_f16(tmem_base + BN, make_smem_desc(a_lo + k4 * 2048, Cfg::BLK, 1024), dones, idesc1, 1u);
           }
         }
         umma_commit(empty0 + 8 * s);
@@ -512,19 +532,24 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
         epilogue_block_transposed(stage, r, lane, row0, nrows, col0, min(32, N2 - col0),
                                   [&](int rr, int cc, float v) { atomicAdd(C + (size_t)rr * ldc + cc, v); });
     }
+    if (do_colsum && warp < 6) {   // warps 2-5: one per TMEM lane quarter
+      uint32_t r16[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)BN, r16);
+      if (row0 + lane < N1) atomicAdd(colsum + row0 + lane, __uint_as_float(r16[0]));
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
 // A: [P][N1] (ld A.ld), B: [P][N2] (ld B.ld); C[N1][ldc] += A^T B.
 template <int NPROD>
 static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, const SplitPtr& A, const SplitPtr& B,
-                                    float* C, int ldc) {
+                                    float* C, int ldc, float* colsum = nullptr) {
   if (P <= 0 || N1 <= 0 || N2 <= 0) return 0;
   CUtensorMap mAh, mAl, mBh, mBl;
   AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)P, (uint64_t)N1, (uint64_t)A.ld, 64, kBK));
@@ -543,7 +568,7 @@ static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, 
     int rows = (int)round_up(ceil_div(P, splits), kBK);
     splits = ceil_div(P, rows);
     dim3 grid(t1, t2, splits);
-    kern<<<grid, kTcThreads, smem, st>>>(mAh, mAl, mBh, mBl, (int)P, N1, N2, rows, C, ldc);
+    kern<<<grid, kTcThreads, smem, st>>>(mAh, mAl, mBh, mBl, (int)P, N1, N2, rows, C, ldc, colsum);
     AVC_LAUNCH_TRY();
     return 0;
   };

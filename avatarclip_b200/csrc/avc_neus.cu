@@ -39,14 +39,21 @@ int gemm_nt(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int
   return launch_gemm_nt(st, M, N, (int)round_up(K, 4), A, lda, w.pack + pk_off, ldb, epi);
 }
 
+int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float scale, float* out);
+
+// C[N1][ldc] += A^T B ; optionally bias_out[i] += sum_p A[p,i] (the bias gradient of the same linear): fused into the
+// tcgen05 kernel as one extra 16-wide MMA against a tile of ones, a separate column-sum kernel for the fp32 engine.
 inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t P, int N1, int N2, const float* A,
-                   int lda, const Split16& A16, const float* B, int ldb, const Split16& B16, float* C, int ldc) {
+                   int lda, const Split16& A16, const float* B, int ldb, const Split16& B16, float* C, int ldc,
+                   float* bias_out = nullptr) {
   (void)w;
   if (pl.cfg.engine == 1) {
     tc::SplitPtr a{A16.hi, A16.lo, lda}, b{B16.hi, B16.lo, ldb};
-    return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, ldc);
+    return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, ldc, bias_out);
   }
-  return launch_gemm_tn(st, P, N1, N2, A, lda, B, ldb, C, ldc);
+  AVC_TRY(launch_gemm_tn(st, P, N1, N2, A, lda, B, ldb, C, ldc));
+  if (bias_out) AVC_TRY(colsum(st, A, lda, N1, P, 1.f, bias_out));
+  return 0;
 }
 
 // -------------------------------------------------------------------------------- packing
@@ -248,7 +255,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   {
     const LinDim& dL = pl.sdf[pl.L];
     const LinDim& dp = pl.sdf[pl.L - 1];
-    int64_t tot = P * (int64_t)(dp.Np > pl.EP ? dp.Np : pl.EP);
+    int64_t tot = P * (int64_t)(dp.Np / 4 > pl.EP ? dp.Np / 4 : pl.EP);   // threads: 4 qt columns each, 1 ge entry each
     k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
                                                         w.z[pl.L - 1], dp.N, dp.Np, P, w.qt[pl.L - 1], w.ge,
                                                         w.qt16[pl.L - 1]);
@@ -340,7 +347,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const LinDim& dx = pl.extra;
     AVC_TRY(thin_tn<3>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b));
     AVC_TRY(thin_tn<3>(st, w.y6bar + 3, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dx.off_v, pl.Hc, 1, wbar + dx.off_b));
-    k_heads_dgrad<<<blocks_for(P * pl.Hc, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0],
+    k_heads_dgrad<<<blocks_for(P * pl.Hc / 4, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0],
                                                               w.cbar16[0]);
     AVC_LAUNCH_TRY();
   }
@@ -349,15 +356,16 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
   for (int l = pl.Lc - 1; l >= 0; --l) {
     const LinDim& c = pl.col[l];
     float* cb = w.cbar[cur];
-    AVC_TRY(colsum(st, cb, pl.Hc, pl.Hc, P, 1.f, wbar + c.off_b));
     if (l > 0) {
-      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], w.ch[l], pl.Hc, w.ch16[l], wbar + c.off_v, c.K));
+      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], w.ch[l], pl.Hc, w.ch16[l], wbar + c.off_v, c.K,
+                      wbar + c.off_b));
       EpiDgradRelu e{w.ch[l], w.cbar[cur ^ 1], pl.Hc, w.cbar16[cur ^ 1]};
       AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, e));
       cur ^= 1;
     } else {
       // lin0 input = [x(3), n(3), feat(F)]: dW[:, 6:] += cbar^T feat ; dW[:, :6] += cbar^T cin6
-      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.F, cb, pl.Hc, w.cbar16[cur], w.feat, pl.Fp, w.feat16, wbar + c.off_v + 6, c.K));
+      AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.F, cb, pl.Hc, w.cbar16[cur], w.feat, pl.Fp, w.feat16, wbar + c.off_v + 6, c.K,
+                      wbar + c.off_b));
       AVC_TRY(thin_tn<6>(st, w.cin, 8, 1.f, cb, pl.Hc, pl.Hc, P, wbar + c.off_v, 1, c.K, nullptr));
       // featbar = cbar . W0[:, 6:]
       EpiStore es{w.featbar, pl.Fp, pl.F, w.featbar16};
@@ -411,8 +419,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     // last linear: row 0 (sdf) via thin ops, rows 1.. (features) via the GEMM tiles
     AVC_TRY(thin_tn<1>(st, w.sdfbar, 1, inv_scale, w.in[pl.L], dL.Kp, dL.K, P, wbar + dL.off_v, 0, 1, wbar + dL.off_b));
     AVC_TRY(gemm_tn(pl, w, st, P, pl.F, dL.K, w.featbar, pl.Fp, w.featbar16, w.in[pl.L], dL.Kp, w.in16[pl.L],
-                    wbar + dL.off_v + dL.K, dL.K));
-    AVC_TRY(colsum(st, w.featbar, pl.Fp, pl.F, P, 1.f, wbar + dL.off_b + 1));
+                    wbar + dL.off_v + dL.K, dL.K, wbar + dL.off_b + 1));
     const LinDim& dp = pl.sdf[pl.L - 1];
     EpiDgrad e;
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = dL.skip ? kSqrtHalf : 1.f;
@@ -423,8 +430,8 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
   }
   for (int l = pl.L - 1; l >= 0; --l) {
     const LinDim& d = pl.sdf[l];
-    AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.zbar[l], d.Np, w.zbar16[l], w.in[l], d.Kp, w.in16[l], wbar + d.off_v, d.K));
-    AVC_TRY(colsum(st, w.zbar[l], d.Np, d.N, P, 1.f, wbar + d.off_b));
+    AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.zbar[l], d.Np, w.zbar16[l], w.in[l], d.Kp, w.in16[l], wbar + d.off_v, d.K,
+                    wbar + d.off_b));
     if (l == 0) break;
     const LinDim& dp = pl.sdf[l - 1];
     EpiDgrad e;

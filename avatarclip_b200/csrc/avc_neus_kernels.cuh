@@ -497,19 +497,22 @@ k_colsum(const float* __restrict__ X, int ld, int NC, int64_t P, int rows_per_bl
 __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL, int E, int EP,
                               const float* __restrict__ zprev, int Nprev, int Npp, int64_t P,
                               float* __restrict__ qt, float* __restrict__ ge, Split16 qt16) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 4 consecutive columns per thread (Npp % 4 == 0)
+  int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   int64_t tot = P * (int64_t)Npp;
-  if (i < tot) {
-    int64_t p = i / Npp;
-    int c = (int)(i - p * Npp);
-    float v = 0.f;
-    if (c < Nprev) {
-      float ua = wsdf[c] * (skipL ? kSqrtHalf : 1.f);
-      v = softplus100_d1(zprev[i]) * ua;
-    }
-    qt[i] = v;
-    split16_put(qt16, (size_t)p, c, v);
+  if (i4 < tot) {
+    int64_t p = i4 / Npp;
+    int c = (int)(i4 - p * Npp);
+    const float4 z = *reinterpret_cast<const float4*>(zprev + i4);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      v[i] = (c + i < Nprev) ? softplus100_d1(zz[i]) * wsdf[c + i] * (skipL ? kSqrtHalf : 1.f) : 0.f;
+    *reinterpret_cast<float4*>(qt + i4) = make_float4(v[0], v[1], v[2], v[3]);
+    split16_put4(qt16, (size_t)p, c, v);
   }
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P * (int64_t)EP) {
     int64_t p = i / EP;
     int e = (int)(i - p * EP);
@@ -585,17 +588,25 @@ __global__ void k_fill_gebar(const float* __restrict__ gebar, int EP, int E, int
 // cbar[p][c] = (sum_i y6bar[p][i] * W6[i][c]) * [h[p][c] > 0]   (heads dgrad + ReLU mask)
 __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __restrict__ W6, int Hc,
                               const float* __restrict__ h, int64_t P, float* __restrict__ cbar, Split16 c16) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * (int64_t)Hc) return;
-  int64_t p = i / Hc;
-  int c = (int)(i - p * Hc);
-  const float* y = y6bar + (size_t)p * 8;
-  float acc = 0.f;
+  // 4 consecutive columns per thread (Hc % 4 == 0): float4 loads / stores
+  int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i4 >= P * (int64_t)Hc) return;
+  int64_t p = i4 / Hc;
+  int c = (int)(i4 - p * Hc);
+  const float4 y0 = *reinterpret_cast<const float4*>(y6bar + (size_t)p * 8);
+  const float4 y1 = *reinterpret_cast<const float4*>(y6bar + (size_t)p * 8 + 4);
+  const float y[6] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int k = 0; k < 6; ++k) acc = fmaf(y[k], W6[(size_t)k * Hc + c], acc);
-  float v = h[i] > 0.f ? acc : 0.f;
-  cbar[i] = v;
-  split16_put(c16, (size_t)p, c, v);
+  for (int k = 0; k < 6; ++k) {
+    const float4 w = *reinterpret_cast<const float4*>(W6 + (size_t)k * Hc + c);
+    acc[0] = fmaf(y[k], w.x, acc[0]); acc[1] = fmaf(y[k], w.y, acc[1]);
+    acc[2] = fmaf(y[k], w.z, acc[2]); acc[3] = fmaf(y[k], w.w, acc[3]);
+  }
+  const float4 hv = *reinterpret_cast<const float4*>(h + i4);
+  float v[4] = {hv.x > 0.f ? acc[0] : 0.f, hv.y > 0.f ? acc[1] : 0.f, hv.z > 0.f ? acc[2] : 0.f, hv.w > 0.f ? acc[3] : 0.f};
+  *reinterpret_cast<float4*>(cbar + i4) = make_float4(v[0], v[1], v[2], v[3]);
+  split16_put4(c16, (size_t)p, c, v);
 }
 
 // =============================================================================================

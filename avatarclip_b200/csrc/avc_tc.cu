@@ -41,7 +41,7 @@ int avc_tc_gemm_nt_test(const float* A, const float* B, int64_t M, int32_t N, in
 // C[N1][N2] += A[P][N1]^T . B[P][N2] through the tcgen05 TN (MN-major) tiles.  C must be initialised by the caller.
 // workspace >= 4 * P * (round_up(N1,8) + round_up(N2,8)) + 2048 bytes.
 int avc_tc_gemm_tn_test(const float* A, const float* B, int64_t P, int32_t N1, int32_t N2, int32_t nprod, float* C,
-                        void* workspace, size_t workspace_bytes, avc_stream_t stream) {
+                        float* colsum, void* workspace, size_t workspace_bytes, avc_stream_t stream) {
   if (!A || !B || !C || !workspace) return AVC_E_NULL;
   if (P <= 0 || N1 <= 0 || N2 <= 0 || (nprod != 1 && nprod != 3)) return AVC_E_SIZE;
   const int l1 = (int)round_up(N1, 8), l2 = (int)round_up(N2, 8);
@@ -56,8 +56,8 @@ int avc_tc_gemm_tn_test(const float* A, const float* B, int64_t P, int32_t N1, i
   tc::k_split_bf16<<<(int)((P * l2 + 255) / 256), 256, 0, st>>>(B, P, N2, N2, bh, bl, l2);
   AVC_LAUNCH_TRY();
   tc::SplitPtr a{ah, al, l1}, b{bh, bl, l2};
-  if (nprod == 3) return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, N2);
-  return tc::launch_gemm_tc_tn<1>(st, P, N1, N2, a, b, C, N2);
+  if (nprod == 3) return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, N2, colsum);
+  return tc::launch_gemm_tc_tn<1>(st, P, N1, N2, a, b, C, N2, colsum);
 }
 
 }  // extern "C"

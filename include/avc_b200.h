@@ -273,10 +273,11 @@ int avc_lbs_fwd(const float* v_shaped, const float* pose, int32_t pose2rot, cons
  * ------------------------------------------------------------------------------------------ */
 int avc_tc_gemm_nt_test(const float* A, const float* B, int64_t M, int32_t N, int32_t K, int32_t nprod,
                         float* C, void* workspace, size_t workspace_bytes, avc_stream_t stream);
-/* Same for the reduction-over-rows tiles (weight gradients): C[N1][N2] += A[P][N1]^T . B[P][N2].
+/* Same for the reduction-over-rows tiles (weight gradients): C[N1][N2] += A[P][N1]^T . B[P][N2]; when colsum is not
+ * NULL also colsum[N1] += column sums of A (the fused bias gradient).
  * workspace >= 4 * P * (round_up(N1,8) + round_up(N2,8)) + 2048 bytes. */
 int avc_tc_gemm_tn_test(const float* A, const float* B, int64_t P, int32_t N1, int32_t N2, int32_t nprod,
-                        float* C, void* workspace, size_t workspace_bytes, avc_stream_t stream);
+                        float* C, float* colsum, void* workspace, size_t workspace_bytes, avc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -45,7 +45,7 @@ def _run_tn(P, N1, N2, nprod, seed=0):
     from avatarclip_b200 import _lib
     L = _lib.lib()
     L.avc_tc_gemm_tn_test.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
-                                      C.c_void_p, C.c_size_t, C.c_void_p]
+                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.avc_tc_gemm_tn_test.restype = C.c_int
     g = torch.Generator().manual_seed(seed)
     A = torch.randn(P, N1, generator=g).cuda()
@@ -54,10 +54,14 @@ def _run_tn(P, N1, N2, nprod, seed=0):
     Cm = base.clone()
     r8 = lambda n: (n + 7) // 8 * 8
     ws = torch.empty(4 * P * (r8(N1) + r8(N2)) + 8192, dtype=torch.uint8, device="cuda")
-    _lib.check(L.avc_tc_gemm_tn_test(A.data_ptr(), B.data_ptr(), P, N1, N2, nprod, Cm.data_ptr(), ws.data_ptr(),
-                                     ws.numel(), _lib.stream_ptr()), "avc_tc_gemm_tn_test")
+    cs = torch.ones(N1, device="cuda")
+    _lib.check(L.avc_tc_gemm_tn_test(A.data_ptr(), B.data_ptr(), P, N1, N2, nprod, Cm.data_ptr(), cs.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "avc_tc_gemm_tn_test")
     torch.cuda.synchronize()
     ref = base.double() + A.double().t() @ B.double()
+    cref = 1.0 + A.double().sum(0)
+    cerr = (cs.double() - cref).abs().max().item() / cref.abs().max().item()
+    assert cerr < 3e-5, ("fused column sum", cerr)
     return (Cm.double() - ref).abs().max().item() / ref.abs().max().item()
 
 
