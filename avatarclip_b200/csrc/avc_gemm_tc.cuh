@@ -192,6 +192,7 @@ struct TcCfg {
   static constexpr int EPI_BYTES = kNtEpiWarps * 32 * 16 * 4;       // per-warp 32x16 fp32 transpose buffers (XOR-swizzled)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 // TMEM -> registers gives every thread one ROW (32 consecutive columns).  Writing that out directly would make each
@@ -415,7 +416,8 @@ struct TcTnCfg {
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
   static constexpr int EPI_BYTES = kEpiWarps * 32 * 33 * 4;        // 33,792 B (a multiple of 1024: the ones tile stays aligned)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + BLK + 768;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
   static_assert(STAGES >= 2, "tile too large for shared memory");
 };
 
@@ -431,7 +433,9 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 1);
   float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
-  uint8_t* ones_tile = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + Cfg::EPI_BYTES;   // 8 KB of bf16 1.0 (1024-B aligned)
+  // 2 KB of bf16 1.0 aliased onto the epilogue staging area: the MMAs that read it have all completed (tfull) before
+  // any epilogue warp writes its staging tile
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(epi_stage);
   const bool do_colsum = (colsum != nullptr) && (blockIdx.y == 0);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull = empty0 + 8 * Cfg::STAGES;
@@ -450,7 +454,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);   // BN accumulator columns + 16 for the column sums (power of 2)
   if (do_colsum) {   // any layout of an all-ones tile is the all-ones tile
-    for (int i = threadIdx.x; i < Cfg::BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3F803F80u;
+    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones_tile)[i] = 0x3F803F80u;
     fence_proxy_async();
   }
   tc_fence_before();
