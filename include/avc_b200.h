@@ -254,6 +254,16 @@ int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   avc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Camera rays: SMPL_Dataset.gen_rays_pose / gen_rays_silhouettes + near_far_from_sphere
+ * (models/dataset.py:252-293, 331-342).  pose_c2w is a HOST pointer to the 4x4 row-major camera-to-world matrix
+ * (lookat, models/utils.py:9-27).  Pixel grid: linspace(0, full-1, W) x linspace(0, full-1, H).  pix[R] lists the
+ * selected canvas pixels (y*W + x; the True entries of the dilated mask) or is NULL for all W*H pixels.
+ * ------------------------------------------------------------------------------------------ */
+int avc_gen_rays(const float* pose_c2w, float fx, float fy, float cx, float cy, int32_t full_w, int32_t full_h,
+                 int32_t W, int32_t H, const int32_t* pix, int32_t R, float* rays_o, float* rays_d, float* near,
+                 float* far, avc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * SMPL linear-blend skinning: my_lbs(v_shaped, pose, v_template, shapedirs, posedirs, J_regressor, parents,
  * lbs_weights, pose2rot) of models/utils.py:176-224 (batch 1; v_template / shapedirs are unused by the reference
  * function and therefore absent here).  pose: [n_joints*3] axis-angle when pose2rot != 0, else [n_joints][3][3]
