@@ -16,6 +16,25 @@ using namespace avc;
 
 namespace {
 
+// Programmatic dependent launch: the tower is a chain of ~230 tiny dependent kernels.  Every kernel lets its
+// successor start launching at once (launch_dependents) and itself waits for its predecessor's completion and memory
+// flush (griddepcontrol.wait) before touching global memory, so launch latency and tail drain overlap.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 
 
 // ------------------------------------------------------------------------------------------------
@@ -39,6 +58,7 @@ template <typename Epi>
 __global__ void __launch_bounds__(128)
 k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
          int k_per_split, Epi epi) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char g_smem[];
   __half (*sA)[GBM][GBK + GPAD] = reinterpret_cast<__half (*)[GBM][GBK + GPAD]>(g_smem);
   __half (*sW)[GBN][GBK + GPAD] =
@@ -132,7 +152,7 @@ int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw,
     AVC_CUDA_TRY(cudaFuncSetAttribute(k_gemm16<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     attr_set = true;
   }
-  k_gemm16<Epi><<<grid, 128, G_SMEM, st>>>(A, lda, Wt, ldw, M, N, K, kper, epi);
+  AVC_CUDA_TRY(launch_pdl(k_gemm16<Epi>, dim3(grid), dim3(128), G_SMEM, st, A, lda, Wt, ldw, M, N, K, kper, epi));
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -219,6 +239,7 @@ __device__ __forceinline__ ResizeTap resize_tap(int dst, float scale, int in) {
 
 __global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int B, int IS, int P,
                              __half* __restrict__ a0, int mode) {
+  pdl_enter();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t tot = (int64_t)B * 3 * IS * IS;
   if (i >= tot) return;
@@ -247,6 +268,7 @@ __global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int
 // adjoint: d canvas += bilinear^T ( d img / std ), d img read from the im2col gradient
 __global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W, int B, int IS, int P,
                                  float* __restrict__ dcanvas, int mode) {
+  pdl_enter();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t tot = (int64_t)B * 3 * IS * IS;
   if (i >= tot) return;
@@ -270,6 +292,7 @@ __global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W,
 // token buffer initialisation: row 0 = class_embedding + pos[0], rows 1.. = pos[t] (the patch GEMM adds onto them)
 __global__ void k_cls_rows(const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
                            float* __restrict__ x) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T * Wd) return;
   int c = i % Wd, t = (i / Wd) % T;
@@ -279,66 +302,96 @@ __global__ void k_cls_rows(const float* __restrict__ cls, const float* __restric
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (fp32 statistics, eps 1e-5): one warp per row.
 // ------------------------------------------------------------------------------------------------
+// Rows are cached in registers (Wd <= 32 * kLnMax): one round trip to memory per operand instead of one per pass.
+constexpr int kLnMax = 32;
+
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
             float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
+  pdl_enter();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * Wd;
+  float xv[kLnMax];
   float s = 0.f;
-  for (int c = lane; c < Wd; c += 32) s += xr[c];
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) { int c = lane + 32 * i; xv[i] = (c < Wd) ? xr[c] : 0.f; s += xv[i]; }
   float mean = warp_sum(s) / (float)Wd;
   float v = 0.f;
-  for (int c = lane; c < Wd; c += 32) { float d = xr[c] - mean; v += d * d; }
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) { int c = lane + 32 * i; float d = (c < Wd) ? xv[i] - mean : 0.f; v += d * d; }
   float rstd = rsqrtf(warp_sum(v) / (float)Wd + 1e-5f);
-  for (int c = lane; c < Wd; c += 32) {
-    float xv = xr[c];
-    float yv = (xv - mean) * rstd * g[c] + b[c];
-    if (y32) y32[(size_t)row * Wd + c] = yv;
-    if (y16) y16[(size_t)row * Wd + c] = __float2half_rn(yv);
-    if (save_x) save_x[(size_t)row * Wd + c] = xv;
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) {
+    int c = lane + 32 * i;
+    if (c < Wd) {
+      float yv = (xv[i] - mean) * rstd * g[c] + b[c];
+      if (y32) y32[(size_t)row * Wd + c] = yv;
+      if (y16) y16[(size_t)row * Wd + c] = __float2half_rn(yv);
+      if (save_x) save_x[(size_t)row * Wd + c] = xv[i];
+    }
   }
 }
 
-// dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat))
+// dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); optionally also the row-scaled fp16
+// copy of the updated dx row (operand of the next input-gradient GEMM)
 __global__ void __launch_bounds__(256)
 k_layernorm_bwd(const float* __restrict__ x, const float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
                 float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx,
                 __half* __restrict__ dx16, float* __restrict__ dx_scale) {
+  pdl_enter();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * row_stride_x;
   const float* dr = dy + (size_t)row * row_stride_dy;
+  float* o = dx + (size_t)row * row_stride_dx;
+  float xv[kLnMax], dg[kLnMax], ov[kLnMax];
   float s = 0.f;
-  for (int c = lane; c < Wd; c += 32) s += xr[c];
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) {
+    int c = lane + 32 * i;
+    bool ok = c < Wd;
+    xv[i] = ok ? xr[c] : 0.f;
+    dg[i] = ok ? dr[c] * g[c] : 0.f;
+    ov[i] = (ok && accumulate) ? o[c] : 0.f;
+    s += xv[i];
+  }
   float mean = warp_sum(s) / (float)Wd;
   float v = 0.f;
-  for (int c = lane; c < Wd; c += 32) { float d = xr[c] - mean; v += d * d; }
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) { int c = lane + 32 * i; float d = (c < Wd) ? xv[i] - mean : 0.f; v += d * d; }
   float rstd = rsqrtf(warp_sum(v) / (float)Wd + 1e-5f);
   float a = 0.f, bq = 0.f;
-  for (int c = lane; c < Wd; c += 32) {
-    float dg = dr[c] * g[c];
-    a += dg; bq += dg * (xr[c] - mean) * rstd;
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) {
+    int c = lane + 32 * i;
+    if (c < Wd) { a += dg[i]; bq += dg[i] * (xv[i] - mean) * rstd; }
   }
   a = warp_sum(a) / (float)Wd; bq = warp_sum(bq) / (float)Wd;
-  float* o = dx + (size_t)row * row_stride_dx;
   float mx = 0.f;
-  for (int c = lane; c < Wd; c += 32) {
-    float xh = (xr[c] - mean) * rstd;
-    float r = rstd * (dr[c] * g[c] - a - xh * bq);
-    r = accumulate ? o[c] + r : r;
-    o[c] = r;
-    mx = fmaxf(mx, fabsf(r));
+#pragma unroll
+  for (int i = 0; i < kLnMax; ++i) {
+    int c = lane + 32 * i;
+    if (c < Wd) {
+      float xh = (xv[i] - mean) * rstd;
+      float r = ov[i] + rstd * (dg[i] - a - xh * bq);
+      ov[i] = r;
+      o[c] = r;
+      mx = fmaxf(mx, fabsf(r));
+    }
   }
-  if (dx16) {      // fused k_to_half_rowscaled of the updated row (operand of the next input-gradient GEMM)
+  if (dx16) {
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
     float sc = 1.f;
     if (mx > 0.f && isfinite(mx)) { int e; frexpf(mx, &e); sc = ldexpf(1.f, 1 - e); }
-    __syncwarp();
-    for (int c = lane; c < Wd; c += 32) dx16[(size_t)row * Wd + c] = __float2half_rn(o[c] * sc);
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+      int c = lane + 32 * i;
+      if (c < Wd) dx16[(size_t)row * Wd + c] = __float2half_rn(ov[i] * sc);
+    }
     if (lane == 0) dx_scale[row] = sc;
   }
 }
@@ -348,6 +401,7 @@ k_layernorm_bwd(const float* __restrict__ x, const float* __restrict__ dy, int M
 __global__ void __launch_bounds__(256)
 k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __half* __restrict__ dst,
                     float* __restrict__ scale, const int* __restrict__ row_map) {
+  pdl_enter();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -380,6 +434,7 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 
 __global__ void __launch_bounds__(512)
 k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   float* q = sm;                  // [T][AP]
   float* k = q + AT * AP;
@@ -436,6 +491,7 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
 __global__ void __launch_bounds__(512)
 k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
                 float* __restrict__ dqkv) {
+  pdl_enter();
   extern __shared__ __align__(16) float sm[];
   float* q = sm;
   float* k = q + AT * AP;
@@ -510,6 +566,7 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
 __global__ void __launch_bounds__(256)
 k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
             const float* __restrict__ proj, int OD, float* __restrict__ emb, float* __restrict__ ynorm) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* y = sm;               // [Wd]
   float* part = y + Wd;        // [4][64]
@@ -561,6 +618,7 @@ k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict_
 // cosine(emb[b], text[b]); torch.cosine_similarity: x.y / max(||x|| * ||y||, 1e-8)
 __global__ void __launch_bounds__(256)
 k_cosine(const float* __restrict__ emb, const float* __restrict__ text, int OD, float* __restrict__ cos_out) {
+  pdl_enter();
   __shared__ float red[3][8];
   const int b = blockIdx.x;
   float ee = 0.f, tt = 0.f, et = 0.f;
@@ -583,6 +641,7 @@ __global__ void __launch_bounds__(256)
 k_head_bwd_dy(int Wd, const float* __restrict__ proj, int OD, const float* __restrict__ text,
               const float* __restrict__ emb, const float* __restrict__ g_cos, const float* __restrict__ g_emb,
               float* __restrict__ dy_out, int rows_per_cta) {
+  pdl_enter();
   extern __shared__ float sm[];
   float* de = sm;            // [OD]
   __shared__ float red[3][8];
@@ -620,6 +679,7 @@ k_head_bwd_dy(int Wd, const float* __restrict__ proj, int OD, const float* __res
 __global__ void __launch_bounds__(256)
 k_head_bwd_ln(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ dy_in,
               float* __restrict__ dx) {
+  pdl_enter();
   __shared__ float red[3][8];
   const int b = blockIdx.x;
   const float* xr = x + (size_t)b * T * Wd;
@@ -660,6 +720,7 @@ k_head_bwd_ln(const float* __restrict__ x, int T, int Wd, const float* __restric
 }
 
 __global__ void k_patch_row_map(int B, int T, int* __restrict__ map) {
+  pdl_enter();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int np = T - 1;
   if (i >= B * np) return;
@@ -701,6 +762,7 @@ int clip_dims(const avc_clip_cfg* c, int* T, int* np, int* pp3) {
   *np = g * g; *T = *np + 1; *pp3 = 3 * c->patch * c->patch;
   if (*T > AT) return AVC_E_BADCFG;
   if (c->width % 64 || c->heads <= 0 || c->width / c->heads != AD || c->width % c->heads) return AVC_E_BADCFG;
+  if (c->width > 32 * kLnMax) return AVC_E_BADCFG;
   if (c->mlp % 64 || *pp3 % 64 || c->layers < 1 || c->layers > AVC_CLIP_MAX_LAYERS || c->out_dim < 1) return AVC_E_BADCFG;
   return 0;
 }
@@ -774,14 +836,14 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
   AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
 
   int64_t npx = (int64_t)B * 3 * IS * IS;
-  k_preprocess<<<(int)((npx + 255) / 256), 256, 0, st>>>(canvases, H, W, B, IS, cfg->patch, w.a0, input_mode);
-  k_cls_rows<<<(B * T * Wd + 255) / 256, 256, 0, st>>>(wt->cls, wt->pos, B, T, Wd, w.tok_pre);
+  AVC_CUDA_TRY(launch_pdl(k_preprocess, dim3((int)((npx + 255) / 256)), dim3(256), 0, st, canvases, H, W, B, IS, cfg->patch, w.a0, input_mode));
+  AVC_CUDA_TRY(launch_pdl(k_cls_rows, dim3((B * T * Wd + 255) / 256), dim3(256), 0, st, wt->cls, wt->pos, B, T, Wd, w.tok_pre));
   AVC_LAUNCH_TRY();
   {
     EpiPatch e{w.tok_pre, T, Wd, np};
     AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 4, e));
   }
-  k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr);
+  AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr));
   AVC_LAUNCH_TRY();
   for (int l = 0; l < cfg->layers; ++l) {
     const avc_clip_layer_weights& lw = wt->layer[l];
@@ -789,15 +851,15 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
     float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
     float* fcp = w.fc_pre + (size_t)l * M * cfg->mlp;
-    k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1);
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1));
     AVC_LAUNCH_TRY();
     { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e)); }
-    k_attention<<<B * cfg->heads, 512, attn_fwd_smem, st>>>(qkv, T, Wd, cfg->heads, w.o16);
+    AVC_CUDA_TRY(launch_pdl(k_attention, dim3(B * cfg->heads), dim3(512), attn_fwd_smem, st, qkv, T, Wd, cfg->heads, w.o16));
     AVC_LAUNCH_TRY();
     { EpiResidual e{w.x, Wd, lw.b_out};
       AVC_TRY(gemm16(st, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 2, e)); }
-    k_layernorm<<<ceil_div(M, 8), 256, 0, st>>>(w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2);
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2));
     AVC_LAUNCH_TRY();
     { EpiFc e{fcp, w.g16, cfg->mlp, lw.b_fc};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_fc, Wd, M, cfg->mlp, Wd, 1, e)); }
@@ -806,9 +868,9 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
   }
   AVC_CUDA_TRY(cudaMemcpyAsync(w.x_final, w.x, sizeof(float) * (size_t)M * Wd, cudaMemcpyDeviceToDevice, st));
   if (Wd % 4) return AVC_E_BADCFG;
-  k_head_proj<<<dim3(B, (cfg->out_dim + 63) / 64), 256, (Wd + 256) * sizeof(float), st>>>(
-      w.x_final, T, Wd, wt->ln_post_g, wt->ln_post_b, wt->proj, cfg->out_dim, w.emb, w.ynorm);
-  k_cosine<<<B, 256, 0, st>>>(w.emb, text_emb, cfg->out_dim, cos_out);
+  AVC_CUDA_TRY(launch_pdl(k_head_proj, dim3(dim3(B, (cfg->out_dim + 63) / 64)), dim3(256), (Wd + 256) * sizeof(float), st, 
+      w.x_final, T, Wd, wt->ln_post_g, wt->ln_post_b, wt->proj, cfg->out_dim, w.emb, w.ynorm));
+  AVC_CUDA_TRY(launch_pdl(k_cosine, dim3(B), dim3(256), 0, st, w.emb, text_emb, cfg->out_dim, cos_out));
   AVC_LAUNCH_TRY();
   AVC_CUDA_TRY(cudaMemcpyAsync(emb_out, w.emb, sizeof(float) * (size_t)B * cfg->out_dim, cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -834,9 +896,9 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
 
   {
     const int rows = 96;
-    k_head_bwd_dy<<<dim3(B, ceil_div(Wd, rows)), 256, cfg->out_dim * sizeof(float), st>>>(
-        Wd, wt->proj, cfg->out_dim, text_emb, w.emb, g_cos, g_emb, w.dO, rows);      // w.dO[0 .. B*Wd) as scratch
-    k_head_bwd_ln<<<B, 256, 0, st>>>(w.x_final, T, Wd, wt->ln_post_g, w.dO, w.dx);
+    AVC_CUDA_TRY(launch_pdl(k_head_bwd_dy, dim3(dim3(B, ceil_div(Wd, rows))), dim3(256), cfg->out_dim * sizeof(float), st, 
+        Wd, wt->proj, cfg->out_dim, text_emb, w.emb, g_cos, g_emb, w.dO, rows));      // w.dO[0 .. B*Wd) as scratch
+    AVC_CUDA_TRY(launch_pdl(k_head_bwd_ln, dim3(B), dim3(256), 0, st, w.x_final, T, Wd, wt->ln_post_g, w.dO, w.dx));
   }
   AVC_LAUNCH_TRY();
   for (int l = cfg->layers - 1; l >= 0; --l) {
@@ -847,7 +909,7 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     const float* fcp = w.fc_pre + (size_t)l * M * mlp;
     // ---- MLP branch: x_out = x_mid + c_proj(QuickGELU(c_fc(ln_2(x_mid))))
     if (l == cfg->layers - 1) {     // later layers get this conversion fused into the previous LayerNorm backward
-      k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr);
+      AVC_CUDA_TRY(launch_pdl(k_to_half_rowscaled, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.dx, M, Wd, Wd, w.d16a, w.scale, nullptr));
       AVC_LAUNCH_TRY();
     }
     { EpiDfc e{fcp, w.d16b, mlp};
@@ -855,32 +917,32 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16b, mlp, (const __half*)lw.w_fc_t, mlp, M, Wd, mlp, 4, e)); }
-    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale);
+    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale));
     AVC_LAUNCH_TRY();
     // ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
     { EpiStoreUnscale e{w.dO, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_out_t, Wd, M, Wd, Wd, 1, e)); }
-    k_attention_bwd<<<B * cfg->heads, 512, attn_bwd_smem, st>>>(qkv, w.dO, T, Wd, cfg->heads, w.dqkv);
+    AVC_CUDA_TRY(launch_pdl(k_attention_bwd, dim3(B * cfg->heads), dim3(512), attn_bwd_smem, st, qkv, w.dO, T, Wd, cfg->heads, w.dqkv));
     AVC_LAUNCH_TRY();
-    k_to_half_rowscaled<<<ceil_div(M, 8), 256, 0, st>>>(w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, nullptr);
+    AVC_CUDA_TRY(launch_pdl(k_to_half_rowscaled, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, nullptr));
     AVC_LAUNCH_TRY();
     AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, 3 * Wd, (const __half*)lw.w_qkv_t, 3 * Wd, M, Wd, 3 * Wd, 3, e)); }
-    k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale);
+    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale));
     AVC_LAUNCH_TRY();
   }
   // ln_pre, patch embedding, pre-processing
-  k_layernorm_bwd<<<ceil_div(M, 8), 256, 0, st>>>(w.tok_pre, w.dx, M, Wd, wt->ln_pre_g, w.dtmp, 0, Wd, Wd, Wd, nullptr,
-                                                  nullptr);
-  k_patch_row_map<<<ceil_div(B * np, 128), 128, 0, st>>>(B, T, w.rowmap);
-  k_to_half_rowscaled<<<ceil_div(B * np, 8), 256, 0, st>>>(w.dtmp, B * np, Wd, Wd, w.d16a, w.scale, w.rowmap);
+  AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, w.dx, M, Wd, wt->ln_pre_g, w.dtmp, 0, Wd, Wd, Wd, nullptr,
+                                                  nullptr));
+  AVC_CUDA_TRY(launch_pdl(k_patch_row_map, dim3(ceil_div(B * np, 128)), dim3(128), 0, st, B, T, w.rowmap));
+  AVC_CUDA_TRY(launch_pdl(k_to_half_rowscaled, dim3(ceil_div(B * np, 8)), dim3(256), 0, st, w.dtmp, B * np, Wd, Wd, w.d16a, w.scale, w.rowmap));
   AVC_LAUNCH_TRY();
   { EpiStoreUnscale e{w.dpatch, pp3, w.scale};
     AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)wt->w_patch_t, Wd, B * np, pp3, Wd, 1, e)); }
   AVC_CUDA_TRY(cudaMemsetAsync(d_canvases, 0, sizeof(float) * (size_t)B * H * W * 3, st));
   int64_t npx = (int64_t)B * 3 * IS * IS;
-  k_preprocess_bwd<<<(int)((npx + 255) / 256), 256, 0, st>>>(w.dpatch, H, W, B, IS, cfg->patch, d_canvases, input_mode);
+  AVC_CUDA_TRY(launch_pdl(k_preprocess_bwd, dim3((int)((npx + 255) / 256)), dim3(256), 0, st, w.dpatch, H, W, B, IS, cfg->patch, d_canvases, input_mode));
   AVC_LAUNCH_TRY();
   return 0;
 }
