@@ -1,0 +1,58 @@
+"""HOCON-subset reader: accessor API of pyhocon's ConfigTree as the reference uses it (main.py:39-127)."""
+import glob
+import os
+
+import pytest
+
+from avatarclip_b200 import conf
+
+SAMPLE = """
+general {
+    base_exp_dir = ./exp/smpl/demo     # trailing comment
+    recording = [
+        ./,
+        ./models
+    ]
+}
+train { learning_rate = 5e-4, end_iter = 100000, use_white_bkgd = False
+        warm_up_end = 500 }
+clip {
+    prompt = a 3D rendering of a {TOREPLACE} in unreal engine
+}
+model {
+    nerf {
+        D = 4,
+        skips=[4],
+        use_viewdirs=True
+    }
+    sdf_network { d_out = 257, skip_in = [4], scale = 1.0, weight_norm = True }
+}
+"""
+
+
+def test_sample():
+    c = conf.parse_string(SAMPLE)
+    assert c["general.base_exp_dir"] == "./exp/smpl/demo"
+    assert c["general.recording"] == ["./", "./models"]
+    assert c.get_float("train.learning_rate") == 5e-4 and c.get_int("train.end_iter") == 100000
+    assert c.get_bool("train.use_white_bkgd") is False
+    assert c.get_float("train.anneal_end", default=0.0) == 0.0
+    assert c.get_string("clip.prompt") == "a 3D rendering of a {TOREPLACE} in unreal engine"
+    assert dict(c["model.sdf_network"]) == {"d_out": 257, "skip_in": [4], "scale": 1.0, "weight_norm": True}
+    assert c["model.nerf.D"] == 4 and c["model.nerf"]["use_viewdirs"] is True
+    with pytest.raises(conf.ConfigMissingException):
+        c.get_float("train.clip_weight")
+    with pytest.raises(KeyError):        # the reference catches bare `except:` / KeyError (main.py:67-127)
+        c["dataset.template_obj"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_all_shipped_confs_parse():
+    files = glob.glob("/root/reference/AvatarGen/AppearanceGen/confs/**/*.conf", recursive=True)
+    assert len(files) == 180
+    for f in files:
+        c = conf.parse_file(f)
+        kw = dict(c["model.sdf_network"])
+        assert kw["d_out"] in (257, 129) and isinstance(kw["skip_in"], list)
+        assert {"n_samples", "n_importance", "n_outside", "up_sample_steps", "perturb"} <= set(c["model.neus_renderer"].keys())
+        assert c.get_float("train.learning_rate") > 0
