@@ -31,6 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 METRIC = "appearance-optim steps/sec (512 rays x 128 samples, CLIP loss)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
+# (r1_ncu_full_gemm_tc_*.txt); None where no capture of a full-size launch exists yet
+TRAFFIC_PER_LAUNCH = {"void avc::tc::gemm_tc_tn_kernel": 138.8e6, "void avc::tc::gemm_tc_nt_kernel": None}
 N_RAYS, CANVAS = 512, 224
 SDF_KW = dict(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
               geometric_init=True, weight_norm=True)
@@ -40,13 +43,18 @@ REN_KW = dict(n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4, per
 
 
 def algorithmic_flops_per_step():
-    """(6.875 F_sdf + 3 F_col) per fine sample point, F = 2*MAC; + CLIP fwd+dgrad for two images."""
+    """(6.875 F_sdf + 3 F_col) per fine sample point, F = 2*MAC; + CLIP fwd+dgrad for two images.
+    Returns (all MLP FLOP, the part executed by the NT tiles, the part executed by the TN (weight-gradient) tiles,
+    CLIP FLOP).  NT: value fwd 1 + gradient chain 1 + placement passes 0.875 + value dgrad 1 + second-order sweep 1
+    = 4.875 F_sdf, colour fwd + dgrad = 2 F_col.  TN: 2 F_sdf + 1 F_col."""
     mac_sdf = 39 * 256 + 6 * 256 * 256 + 256 * 217 + 256 * 257        # 9 linears of the 8x256 net
     mac_col = 262 * 256 + 3 * 256 * 256 + 2 * 3 * 256                 # 4x256 + two 3-wide heads
     pts = N_RAYS * (REN_KW["n_samples"] + REN_KW["n_importance"])
     mlp = (6.875 * 2 * mac_sdf + 3 * 2 * mac_col) * pts
+    nt = (4.875 * 2 * mac_sdf + 2 * 2 * mac_col) * pts
+    tn = (2.0 * 2 * mac_sdf + 1 * 2 * mac_col) * pts
     clip = 2 * 17.6e9
-    return mlp, clip
+    return mlp, nt, tn, clip
 
 
 def host_cores() -> int:
@@ -243,10 +251,22 @@ def run_native(args):
     ms_value, ms_e2e = t.tolist()
 
     if rank == 0:
-        mlp_flops, clip_flops = algorithmic_flops_per_step()
+        mlp_flops, nt_flops, tn_flops, clip_flops = algorithmic_flops_per_step()
         peak_tf, peak_hbm, peak_src = peaks()
-        achieved = mlp_flops / (ms_render * 1e-3) / 1e12
+        achieved_step = mlp_flops / (ms_render * 1e-3) / 1e12
         dom = max(table.items(), key=lambda kv: kv[1][1])[0] if table and "error" not in table else None
+        # dominant kernel: algorithmic FLOP its launches execute per step / the sum of their device durations in the
+        # profiled step (CUPTI kernel records taken live in this process, not under ncu)
+        kern_us = {k: v for k, v in table.items() if isinstance(v, list)}
+        dom_flops = {"void avc::tc::gemm_tc_nt_kernel": nt_flops, "void avc::tc::gemm_tc_tn_kernel": tn_flops,
+                     "void avc::gemm_nt_kernel": nt_flops, "avc::gemm_tn_kernel": tn_flops}.get(dom)
+        if dom_flops is not None and dom in kern_us and kern_us[dom][1] > 0:
+            n_launch, dom_us = kern_us[dom]
+            achieved = dom_flops / (dom_us * 1e-6) / 1e12
+            per_launch = {"launches_per_step": n_launch, "avg_launch_us": dom_us / n_launch,
+                          "algorithmic_gflop_per_launch": dom_flops / n_launch / 1e9}
+        else:
+            achieved, per_launch = achieved_step, None
         line = {
             "metric": METRIC, "value": world * K / (ms_value * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak",
@@ -261,11 +281,18 @@ def run_native(args):
             "gpu_launches": None if launches_per_step is None else launches_per_step * K,
             "gpu_launches_per_step": launches_per_step,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None,
-                         "scope": "algorithmic MLP FLOP/step (SURVEY 8d: 0.577 TFLOP) / CUDA-event time of "
-                                  "avc_neus_render_fwd + avc_neus_render_bwd; peak = " + peak_src,
-                         "dominant_kernel": dom, "ms_render_fwd_bwd": ms_render},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf,
+                         "traffic": TRAFFIC_PER_LAUNCH.get(dom),
+                         "per_launch": per_launch,
+                         "scope": "algorithmic FLOP executed by the dominant kernel's launches in one step (SURVEY 8d "
+                                  "split: NT tiles 4.875 F_sdf + 2 F_col per point, TN tiles 2 F_sdf + F_col) / sum of "
+                                  "their device durations (CUPTI, live); peak = " + peak_src + "; the kernel runs 3 "
+                                  "bf16 MMAs per product (two-term split), so its ceiling is peak/3",
+                         "step_level": {"achieved": achieved_step, "frac": achieved_step / peak_tf,
+                                        "ms_render_fwd_bwd": ms_render,
+                                        "note": "all MLP FLOP/step (0.577 T) / CUDA-event time of render fwd+bwd"},
+                         "kernel_time_us_per_step": {k: round(v[1], 1) for k, v in sorted(kern_us.items(), key=lambda kv: -kv[1][1])[:8]}},
             "last_loss": last,
             "phases_ms": {k: round(v, 4) for k, v in phases.items()},
         }
@@ -336,6 +363,7 @@ def cpu_baseline(sp, cp, clip_sd, text, view, sample_rays=128):
         z = on.hierarchical_z(lambda x: on.sdf_value(orc.sp, orc.sconf, x), orc.rconf, v.rays_o, v.rays_d,
                               v.near.reshape(-1, 1), v.far.reshape(-1, 1), v.jitter.reshape(-1, 1))
     t_place = time.perf_counter() - t0
+    timed_oracle_step(orc, v, N_RAYS)          # untimed warm-up (allocator, thread pool)
     tm = timed_oracle_step(orc, v, N_RAYS)
     # forward of render_core alone (with graph) ~ fwd_all - placement - clip/stage forward; measure clip fwd directly
     from oracle import clip_vit as cv
