@@ -187,9 +187,12 @@ def run_native(args):
     for i in range(Wm):
         tr.step(resident[i % n_views])
     barrier()
+    # one extra step on EVERY rank (it contains the all-reduce); only rank 0 records it with CUPTI
     launches_per_step, total_launches, table = (None, None, {})
     if rank == 0:
         launches_per_step, total_launches, table = count_my_launches(lambda: tr.step(resident[0]))
+    else:
+        tr.step(resident[0])
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
