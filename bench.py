@@ -164,6 +164,8 @@ def run_native(args):
     pg = None
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints "NCCL version ..." on STDOUT when NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
+        os.environ["NCCL_DEBUG"] = os.environ.get("AVC_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=device)
         pg = dist.group.WORLD
     from avatarclip_b200.trainer import AppearanceTrainer, DeviceView
