@@ -75,6 +75,8 @@ def lib():
                                       P(NeusCotangents), vp, vp, sz, i64, i32, vp]
     L.avc_neus_sdf_query.argtypes = [P(NeusCfg), vp, vp, i64, vp, vp, sz, vp]
     L.avc_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, vp]
+    L.avc_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]
+    L.avc_adam_step_dev.restype = C.c_int
     for name in ("avc_neus_param_count", "avc_neus_param_offset", "avc_neus_workspace_bytes",
                  "avc_neus_render_fwd", "avc_neus_render_bwd", "avc_neus_sdf_query", "avc_adam_step"):
         getattr(L, name).restype = C.c_int

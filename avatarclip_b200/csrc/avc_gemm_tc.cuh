@@ -13,6 +13,7 @@
 // warps 2-5 epilogue (TMEM lane quarter = warp_id % 4).  Tile 128 x BN, K step 64 (one 128-byte swizzle atom),
 // multi-stage shared-memory ring with full/empty mbarriers, accumulator hand-off through tcgen05.commit.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -21,7 +22,6 @@
 #include "avc_common.cuh"
 
 namespace avc {
-struct EpiPre;   // avc_neus_kernels.cuh
 namespace tc {
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -179,17 +179,17 @@ struct SplitPtr {            // two-term bf16 split of an fp32 matrix, both [row
 constexpr int kBM = 128, kBK = 64;
 constexpr int kTcThreads = 320;   // TN kernel: warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
 constexpr int kEpiWarps = 8;
-constexpr int kNtEpiWarps = 16;   // NT kernel: warps 2-17 (four per quarter): the epilogue is issue/latency bound
-constexpr int kNtThreads = 64 + 32 * kNtEpiWarps;
+// NT kernel: EW epilogue warps (EW/4 per TMEM lane quarter) and PFB registers per thread of prefetched epilogue
+// operands are template parameters; the launcher uses 16 warps / 32 registers (see launch_gemm_tc_nt).
 
-template <int BN, int NPROD>
+template <int BN, int NPROD, int EW = 8>
 struct TcCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;                    // one (hi or lo) A slab: 16 KB
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
   static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
-  static constexpr int EPI_BYTES = kNtEpiWarps * 32 * 16 * 4;       // per-warp 32x16 fp32 transpose buffers (XOR-swizzled)
+  static constexpr int EPI_BYTES = EW * 32 * 16 * 4;       // per-warp 32x16 fp32 transpose buffers (XOR-swizzled)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
@@ -216,15 +216,40 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Epilogue functor interface (see avc_neus_kernels.cuh): functors with a nested `Aux` type split into
+// prefetch(row, col) -> Aux and operator()(row, col, acc, aux); plain functors only have operator()(row, col, acc).
+struct NoAux {};
+template <typename E, typename = void>
+struct EpiTraits {
+  using Aux = NoAux;
+  static __device__ __forceinline__ Aux prefetch(const E&, int, int) { return {}; }
+  static __device__ __forceinline__ void apply(const E& e, int r, int c, float4 a, const Aux&) { e(r, c, a); }
+};
+template <typename E>
+struct EpiTraits<E, std::void_t<typename E::Aux>> {
+  using Aux = typename E::Aux;
+  static __device__ __forceinline__ Aux prefetch(const E& e, int r, int c) { return e.prefetch(r, c); }
+  static __device__ __forceinline__ void apply(const E& e, int r, int c, float4 a, const Aux& x) { e(r, c, a, x); }
+};
+
 // Persistent: gridDim.x CTAs (<= one per SM) walk the output tiles t = blockIdx.x, +gridDim.x, ...  The accumulator
 // is double buffered in TMEM (2 x BN columns) so the epilogue of tile i runs while the TMA/MMA warps already work
 // on tile i+1:  tfull[b] (MMA -> epilogue, tcgen05.commit)  /  tempty[b] (epilogue -> MMA, one arrive per warp).
-template <int BN, int NPROD, typename Epi>
-__global__ void __launch_bounds__(kNtThreads, 1)
+template <int BN, int NPROD, int EW, int PFB, typename Epi>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                   int M, int N, int K, Epi epi) {
-  using Cfg = TcCfg<BN, NPROD>;
+  using Cfg = TcCfg<BN, NPROD, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
   uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -243,7 +268,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
     if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, kNtEpiWarps); }
+    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, EW); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
@@ -307,8 +332,35 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     }
     __syncwarp();
   } else {
+    using Tr = EpiTraits<Epi>;
+    using Aux = typename Tr::Aux;
+    // Sub-blocks of 16 columns: the EW/4 warps of a TMEM lane quarter interleave them (NSUB per warp and tile).  The
+    // global loads of the epilogue that do not depend on the accumulator (stashed activations, biases: Epi::prefetch)
+    // are issued NPF sub-blocks ahead, across tile boundaries, so that they are in flight while the warp waits for
+    // the MMA and works through the previous sub-block.  Prefetch addresses are clamped into the matrix instead of
+    // predicated (no divergence, no zero-filling): a clamped value is never used.
+    constexpr int NSUB = BN / 16 / (EW / 4);
+    constexpr int NPF0 = PFB / (int)sizeof(Aux);       // PFB = registers per thread spent on operands in flight
+    constexpr int NPF = NPF0 < 1 ? 1 : (NPF0 >= NSUB ? NSUB : (NPF0 >= 2 && NSUB % 2 == 0 ? 2 : 1));
     const int q = warp & 3;               // TMEM lane quarter this warp may access
-    float* stage = epi_stage + (warp - 2) * 32 * 16;
+    const int cw = (warp - 2) >> 2;       // first sub-block of this warp
+    const int cg = (lane & 3) * 4, ri = lane >> 2;
+    // per-warp 32 x 16 fp32 transpose tile, 16-byte chunks XOR-swizzled with (row >> 1) & 3: the row-per-lane
+    // st.shared.v4 of the TMEM values and the 8-rows-x-4-chunks ld.shared.v4 of a pass are both conflict free
+    const uint32_t stage = smem_u32(epi_stage) + (uint32_t)(warp - 2) * 2048u;
+    const uint32_t st_row = stage + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
+    const uint32_t ld_addr = stage + (uint32_t)ri * 64u + (uint32_t)(((lane & 3) ^ ((ri >> 1) & 3)) * 16);
+    const int col_last = (N - 1) & ~3, row_last = M - 1, tile_last = ntiles - 1;
+    Aux aux[NPF][4];
+    auto issue = [&](Aux (&dst)[4], int tile, int sb) {
+      tile = min(tile, tile_last);
+      const int row = (tile / tiles_n) * kBM + q * 32 + ri;
+      const int col = min((tile % tiles_n) * BN + (cw + sb * (EW / 4)) * 16 + cg, col_last);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) dst[p] = Tr::prefetch(epi, min(row + 8 * p, row_last), col);
+    };
+#pragma unroll
+    for (int s = 0; s < NPF; ++s) issue(aux[s], blockIdx.x, s);
     int lt = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
@@ -317,30 +369,28 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
       tc_fence_after();
       const int row0 = m0 + q * 32;
       const int nrows = min(32, M - row0);
-      // the four warps of a TMEM lane quarter interleave 16-column sub-blocks; every sub-block is transposed through a
-      // swizzled shared-memory tile so that one warp pass covers 8 rows x 16 columns: the functor's float4 accesses
-      // are 64-byte row segments (whole sectors), 4 passes per sub-block
-#pragma unroll 1
-      for (int c = (warp - 2) >> 2; c < BN / 16; c += kNtEpiWarps / 4) {
-        const int col0 = n0 + c * 16;
-        if (col0 >= N) break;
-        uint32_t r[16];
-        tmem_ld16(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
-        if (nrows > 0) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) stage[lane * 16 + (j ^ ((lane >> 1) & 15))] = __uint_as_float(r[j]);   // conflict-free
+      for (int sb = 0; sb < NSUB; ++sb) {
+        const int c = cw + sb * (EW / 4);
+        const int col0 = n0 + c * 16;
+        if (col0 < N && nrows > 0) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), r);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            st_shared_v4(st_row + (((uint32_t)c4 ^ st_sw) << 4), r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
           __syncwarp();
-          const int cg = (lane & 3) * 4;
           if (col0 + cg < N) {
-#pragma unroll 2
-            for (int i = lane >> 2; i < nrows; i += 8) {
-              const float* sp = stage + i * 16;
-              const int sw = (i >> 1) & 15;
-              epi(row0 + i, col0 + cg, make_float4(sp[cg ^ sw], sp[(cg + 1) ^ sw], sp[(cg + 2) ^ sw], sp[(cg + 3) ^ sw]));
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const int i = ri + 8 * p;
+              if (i < nrows) Tr::apply(epi, row0 + i, col0 + cg, ld_shared_v4(ld_addr + (uint32_t)p * 512u), aux[sb % NPF][p]);
             }
           }
           __syncwarp();
         }
+        // refill the slot just consumed: NPF sub-blocks ahead in this warp's (tile, sub-block) sequence
+        issue(aux[sb % NPF], t + ((sb + NPF) / NSUB) * gridDim.x, (sb + NPF) % NSUB);
       }
       tc_fence_before();
       __syncwarp();
@@ -355,10 +405,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   }
 }
 
-template <int BN, int NPROD, typename Epi>
+template <int BN, int NPROD, int EW, int PFB, typename Epi>
 static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
                                        const Epi& epi) {
-  using Cfg = TcCfg<BN, NPROD>;
+  using Cfg = TcCfg<BN, NPROD, EW>;
   CUtensorMap mAh, mAl, mBh, mBl;
   AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
   AVC_TRY(make_map_bf16_cached(&mBh, B.hi, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
@@ -368,7 +418,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   } else {
     mAl = mAh; mBl = mBh;
   }
-  auto kern = gemm_tc_nt_kernel<BN, NPROD, Epi>;
+  auto kern = gemm_tc_nt_kernel<BN, NPROD, EW, PFB, Epi>;
   static bool attr_set = false;    // per template instantiation
   if (!attr_set) {
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -382,23 +432,21 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   }
   const int ntiles = ceil_div(M, kBM) * ceil_div(N, BN);
   dim3 grid(ntiles < num_sms ? ntiles : num_sms);      // persistent: at most one CTA per SM
-  kern<<<grid, kNtThreads, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
+  kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
   AVC_LAUNCH_TRY();
   return 0;
 }
 
-// N <= 64 -> BN 64, N <= 128 -> BN 128, else BN 256 (tiles in y)
+// N <= 64 -> one 64-wide tile, else 128-wide tiles: with one 256-wide tile per 128 rows a 65536-row GEMM would have
+// 512 tiles = 3.46 waves over 148 persistent CTAs (13 % tail); 1024 tiles = 6.9 waves (1.4 % tail).
 template <int NPROD, typename Epi>
 static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
                                     const Epi& epi) {
   if (M <= 0 || N <= 0) return 0;
-  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, Epi>(st, M, N, K, A, B, epi);
-  // N > 128 is covered by several 128-wide tiles: with one 256-wide tile per 128 rows a 65536-row GEMM has 512 tiles
-  // = 3.46 waves over 148 persistent CTAs (13 % tail); 1024 tiles = 6.9 waves (1.4 % tail), 3 pipeline stages fit
-  static int wide = -1;       // AVC_TC_BN=256 selects one 256-wide tile per 128 rows instead (tuning knob)
-  if (wide < 0) { const char* e = getenv("AVC_TC_BN"); wide = (e && atoi(e) == 256) ? 1 : 0; }
-  if (wide && N > 128) return launch_gemm_tc_nt_bn<256, NPROD, Epi>(st, M, N, K, A, B, epi);
-  return launch_gemm_tc_nt_bn<128, NPROD, Epi>(st, M, N, K, A, B, epi);
+  // 16 epilogue warps, one (32-byte operands) or two (16-byte operands) sub-blocks of prefetch.  Measured per step
+  // (73 launches, B200): 16 warps / 32 regs 3.01 ms, 16 / 16 3.02 ms, 8 warps / 64 regs 3.32 ms, 8 / 32 3.34 ms.
+  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, Epi>(st, M, N, K, A, B, epi);
+  return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, Epi>(st, M, N, K, A, B, epi);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel

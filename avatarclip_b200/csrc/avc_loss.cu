@@ -56,24 +56,36 @@ k_canvas_bg(avc_loss_inputs in, float* __restrict__ canvases, float* __restrict_
 }
 
 struct Shade {
-  float n[3], r, nh[3], lh[3], dot, diff, shade, shade2;
+  float n[3], r, nh[3], lh[3], dot, diff, shade, shade2, amb;
   bool low, nan_;
 };
 
+// per-view draws: device copy (graph replay) when given, else the host fields
+__device__ __forceinline__ void view_draws(const avc_loss_inputs& in, float ld[3], float* amb) {
+  if (in.view_scalars) {
+    ld[0] = in.view_scalars[0]; ld[1] = in.view_scalars[1]; ld[2] = in.view_scalars[2]; *amb = in.view_scalars[3];
+  } else {
+    ld[0] = in.light_dir[0]; ld[1] = in.light_dir[1]; ld[2] = in.light_dir[2]; *amb = in.ambience;
+  }
+}
+
 __device__ __forceinline__ Shade shade_terms(const avc_loss_inputs& in, const float n[3], float wsum) {
   Shade s;
+  float ldir[3], amb;
+  view_draws(in, ldir, &amb);
   s.n[0] = n[0]; s.n[1] = n[1]; s.n[2] = n[2];
   s.r = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-  float ln = sqrtf(in.light_dir[0] * in.light_dir[0] + in.light_dir[1] * in.light_dir[1] + in.light_dir[2] * in.light_dir[2]);
+  float ln = sqrtf(ldir[0] * ldir[0] + ldir[1] * ldir[1] + ldir[2] * ldir[2]);
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     s.nh[a] = n[a] / (s.r + 1e-7f);                                    // main.py:430
-    s.lh[a] = in.light_dir[a] / (ln + 1e-7f);                          // :436
+    s.lh[a] = ldir[a] / (ln + 1e-7f);                                  // :436
   }
   s.dot = s.nh[0] * s.lh[0] + s.nh[1] * s.lh[1] + s.nh[2] * s.lh[2];
   s.nan_ = isnan(s.dot);
   s.diff = s.nan_ ? 1.0f : fminf(fmaxf(s.dot, 0.f), 1.f);             // :438-439
-  s.shade = in.ambience + (1.f - in.ambience) * s.diff;               // :440-442
+  s.shade = amb + (1.f - amb) * s.diff;                               // :440-442
+  s.amb = amb;
   s.low = wsum < 0.5f;
   s.shade2 = s.low ? 1.0f : s.shade;                                  // :450-452 (l_ratio = 1)
   return s;
@@ -163,7 +175,7 @@ k_shade_bwd(avc_loss_inputs in, const float* __restrict__ d_canvases, const floa
     dcol[c] = sg * m / mask_sum;
   }
   // shade = amb + (1-amb) * clamp(dot, 0, 1) ; dot = nh . lh ; nh = n / (|n| + 1e-7)
-  float d_dot = (!s.nan_ && s.dot > 0.f && s.dot < 1.f) ? d_shade * (1.f - in.ambience) : 0.f;
+  float d_dot = (!s.nan_ && s.dot > 0.f && s.dot < 1.f) ? d_shade * (1.f - s.amb) : 0.f;
   float dnh[3] = {d_dot * s.lh[0], d_dot * s.lh[1], d_dot * s.lh[2]};
   float ndn = s.n[0] * dnh[0] + s.n[1] * dnh[1] + s.n[2] * dnh[2];
   float re = s.r + 1e-7f;

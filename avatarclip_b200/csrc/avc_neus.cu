@@ -158,16 +158,21 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
   const float* pack = w.pack;
   for (int l = 0; l < pl.L; ++l) {
     const LinDim& d = pl.sdf[l];
-    EpiValue e;
+    const bool fast = pl.cfg.engine == 1;
+    EpiValue<false> e;
     e.bias = pack + d.pk_b;
-    e.Z = stash ? w.z[l] : nullptr; e.ldz = d.Np;
+    e.D1 = stash ? w.z[l] : nullptr; e.ldz = d.Np;     // w.z[l] holds softplus'(z_l), see EpiValue
     // tcgen05 engine: the fp32 copy of a hidden activation is only read by the thin sdf head (layer L)
     e.OUT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.in[l + 1]; e.ldo = pl.sdf[l + 1].Kp;
     e.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
     e.N = d.N;
     e.o16 = w.in16[l + 1];
-    e.fast = pl.cfg.engine == 1;
-    AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, e));
+    if (fast) {
+      EpiValue<true> ef{e.bias, e.D1, e.ldz, e.OUT, e.ldo, e.oscale, e.N, e.o16};
+      AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, ef));
+    } else {
+      AVC_TRY(gemm_nt(pl, w, st, Pn, d.N, d.K, w.in[l], d.Kp, w.in16[l], d.pk_W, d.Kp, e));
+    }
   }
   const LinDim& dl = pl.sdf[pl.L];
   OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale, sdf_nz, sdf_pitch};
@@ -265,9 +270,8 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
       const LinDim& dq = pl.sdf[l - 1];
       EpiChain e;
       e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
-      e.Zprev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
+      e.D1prev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
       e.q16 = w.qt16[l - 1];
-      e.fast = pl.cfg.engine == 1;
       AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
     }
     const LinDim& d0 = pl.sdf[0];
@@ -398,7 +402,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.qt[l], d.Np, w.qt16[l], ub, d.Kp, ub16, wbar + d.off_v, d.K));
     const LinDim& dn = pl.sdf[l + 1];
     EpiChainBwd e;
-    e.N = d.N; e.Np = d.Np; e.Z = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
+    e.N = d.N; e.Np = d.Np; e.D1 = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
     // tcgen05 engine: the fp32 copy of ubar_{l+1} is only read by the column sum at the last linear
     e.UNEXT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.ubar[ucur ^ 1];
     e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
@@ -423,7 +427,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const LinDim& dp = pl.sdf[pl.L - 1];
     EpiDgrad e;
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = dL.skip ? kSqrtHalf : 1.f;
-    e.Zprev = w.z[pl.L - 1]; e.ZBARprev = w.zbar[pl.L - 1];
+    e.D1prev = w.z[pl.L - 1]; e.ZBARprev = w.zbar[pl.L - 1];
     e.sdfbar = w.sdfbar; e.wsdf = pack + pl.pk_wsdf; e.sdf_inv_scale = inv_scale;
     e.z16 = w.zbar16[pl.L - 1];
     AVC_TRY(gemm_nt(pl, w, st, P, dp.N, pl.F, w.featbar, pl.Fp, w.featbar16, dL.pk_WT, pl.Fp, e));
@@ -436,7 +440,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     const LinDim& dp = pl.sdf[l - 1];
     EpiDgrad e;
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = d.skip ? kSqrtHalf : 1.f;
-    e.Zprev = w.z[l - 1]; e.ZBARprev = w.zbar[l - 1];
+    e.D1prev = w.z[l - 1]; e.ZBARprev = w.zbar[l - 1];
     e.sdfbar = nullptr; e.wsdf = nullptr; e.sdf_inv_scale = 1.f;
     e.z16 = w.zbar16[l - 1];
     AVC_TRY(gemm_nt(pl, w, st, P, dp.N, d.N, w.zbar[l], d.Np, w.zbar16[l], d.pk_WT, d.Np, e));
@@ -666,6 +670,18 @@ int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
   double bc2 = 1.0 - pow((double)beta2, (double)step);
   k_adam<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+int avc_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float* state,
+                      float beta1, float beta2, float eps, float grad_scale, avc_stream_t stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return AVC_E_NULL;
+  if (n <= 0) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_adam_state<<<1, 32, 0, st>>>(state, beta1, beta2);
+  k_adam_dev<<<blocks_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps,
+                                                 grad_scale);
   AVC_LAUNCH_TRY();
   return 0;
 }

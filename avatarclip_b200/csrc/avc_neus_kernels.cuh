@@ -21,18 +21,18 @@ __device__ __forceinline__ void split16_put(const Split16& s, size_t row, int co
   s.hi[row * s.ld + col] = h;
   s.lo[row * s.ld + col] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);       // one F2FP.BF16.F32.PACK_AB
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int col, const float v[4]) {
   if (!s.hi) return;
-  __nv_bfloat16 h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { h[i] = __float2bfloat16_rn(v[i]); l[i] = __float2bfloat16_rn(v[i] - __bfloat162float(h[i])); }
-  *reinterpret_cast<uint2*>(s.hi + row * s.ld + col) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(s.lo + row * s.ld + col) = *reinterpret_cast<const uint2*>(l);
+  const uint32_t h01 = bf16x2_bits(v[0], v[1]), h23 = bf16x2_bits(v[2], v[3]);
+  const float r0 = v[0] - __uint_as_float(h01 << 16), r1 = v[1] - __uint_as_float(h01 & 0xffff0000u);
+  const float r2 = v[2] - __uint_as_float(h23 << 16), r3 = v[3] - __uint_as_float(h23 & 0xffff0000u);
+  *reinterpret_cast<uint2*>(s.hi + row * s.ld + col) = make_uint2(h01, h23);
+  *reinterpret_cast<uint2*>(s.lo + row * s.ld + col) = make_uint2(bf16x2_bits(r0, r1), bf16x2_bits(r2, r3));
 }
-
-// Values an epilogue functor needs from global memory for one output element.  The tcgen05 epilogue issues the
-// `load`s of several rows back to back before finishing any of them (memory-level parallelism).
-struct EpiPre { float a, b, c; };
 
 // SFU (ex2/lg2.approx based) softplus for the tcgen05 engine's epilogues, which are instruction-issue bound:
 // |error| <~ 1e-8 absolute on softplus (value / 100), ~2 ulp on softplus'.  The fp32 engine keeps libm accuracy.
@@ -43,9 +43,24 @@ __device__ __forceinline__ float softplus100_fast(float z) {
 // softplus' with SFU exp/div
 __device__ __forceinline__ float softplus100_d1_fast(float z) {
   float bz = z * kBeta;
-  if (bz > kThresh) return 1.0f;
   float e = __expf(bz);
-  return __fdividef(e, e + 1.0f);
+  return bz > kThresh ? 1.0f : __fdividef(e, e + 1.0f);
+}
+// softplus and softplus' of the same argument, sharing the exponential; branch free (the selects discard the inf / NaN
+// the discarded arm produces for large arguments).  FAST: SFU ex2 / lg2 / rcp;  else libm accuracy.
+template <bool FAST>
+__device__ __forceinline__ void softplus100_both(float z, float* h, float* d1) {
+  if (FAST) {
+    const float bz = z * kBeta;
+    const float e = __expf(bz);
+    const float t = 1.0f + e;
+    const bool big = bz > kThresh;
+    *h = big ? z : __logf(t) * (1.0f / kBeta);
+    *d1 = big ? 1.0f : __fdividef(e, t);
+  } else {
+    *h = softplus100(z);
+    *d1 = softplus100_d1(z);
+  }
 }
 
 // =============================================================================================
@@ -493,7 +508,8 @@ k_colsum(const float* __restrict__ X, int ld, int NC, int64_t P, int rows_per_bl
 // =============================================================================================
 // Gradient chain helpers (SDFNetwork.gradient, models/fields.py:96-107, as a reverse sweep).
 // =============================================================================================
-// u_L = row 0 of W_L (constant):  qt[L-1] = softplus'(z[L-1]) * ua_L ; ge initialised.
+// u_L = row 0 of W_L (constant):  qt[L-1] = softplus'(z[L-1]) * ua_L ; ge initialised.  `zprev` is the stash of
+// softplus'(z[L-1]) the value pass left (EpiValue::D1).
 __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL, int E, int EP,
                               const float* __restrict__ zprev, int Nprev, int Npp, int64_t P,
                               float* __restrict__ qt, float* __restrict__ ge, Split16 qt16) {
@@ -508,7 +524,7 @@ __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL,
     float v[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      v[i] = (c + i < Nprev) ? softplus100_d1(zz[i]) * wsdf[c + i] * (skipL ? kSqrtHalf : 1.f) : 0.f;
+      v[i] = (c + i < Nprev) ? zz[i] * wsdf[c + i] * (skipL ? kSqrtHalf : 1.f) : 0.f;
     *reinterpret_cast<float4*>(qt + i4) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(qt16, (size_t)p, c, v);
   }
@@ -611,31 +627,46 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
 
 // =============================================================================================
 // GEMM epilogue functors.  (row, col..col+3, acc) with col % 4 == 0; N = valid output width.
+//
+// Every functor splits its work in two so that the tcgen05 epilogue can issue the global loads that do NOT depend
+// on the accumulator a whole tile ahead (the epilogue is bound by bytes in flight, not by issue slots):
+//     Aux  prefetch(row, col)                      the stashed activations / biases this output group needs
+//     void operator()(row, col, acc, aux)          the arithmetic and the stores
+// operator()(row, col, acc) is the two back to back (what the fp32 FFMA engine calls).
 // =============================================================================================
 #define AVC_EPI_UNPACK float v[4] = {a.x, a.y, a.z, a.w}
+#define AVC_EPI_DIRECT \
+  __device__ __forceinline__ void operator()(int row, int col, float4 a) const { (*this)(row, col, a, prefetch(row, col)); }
 
-// value chain: z = acc + b ; Z[row] = z (padding zero) ; OUT[row][col] = softplus(z) * oscale (col < N)
+// start of the last whole 4-column group below n, or `col` when that is smaller: an always-valid prefetch address
+__device__ __forceinline__ int clamp_group(int col, int n) { return max(0, min(col, (n - 4) & ~3)); }
+
+__device__ __forceinline__ float4 load4_guarded(const float* p, int col, int N) {
+  float4 r;
+  r.x = col < N ? p[col] : 0.f; r.y = col + 1 < N ? p[col + 1] : 0.f;
+  r.z = col + 2 < N ? p[col + 2] : 0.f; r.w = col + 3 < N ? p[col + 3] : 0.f;
+  return r;
+}
+
+// value chain: z = acc + b ; OUT[row][col] = softplus(z) * oscale (col < N) ; D1[row][col] = softplus'(z) (padding
+// zero): the stash every later pass needs -- the gradient chain, the second-order sweep and the value backward only
+// ever use softplus' (softplus'' = beta * sp' * (1 - sp')), so the pre-activation itself is not kept.
+template <bool FAST>
 struct EpiValue {
-  const float* bias; float* Z; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16; int fast;
-  // scalar form used by the tcgen05 epilogue (lane <-> column: coalesced rows)
-  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    float z = a + p.a;
-    if (Z) Z[(size_t)row * ldz + col] = z;
-    float h = softplus100(z) * oscale;
-    if (OUT) OUT[(size_t)row * ldo + col] = h;
-    split16_put(o16, (size_t)row, col, h);
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  const float* bias; float* D1; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
+  struct Aux { float4 b; };
+  __device__ __forceinline__ Aux prefetch(int, int col) const { return {load4_guarded(bias, col, N)}; }
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    float zz[4], hh[4];
+    const float bb[4] = {x.b.x, x.b.y, x.b.z, x.b.w};
+    float dd[4], hh[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      bool ok = col + i < N;
-      zz[i] = ok ? v[i] + bias[col + i] : 0.f;
-      hh[i] = (fast ? softplus100_fast(zz[i]) : softplus100(zz[i])) * oscale;
+      softplus100_both<FAST>(v[i] + bb[i], &hh[i], &dd[i]);
+      hh[i] *= oscale;
+      if (col + i >= N) { hh[i] = 0.f; dd[i] = 0.f; }
     }
-    if (Z) *reinterpret_cast<float4*>(Z + (size_t)row * ldz + col) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+    if (D1) *reinterpret_cast<float4*>(D1 + (size_t)row * ldz + col) = make_float4(dd[0], dd[1], dd[2], dd[3]);
     if (col + 3 < N) {
       if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(hh[0], hh[1], hh[2], hh[3]);
       split16_put4(o16, (size_t)row, col, hh);
@@ -646,60 +677,40 @@ struct EpiValue {
       }
     }
   }
+  AVC_EPI_DIRECT
 };
 
 // out = acc + b (feature rows of the last SDF linear)
 struct EpiBias {
   const float* bias; float* OUT; int ldo; int N; Split16 o16;
-  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    float v = a + p.a;
-    OUT[(size_t)row * ldo + col] = v;
-    split16_put(o16, (size_t)row, col, v);
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  struct Aux { float4 b; };
+  __device__ __forceinline__ Aux prefetch(int, int col) const { return {load4_guarded(bias, col, N)}; }
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
+    const float bb[4] = {x.b.x, x.b.y, x.b.z, x.b.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] + bias[col + i] : 0.f;
+    for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] + bb[i] : 0.f;
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
+  AVC_EPI_DIRECT
 };
 
 // gradient chain, layer l >= 1: u = acc (width K_l).  Columns < Nprev: ua = u * s, qt_prev = sp'(z_prev) * ua;
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
+// D1prev = the softplus' stash of layer l-1.
 struct EpiChain {
-  int Nprev, Npp; float s; const float* Zprev; float* QTprev; float* GE; int EP; int E; Split16 q16; int fast;
-  __device__ __forceinline__ EpiPre load(int row, int c) const {
-    EpiPre p = {0.f, 0.f, 0.f};
-    if (c < Nprev) p.a = Zprev[(size_t)row * Npp + c];
-    else if (c - Nprev < E) p.b = GE[(size_t)row * EP + (c - Nprev)];
-    return p;
+  int Nprev, Npp; float s; const float* D1prev; float* QTprev; float* GE; int EP; int E; Split16 q16;
+  struct Aux { float4 d; };
+  __device__ __forceinline__ Aux prefetch(int row, int col) const {
+    const int c = clamp_group(col, Nprev);    // always a valid address; the value is only used when col + 3 < Nprev
+    return {*reinterpret_cast<const float4*>(D1prev + (size_t)row * Npp + c)};
   }
-  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
-    if (c < Nprev) {
-      float qv = softplus100_d1(p.a) * a * s;
-      QTprev[(size_t)row * Npp + c] = qv;
-      split16_put(q16, (size_t)row, c, qv);
-    } else {
-      if (c < Npp) { QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
-      int e = c - Nprev;
-      if (e < E) GE[(size_t)row * EP + e] = p.b + a * kSqrtHalf;
-    }
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
     if (col + 3 < Nprev) {        // fast path: whole group inside the hidden part
       const size_t o = (size_t)row * Npp + col;
-      const float4 z = *reinterpret_cast<const float4*>(Zprev + o);
-      float q[4];
-      if (fast) {
-        q[0] = softplus100_d1_fast(z.x) * v[0] * s; q[1] = softplus100_d1_fast(z.y) * v[1] * s;
-        q[2] = softplus100_d1_fast(z.z) * v[2] * s; q[3] = softplus100_d1_fast(z.w) * v[3] * s;
-      } else {
-        q[0] = softplus100_d1(z.x) * v[0] * s; q[1] = softplus100_d1(z.y) * v[1] * s;
-        q[2] = softplus100_d1(z.z) * v[2] * s; q[3] = softplus100_d1(z.w) * v[3] * s;
-      }
+      float q[4] = {x.d.x * v[0] * s, x.d.y * v[1] * s, x.d.z * v[2] * s, x.d.w * v[3] * s};
       *reinterpret_cast<float4*>(QTprev + o) = make_float4(q[0], q[1], q[2], q[3]);
       split16_put4(q16, (size_t)row, col, q);
       return;
@@ -708,7 +719,7 @@ struct EpiChain {
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
       if (c < Nprev) {
-        float qv = softplus100_d1(Zprev[(size_t)row * Npp + c]) * v[i] * s;
+        float qv = D1prev[(size_t)row * Npp + c] * v[i] * s;
         QTprev[(size_t)row * Npp + c] = qv;
         split16_put(q16, (size_t)row, c, qv);
       } else {
@@ -718,45 +729,36 @@ struct EpiChain {
       }
     }
   }
+  AVC_EPI_DIRECT
 };
 
 // gradient chain, layer 0: ge += acc  (width E)
 struct EpiGe {
   float* GE; int EP; int E;
-  __device__ __forceinline__ EpiPre load(int row, int col) const {
-    return {col < E ? GE[(size_t)row * EP + col] : 0.f, 0.f, 0.f};
+  struct Aux { float4 g; };
+  __device__ __forceinline__ Aux prefetch(int row, int col) const {     // EP % 4 == 0: the padding is addressable
+    return {*reinterpret_cast<const float4*>(GE + (size_t)row * EP + clamp_group(col, EP))};
   }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    if (col < E) GE[(size_t)row * EP + col] = p.a + a;
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
+    const float gg[4] = {x.g.x, x.g.y, x.g.z, x.g.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-      if (col + i < E) GE[(size_t)row * EP + col + i] += v[i];
+      if (col + i < E) GE[(size_t)row * EP + col + i] = gg[i] + v[i];
   }
+  AVC_EPI_DIRECT
 };
 
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
 struct EpiColor0 {
   const float* bias; const float* cin; const float* Wx; float* OUT; int ldo; Split16 o16;
-  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
-    const float4 c1 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4);
-    const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8);
-    const float4 w1 = *reinterpret_cast<const float4*>(Wx + (size_t)col * 8 + 4);
-    float z = a + p.a;
-    z = fmaf(c0.x, w0.x, z); z = fmaf(c0.y, w0.y, z); z = fmaf(c0.z, w0.z, z);
-    z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
-    z = fmaxf(z, 0.f);
-    OUT[(size_t)row * ldo + col] = z;
-    split16_put(o16, (size_t)row, col, z);
+  struct Aux { float4 c0, c1; };
+  __device__ __forceinline__ Aux prefetch(int row, int) const {
+    return {*reinterpret_cast<const float4*>(cin + (size_t)row * 8), *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4)};
   }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    const float4 c0 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8);
-    const float4 c1 = *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4);
+    const float4 c0 = x.c0, c1 = x.c1;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)(col + i) * 8);
@@ -769,51 +771,45 @@ struct EpiColor0 {
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
+  AVC_EPI_DIRECT
 };
 
 struct EpiRelu {
   const float* bias; float* OUT; int ldo; Split16 o16;
-  __device__ __forceinline__ EpiPre load(int, int col) const { return {bias[col], 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    float v = fmaxf(a + p.a, 0.f);
-    OUT[(size_t)row * ldo + col] = v;
-    split16_put(o16, (size_t)row, col, v);
+  struct Aux { float4 b; };
+  __device__ __forceinline__ Aux prefetch(int, int col) const {
+    return {make_float4(bias[col], bias[col + 1], bias[col + 2], bias[col + 3])};
   }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i] + bias[col + i], 0.f);
+    v[0] = fmaxf(v[0] + x.b.x, 0.f); v[1] = fmaxf(v[1] + x.b.y, 0.f);
+    v[2] = fmaxf(v[2] + x.b.z, 0.f); v[3] = fmaxf(v[3] + x.b.w, 0.f);
     *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
+  AVC_EPI_DIRECT
 };
 
 // colour dgrad: out = acc * [h > 0]
 struct EpiDgradRelu {
   const float* Hm; float* OUT; int ld; Split16 o16;
-  __device__ __forceinline__ EpiPre load(int row, int col) const { return {Hm[(size_t)row * ld + col], 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre& p) const {
-    float v = p.a > 0.f ? a : 0.f;
-    OUT[(size_t)row * ld + col] = v;
-    split16_put(o16, (size_t)row, col, v);
+  struct Aux { float4 h; };
+  __device__ __forceinline__ Aux prefetch(int row, int col) const {
+    return {*reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col)};
   }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    const float4 h = *reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col);
+    const float4 h = x.h;
     v[0] = h.x > 0.f ? v[0] : 0.f; v[1] = h.y > 0.f ? v[1] : 0.f; v[2] = h.z > 0.f ? v[2] : 0.f; v[3] = h.w > 0.f ? v[3] : 0.f;
     *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
+  AVC_EPI_DIRECT
 };
 
 struct EpiStore {
   float* OUT; int ldo; int N; Split16 o16;
-  __device__ __forceinline__ EpiPre load(int, int) const { return {0.f, 0.f, 0.f}; }
-  __device__ __forceinline__ void one(int row, int col, float a, const EpiPre&) const {
-    OUT[(size_t)row * ldo + col] = a;
-    split16_put(o16, (size_t)row, col, a);
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] : 0.f;
@@ -822,34 +818,26 @@ struct EpiStore {
   }
 };
 
-// second-order sweep, layer l < L: qbar = acc (width N_l).
+// second-order sweep, layer l < L: qbar = acc (width N_l).  D1 = softplus'(z_l) stash.
 //   ubar_next[row][col] = sp'(z_l) * qbar * s_next            (col < N_l)
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
-  int N, Np; const float* Z; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
-  __device__ __forceinline__ EpiPre load(int row, int c) const {
-    return {Z[(size_t)row * Np + c], QT[(size_t)row * Np + c], 0.f};
+  int N, Np; const float* D1; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
+  struct Aux { float4 d, qt; };
+  __device__ __forceinline__ Aux prefetch(int row, int col) const {
+    const size_t o = (size_t)row * Np + clamp_group(col, N);
+    return {*reinterpret_cast<const float4*>(D1 + o), *reinterpret_cast<const float4*>(QT + o)};
   }
-  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
-    float s1 = softplus100_d1(p.a);
-    float uv = s1 * a * s_next;
-    if (UNEXT) UNEXT[(size_t)row * ldu + c] = uv;
-    split16_put(u16, (size_t)row, c, uv);
-    ZBAR[(size_t)row * Np + c] = kBeta * (1.f - s1) * p.b * a;
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
     if (col + 3 < N) {
       const size_t o = (size_t)row * Np + col;
-      const float4 z = *reinterpret_cast<const float4*>(Z + o);
-      const float4 qt = *reinterpret_cast<const float4*>(QT + o);
-      const float zz[4] = {z.x, z.y, z.z, z.w}, qq[4] = {qt.x, qt.y, qt.z, qt.w};
+      const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w}, qq[4] = {x.qt.x, x.qt.y, x.qt.z, x.qt.w};
       float u[4], zb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float s1 = softplus100_d1_fast(zz[i]);
-        u[i] = s1 * v[i] * s_next;
-        zb[i] = kBeta * (1.f - s1) * qq[i] * v[i];
+        u[i] = dd[i] * v[i] * s_next;
+        zb[i] = kBeta * (1.f - dd[i]) * qq[i] * v[i];
       }
       if (UNEXT) *reinterpret_cast<float4*>(UNEXT + (size_t)row * ldu + col) = make_float4(u[0], u[1], u[2], u[3]);
       split16_put4(u16, (size_t)row, col, u);
@@ -861,7 +849,7 @@ struct EpiChainBwd {
     for (int i = 0; i < 4; ++i) {
       int c = col + i;
       if (c < N) {
-        float s1 = softplus100_d1_fast(Z[(size_t)row * Np + c]);
+        float s1 = D1[(size_t)row * Np + c];
         float uv = s1 * v[i] * s_next;
         if (UNEXT) UNEXT[(size_t)row * ldu + c] = uv;
         split16_put(u16, (size_t)row, c, uv);
@@ -872,43 +860,31 @@ struct EpiChainBwd {
     }
     *reinterpret_cast<float4*>(ZBAR + (size_t)row * Np + col) = make_float4(zb[0], zb[1], zb[2], zb[3]);
   }
+  AVC_EPI_DIRECT
 };
 
 // value backward dgrad into layer l-1: abar = (acc [+ sdfbar[row] * wsdf[col]]) * s ;
-//   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev)
+//   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev);  D1prev = softplus'(z_prev) stash
 struct EpiDgrad {
-  int Nprev, Npp; float s; const float* Zprev; float* ZBARprev; const float* sdfbar; const float* wsdf;
+  int Nprev, Npp; float s; const float* D1prev; float* ZBARprev; const float* sdfbar; const float* wsdf;
   float sdf_inv_scale; Split16 z16;
-  __device__ __forceinline__ EpiPre load(int row, int c) const {
-    EpiPre p = {0.f, 0.f, 0.f};
-    if (c < Nprev) {
-      size_t o = (size_t)row * Npp + c;
-      p.a = Zprev[o]; p.b = ZBARprev[o];
-      if (sdfbar) p.c = sdfbar[row] * sdf_inv_scale * wsdf[c];
-    }
-    return p;
+  struct Aux { float4 d, zb; };
+  __device__ __forceinline__ Aux prefetch(int row, int col) const {
+    const size_t o = (size_t)row * Npp + clamp_group(col, Nprev);
+    return {*reinterpret_cast<const float4*>(D1prev + o), *reinterpret_cast<const float4*>(ZBARprev + o)};
   }
-  __device__ __forceinline__ void one(int row, int c, float a, const EpiPre& p) const {
-    if (c >= Nprev) return;
-    size_t o = (size_t)row * Npp + c;
-    float zv = fmaf(softplus100_d1(p.a), (a + p.c) * s, p.b);
-    ZBARprev[o] = zv;
-    split16_put(z16, (size_t)row, c, zv);
-  }
-  __device__ void operator()(int row, int col, float4 a) const {
+  __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
     float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;
     if (col + 3 < Nprev) {
       const size_t o = (size_t)row * Npp + col;
-      const float4 z = *reinterpret_cast<const float4*>(Zprev + o);
-      const float4 zb = *reinterpret_cast<const float4*>(ZBARprev + o);
-      const float zz[4] = {z.x, z.y, z.z, z.w}, zo[4] = {zb.x, zb.y, zb.z, zb.w};
+      const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w}, zo[4] = {x.zb.x, x.zb.y, x.zb.z, x.zb.w};
       float r[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float ab = v[i];
         if (sdfbar) ab = fmaf(sb, wsdf[col + i], ab);
-        r[i] = fmaf(softplus100_d1_fast(zz[i]), ab * s, zo[i]);
+        r[i] = fmaf(dd[i], ab * s, zo[i]);
       }
       *reinterpret_cast<float4*>(ZBARprev + o) = make_float4(r[0], r[1], r[2], r[3]);
       split16_put4(z16, (size_t)row, col, r);
@@ -921,12 +897,13 @@ struct EpiDgrad {
         float ab = v[i];
         if (sdfbar) ab = fmaf(sb, wsdf[c], ab);
         size_t o = (size_t)row * Npp + c;
-        float zv = fmaf(softplus100_d1_fast(Zprev[o]), ab * s, ZBARprev[o]);
+        float zv = fmaf(D1prev[o], ab * s, ZBARprev[o]);
         ZBARprev[o] = zv;
         split16_put(z16, (size_t)row, c, zv);
       }
     }
   }
+  AVC_EPI_DIRECT
 };
 
 // =============================================================================================
@@ -1243,6 +1220,29 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
                        float bc2_sqrt, float gscale) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  float gi = g[i] * gscale;
+  float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
+  float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
+  float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// Device-state variant for CUDA-graph replay: state[0] = steps so far, state[1] = lr, state[2] = 1 - b1^t, state[3] =
+// sqrt(1 - b2^t).
+__global__ void k_adam_state(float* __restrict__ state, float b1, float b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float t = state[0] + 1.0f;
+    state[0] = t;
+    state[2] = 1.0f - powf(b1, t);
+    state[3] = sqrtf(1.0f - powf(b2, t));
+  }
+}
+__global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1, float b2,
+                           float eps, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr = state[1], bc1 = state[2], bc2_sqrt = state[3];
   float gi = g[i] * gscale;
   float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
   float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;

@@ -22,7 +22,7 @@ class LossInputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("color_fine", "extra_color_fine", "gradients", "weights", "weight_sum",
                                           "gradient_error", "pix", "in_mask", "true_rgb", "mask", "background")] + \
                [("bg_choice", C.c_int32), ("light_dir", C.c_float * 3), ("ambience", C.c_float),
-                ("igr_weight", C.c_float), ("mask_weight", C.c_float), ("clip_weight", C.c_float),
+                ("view_scalars", C.c_void_p), ("igr_weight", C.c_float), ("mask_weight", C.c_float), ("clip_weight", C.c_float),
                 ("R", C.c_int32), ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
 
 
@@ -41,7 +41,7 @@ class StepInputs:
     """Per-step, non-differentiable inputs of the stage (all CUDA tensors)."""
 
     def __init__(self, pix, in_mask, true_rgb, mask, H, W, light_dir, ambience, bg_choice=3, background=None,
-                 igr_weight=0.1, mask_weight=0.5, clip_weight=1.0):
+                 igr_weight=0.1, mask_weight=0.5, clip_weight=1.0, view_scalars=None):
         self.pix = pix.to(torch.int32).contiguous()
         self.in_mask = in_mask.to(torch.uint8).contiguous().reshape(-1)
         self.true_rgb = true_rgb.float().contiguous().reshape(-1, 3)
@@ -51,6 +51,9 @@ class StepInputs:
         self.light_dir = [float(v) for v in light_dir]
         self.ambience = float(ambience)
         self.bg_choice = int(bg_choice)
+        # optional DEVICE [4] copy of (light_dir, ambience): read by the kernels instead of the host values, so a
+        # captured CUDA graph of the step can be replayed on a new view
+        self.view_scalars = view_scalars
         self.igr_weight, self.mask_weight, self.clip_weight = float(igr_weight), float(mask_weight), float(clip_weight)
 
 
@@ -65,6 +68,7 @@ def make_inputs(render_out: Dict[str, torch.Tensor], si: StepInputs) -> LossInpu
     li.bg_choice = si.bg_choice
     li.light_dir = (C.c_float * 3)(*si.light_dir)
     li.ambience, li.igr_weight, li.mask_weight, li.clip_weight = si.ambience, si.igr_weight, si.mask_weight, si.clip_weight
+    li.view_scalars = None if si.view_scalars is None else si.view_scalars.data_ptr()
     li.R, li.S, li.H, li.W = R, S, si.H, si.W
     return li
 

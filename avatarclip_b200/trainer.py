@@ -18,30 +18,37 @@ import torch
 
 from . import _lib, dist as avc_dist, losses
 from .renderer import NeuSRenderer, render_backward_raw, render_forward_raw
-from .workload import HostView
+from .workload import VIEW_FIELDS, HostView
 
 
 class DeviceView:
-    """Device-resident copy of a HostView; ``upload`` refreshes it from (pinned) host memory."""
+    """Device-resident copy of a HostView.  All tensors are views of ONE device buffer with the HostView.pack()
+    layout, so ``upload`` is a single (async, when the host side is pinned) H2D copy and the addresses never change
+    -- which is what lets a captured CUDA graph of the step be replayed on every new view."""
 
     def __init__(self, hv: HostView, device):
         self.device = torch.device(device)
         self.H, self.W = hv.H, hv.W
-        mk = lambda t: None if t is None else torch.empty(t.shape, dtype=t.dtype, device=self.device)
-        self.rays_o, self.rays_d = mk(hv.rays_o), mk(hv.rays_d)
-        self.near, self.far, self.jitter = mk(hv.near), mk(hv.far), mk(hv.jitter)
-        self.pix, self.in_mask = mk(hv.pix), mk(hv.in_mask)
-        self.true_rgb, self.mask = mk(hv.true_rgb), mk(hv.mask)
-        self.ray_background, self.canvas_background = mk(hv.ray_background), mk(hv.canvas_background)
+        hv.pack()
+        self._layout, total = hv.layout()
+        self.flat = torch.empty(total, dtype=torch.uint8, device=self.device)
+        for name in VIEW_FIELDS:
+            setattr(self, name, None)
+        for name, off, shape, dtype, nb in self._layout:
+            setattr(self, name, self.flat[off:off + nb].view(dtype).reshape(shape))
         self.upload(hv)
 
     def upload(self, hv: HostView):
-        for name in ("rays_o", "rays_d", "near", "far", "jitter", "pix", "in_mask", "true_rgb", "mask",
-                     "ray_background", "canvas_background"):
-            src, dst = getattr(hv, name), getattr(self, name)
-            if src is not None:
-                dst.copy_(src, non_blocking=True)
+        hv.pack()
+        if hv.flat.numel() != self.flat.numel() or hv.layout()[0] != self._layout:
+            raise ValueError("DeviceView.upload: the view's tensor shapes differ from the ones this buffer was built for")
+        self.flat.copy_(hv.flat, non_blocking=True)
         self.bg_choice, self.light_dir, self.ambience = hv.bg_choice, hv.light_dir, hv.ambience
+
+    def copy_from(self, other: "DeviceView"):
+        """Device-to-device refresh (one copy) from another resident view of the same layout."""
+        self.flat.copy_(other.flat, non_blocking=True)
+        self.bg_choice, self.light_dir, self.ambience = other.bg_choice, other.light_dir, other.ambience
 
 
 class AppearanceTrainer:
@@ -71,6 +78,13 @@ class AppearanceTrainer:
         self.scalars = None
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.phase_events = None      # set to [] to record a CUDA event after every phase of the next step
+        # CUDA-graph mode (capture() / replay()): Adam's step counter and lr live on the device
+        self._graph = None
+        self._graph_key = None
+        self._graph_loss = None
+        self._adam_state = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._lr_on_device = None
+        self._dev_step = -1
 
     # ------------------------------------------------------------------------------------------
     def forward_backward(self, dv: DeviceView, cos_anneal: float = 1.0) -> torch.Tensor:
@@ -93,7 +107,8 @@ class AppearanceTrainer:
         self._out = out
         mark("render_fwd")
         si = losses.StepInputs(dv.pix, dv.in_mask, dv.true_rgb, dv.mask, dv.H, dv.W, dv.light_dir, dv.ambience,
-                               dv.bg_choice, dv.canvas_background, self.igr_weight, self.mask_weight, self.clip_weight)
+                               dv.bg_choice, dv.canvas_background, self.igr_weight, self.mask_weight, self.clip_weight,
+                               view_scalars=dv.scalars)
         canv, scal = losses.stage_forward(out, si)
         self.scalars = scal
         mark("loss_stage_fwd")
@@ -138,3 +153,62 @@ class AppearanceTrainer:
         self.forward_backward(dv, cos_anneal)
         self.optimizer_step(lr)
         return self.loss_value()
+
+    # ------------------------------------------------------------------------------------------
+    # CUDA-graph mode: the ~370 launches of a step are captured once on a *static* DeviceView and replayed; the
+    # caller refreshes that view in place (upload / copy_from) between replays.  Single GPU: the whole step including
+    # Adam is in the graph.  View-sharded multi-GPU: the graph ends at the flat gradient, the all-reduce and Adam
+    # are launched after it (NCCL stays outside the capture).
+    def _graph_body(self, dv: DeviceView, cos_anneal: float, with_adam: bool):
+        self.forward_backward(dv, cos_anneal)
+        if with_adam:
+            b1, b2 = self.betas
+            _lib.check(_lib.lib().avc_adam_step_dev(_lib.ptr(self.fp.flat), _lib.ptr(self.grad),
+                                                    _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.fp.n,
+                                                    _lib.ptr(self._adam_state), b1, b2, self.eps, 1.0,
+                                                    _lib.stream_ptr()), "avc_adam_step_dev")
+        return self.loss_value()
+
+    def capture(self, dv: DeviceView, cos_anneal: float = 1.0):
+        """Capture the step on ``dv`` (whose buffer addresses, bg_choice and cos_anneal are frozen into the graph)."""
+        if self.phase_events is not None:
+            raise RuntimeError("capture(): phase events cannot be recorded inside a graph")
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):               # warm-up off the capture: workspaces, tensor maps, attributes
+            self.forward_backward(dv, cos_anneal)
+            self.loss_value()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self._set_device_adam(self.lr)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._graph_loss = self._graph_body(dv, cos_anneal, with_adam=(self.world == 1))
+        self._graph, self._graph_key = g, (id(dv), dv.bg_choice, float(cos_anneal))
+        return g
+
+    def _set_device_adam(self, lr: float):
+        self._adam_state[0].fill_(float(self.iter_step))
+        self._adam_state[1].fill_(float(lr))
+        self._lr_on_device = float(lr)
+        self._dev_step = self.iter_step
+
+    def replay(self, dv: DeviceView, lr: Optional[float] = None, cos_anneal: float = 1.0) -> torch.Tensor:
+        """One step through the captured graph (captures first / again when the frozen arguments changed)."""
+        if self._graph is None or self._graph_key != (id(dv), dv.bg_choice, float(cos_anneal)):
+            self.capture(dv, cos_anneal)
+        lr = self.lr if lr is None else lr
+        if self.world == 1:
+            if self._dev_step != self.iter_step:      # eager steps ran in between: resynchronise the device counter
+                self._set_device_adam(lr)
+            elif lr != self._lr_on_device:
+                self._adam_state[1].fill_(float(lr))
+                self._lr_on_device = float(lr)
+            self._graph.replay()
+            self.iter_step += 1
+            self._dev_step = self.iter_step
+        else:
+            self._graph.replay()
+            self.optimizer_step(lr)
+        return self._graph_loss

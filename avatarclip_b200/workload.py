@@ -18,6 +18,10 @@ import numpy as np
 import torch
 
 
+VIEW_FIELDS = ("rays_o", "rays_d", "near", "far", "jitter", "pix", "in_mask", "true_rgb", "mask", "ray_background",
+               "canvas_background", "scalars")
+
+
 @dataclass
 class HostView:
     """Everything one train_clip step consumes, as CPU tensors (pinned when requested)."""
@@ -37,10 +41,43 @@ class HostView:
     ambience: float
     H: int
     W: int
+    scalars: Optional[torch.Tensor] = None   # [4] = light_dir, ambience (what the loss stage reads on the device)
+    flat: Optional[torch.Tensor] = None      # uint8 buffer all the tensors above are views of, once pack() ran
+
+    def __post_init__(self):
+        if self.scalars is None:
+            self.scalars = torch.tensor([float(self.light_dir[0]), float(self.light_dir[1]), float(self.light_dir[2]),
+                                         float(self.ambience)], dtype=torch.float32)
+
+    def layout(self):
+        """[(field, byte offset, shape, dtype, bytes)], total bytes: one 256 B-aligned slot per present tensor."""
+        items, off = [], 0
+        for name in VIEW_FIELDS:
+            t = getattr(self, name)
+            if t is None:
+                continue
+            nb = t.numel() * t.element_size()
+            items.append((name, off, tuple(t.shape), t.dtype, nb))
+            off = (off + nb + 255) // 256 * 256
+        return items, off
+
+    def pack(self, pin: bool = False) -> "HostView":
+        """Move every tensor into ONE contiguous (optionally pinned) buffer so a step's inputs are a single H2D copy."""
+        if self.flat is not None:
+            return self
+        items, total = self.layout()
+        flat = torch.zeros(total, dtype=torch.uint8)
+        if pin and torch.cuda.is_available():
+            flat = flat.pin_memory()
+        for name, off, shape, dtype, nb in items:
+            dst = flat[off:off + nb].view(dtype).reshape(shape)
+            dst.copy_(getattr(self, name))
+            setattr(self, name, dst)
+        self.flat = flat
+        return self
 
     def tensors(self):
-        return [t for t in (self.rays_o, self.rays_d, self.near, self.far, self.jitter, self.pix, self.in_mask,
-                            self.true_rgb, self.mask, self.ray_background, self.canvas_background) if t is not None]
+        return [t for t in (getattr(self, n) for n in VIEW_FIELDS) if t is not None]
 
     def h2d_bytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors())
@@ -112,10 +149,4 @@ def make_view(index: int, n_rays: int = 512, H: int = 224, W: int = 224, seed: i
     hv = HostView(rays_o, rays_d, near.contiguous(), far.contiguous(), jitter, pix,
                   torch.from_numpy(dm.reshape(-1).astype(np.uint8)), true_rgb, mask, ray_bg, canvas_bg, bg_choice,
                   light.astype(np.float32), float(rng.uniform(0, 0.2)), H, W)
-    if pin and torch.cuda.is_available():
-        for name in ("rays_o", "rays_d", "near", "far", "jitter", "pix", "in_mask", "true_rgb", "mask",
-                     "ray_background", "canvas_background"):
-            t = getattr(hv, name)
-            if t is not None:
-                setattr(hv, name, t.pin_memory())
-    return hv
+    return hv.pack(pin=pin)

@@ -227,6 +227,8 @@ typedef struct avc_loss_inputs {
   int32_t bg_choice;             /* 0 white, 1/2 per-pixel grey, 3 black (main.py:387-415) */
   float light_dir[3];            /* sphere_coord(theta+U, phi+U) of main.py:433 (un-normalised) */
   float ambience;                /* main.py:440 */
+  const float* view_scalars;     /* NULL, or DEVICE [4] = {light_dir[3], ambience}: overrides the two host fields above
+                                    (lets a captured CUDA graph of the step be replayed with new per-view draws) */
   float igr_weight, mask_weight, clip_weight;  /* conf train.* */
   int32_t R, S, H, W;
 } avc_loss_inputs;
@@ -252,6 +254,11 @@ int avc_loss_stage_bwd(const avc_loss_inputs* in, const float* d_canvases, const
 int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
                   avc_stream_t stream);
+/* Same update with the step counter and the learning rate in DEVICE memory, so that the call can be captured
+ * once in a CUDA graph and replayed: state[0] = step count so far (incremented by the call), state[1] = lr
+ * (written by the host before each replay), state[2..3] = scratch. */
+int avc_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float* state, float beta1, float beta2, float eps, float grad_scale, avc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Camera rays: SMPL_Dataset.gen_rays_pose / gen_rays_silhouettes + near_far_from_sphere
