@@ -180,7 +180,8 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
                                                            pack + pl.pk_bsdf, Pn, os);
   AVC_LAUNCH_TRY();
   if (want_feat) {
-    EpiBias e{pack + dl.pk_b, w.feat, pl.Fp, pl.F, w.feat16};
+    // tcgen05 engine: every consumer of the features reads the split (colour lin0 A operand, its weight gradient)
+    EpiBias e{pack + dl.pk_b, pl.cfg.engine == 1 ? nullptr : w.feat, pl.Fp, pl.F, w.feat16};
     AVC_TRY(gemm_nt(pl, w, st, Pn, pl.F, dl.K, w.in[pl.L], dl.Kp, w.in16[pl.L], dl.pk_W, dl.Kp, e));
   }
   return 0;
@@ -260,9 +261,11 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   {
     const LinDim& dL = pl.sdf[pl.L];
     const LinDim& dp = pl.sdf[pl.L - 1];
+    // tcgen05 engine: qt_l is only ever consumed as a split operand (gradient chain, second-order sweep, dW)
+    const bool tc1 = pl.cfg.engine == 1;
     int64_t tot = P * (int64_t)(dp.Np / 4 > pl.EP ? dp.Np / 4 : pl.EP);   // threads: 4 qt columns each, 1 ge entry each
     k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
-                                                        w.z[pl.L - 1], dp.N, dp.Np, P, w.qt[pl.L - 1], w.ge,
+                                                        w.z[pl.L - 1], dp.N, dp.Np, P, tc1 ? nullptr : w.qt[pl.L - 1], w.ge,
                                                         w.qt16[pl.L - 1]);
     AVC_LAUNCH_TRY();
     for (int l = pl.L - 1; l >= 1; --l) {
@@ -270,7 +273,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
       const LinDim& dq = pl.sdf[l - 1];
       EpiChain e;
       e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
-      e.D1prev = w.z[l - 1]; e.QTprev = w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
+      e.D1prev = w.z[l - 1]; e.QTprev = tc1 ? nullptr : w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
       e.q16 = w.qt16[l - 1];
       AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
     }
@@ -284,11 +287,13 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   // ---- colour net
   {
     const LinDim& c0 = pl.col[0];
-    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, w.ch[1], pl.Hc, w.ch16[1]};
+    // tcgen05 engine: the fp32 copy of a hidden colour activation is only read by the heads (layer Lc)
+    const bool tc1 = pl.cfg.engine == 1;
+    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc, w.ch16[1]};
     AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
     for (int l = 1; l < pl.Lc; ++l) {
       const LinDim& c = pl.col[l];
-      EpiRelu e{pack + c.pk_b, w.ch[l + 1], pl.Hc, w.ch16[l + 1]};
+      EpiRelu e{pack + c.pk_b, (tc1 && l + 1 < pl.Lc) ? nullptr : w.ch[l + 1], pl.Hc, w.ch16[l + 1]};
       AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, w.ch16[l], c.pk_W, pl.Hc, e));
     }
     OutHeads oh{w.rgb6};
@@ -363,7 +368,10 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     if (l > 0) {
       AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], w.ch[l], pl.Hc, w.ch16[l], wbar + c.off_v, c.K,
                       wbar + c.off_b));
-      EpiDgradRelu e{w.ch[l], w.cbar[cur ^ 1], pl.Hc, w.cbar16[cur ^ 1]};
+      // tcgen05 engine: ReLU mask from the split of ch[l]; the fp32 copy of cbar is only read at layer 0 (thin ops)
+      const bool tc1 = pl.cfg.engine == 1;
+      EpiDgradRelu e{tc1 ? nullptr : w.ch[l], w.ch16[l].hi, (tc1 && l > 1) ? nullptr : w.cbar[cur ^ 1], pl.Hc,
+                     w.cbar16[cur ^ 1]};
       AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, e));
       cur ^= 1;
     } else {
@@ -372,7 +380,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
                       wbar + c.off_b));
       AVC_TRY(thin_tn<6>(st, w.cin, 8, 1.f, cb, pl.Hc, pl.Hc, P, wbar + c.off_v, 1, c.K, nullptr));
       // featbar = cbar . W0[:, 6:]
-      EpiStore es{w.featbar, pl.Fp, pl.F, w.featbar16};
+      EpiStore es{pl.cfg.engine == 1 ? nullptr : w.featbar, pl.Fp, pl.F, w.featbar16};
       AVC_TRY(gemm_nt(pl, w, st, P, pl.F, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, es));
       // nbar += cbar . W0[:, 3:6]   (d/d points is discarded: pts is a leaf, models/fields.py:97)
       OutNbarAdd on{w.nbar};
@@ -402,7 +410,8 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     AVC_TRY(gemm_tn(pl, w, st, P, d.N, d.K, w.qt[l], d.Np, w.qt16[l], ub, d.Kp, ub16, wbar + d.off_v, d.K));
     const LinDim& dn = pl.sdf[l + 1];
     EpiChainBwd e;
-    e.N = d.N; e.Np = d.Np; e.D1 = w.z[l]; e.QT = w.qt[l]; e.ZBAR = w.zbar[l];
+    e.N = d.N; e.Np = d.Np; e.D1 = w.z[l]; e.QT = pl.cfg.engine == 1 ? nullptr : w.qt[l]; e.qt16 = w.qt16[l];
+    e.ZBAR = w.zbar[l];
     // tcgen05 engine: the fp32 copy of ubar_{l+1} is only read by the column sum at the last linear
     e.UNEXT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.ubar[ucur ^ 1];
     e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
@@ -429,7 +438,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = dL.skip ? kSqrtHalf : 1.f;
     e.D1prev = w.z[pl.L - 1]; e.ZBARprev = w.zbar[pl.L - 1];
     e.sdfbar = w.sdfbar; e.wsdf = pack + pl.pk_wsdf; e.sdf_inv_scale = inv_scale;
-    e.z16 = w.zbar16[pl.L - 1];
+    e.z16 = w.zbar16[pl.L - 1]; e.store_f32 = pl.cfg.engine != 1;
     AVC_TRY(gemm_nt(pl, w, st, P, dp.N, pl.F, w.featbar, pl.Fp, w.featbar16, dL.pk_WT, pl.Fp, e));
   }
   for (int l = pl.L - 1; l >= 0; --l) {
@@ -442,7 +451,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     e.Nprev = dp.N; e.Npp = dp.Np; e.s = d.skip ? kSqrtHalf : 1.f;
     e.D1prev = w.z[l - 1]; e.ZBARprev = w.zbar[l - 1];
     e.sdfbar = nullptr; e.wsdf = nullptr; e.sdf_inv_scale = 1.f;
-    e.z16 = w.zbar16[l - 1];
+    e.z16 = w.zbar16[l - 1]; e.store_f32 = pl.cfg.engine != 1;
     AVC_TRY(gemm_nt(pl, w, st, P, dp.N, d.N, w.zbar[l], d.Np, w.zbar16[l], d.pk_WT, d.Np, e));
   }
   return 0;

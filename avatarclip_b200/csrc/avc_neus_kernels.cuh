@@ -21,6 +21,16 @@ __device__ __forceinline__ void split16_put(const Split16& s, size_t row, int co
   s.hi[row * s.ld + col] = h;
   s.lo[row * s.ld + col] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
+// value of the two-term split at 4 consecutive columns: hi + lo (what the tcgen05 GEMMs see of this operand)
+__device__ __forceinline__ void split16_get4(uint2 hi, uint2 lo, float v[4]) {
+  v[0] = __uint_as_float(hi.x << 16) + __uint_as_float(lo.x << 16);
+  v[1] = __uint_as_float(hi.x & 0xffff0000u) + __uint_as_float(lo.x & 0xffff0000u);
+  v[2] = __uint_as_float(hi.y << 16) + __uint_as_float(lo.y << 16);
+  v[3] = __uint_as_float(hi.y & 0xffff0000u) + __uint_as_float(lo.y & 0xffff0000u);
+}
+__device__ __forceinline__ float split16_get(const Split16& s, size_t row, int col) {
+  return __bfloat162float(s.hi[row * s.ld + col]) + __bfloat162float(s.lo[row * s.ld + col]);
+}
 __device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);       // one F2FP.BF16.F32.PACK_AB
   return *reinterpret_cast<uint32_t*>(&t);
@@ -525,7 +535,7 @@ __global__ void k_chain_start(const float* __restrict__ wsdf, int KL, int skipL,
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       v[i] = (c + i < Nprev) ? zz[i] * wsdf[c + i] * (skipL ? kSqrtHalf : 1.f) : 0.f;
-    *reinterpret_cast<float4*>(qt + i4) = make_float4(v[0], v[1], v[2], v[3]);
+    if (qt) *reinterpret_cast<float4*>(qt + i4) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(qt16, (size_t)p, c, v);
   }
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -690,7 +700,7 @@ struct EpiBias {
     const float bb[4] = {x.b.x, x.b.y, x.b.z, x.b.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] + bb[i] : 0.f;
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
   AVC_EPI_DIRECT
@@ -698,7 +708,7 @@ struct EpiBias {
 
 // gradient chain, layer l >= 1: u = acc (width K_l).  Columns < Nprev: ua = u * s, qt_prev = sp'(z_prev) * ua;
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
-// D1prev = the softplus' stash of layer l-1.
+// D1prev = the softplus' stash of layer l-1.  QTprev (fp32 copy) may be NULL: the tcgen05 engine keeps only the split.
 struct EpiChain {
   int Nprev, Npp; float s; const float* D1prev; float* QTprev; float* GE; int EP; int E; Split16 q16;
   struct Aux { float4 d; };
@@ -711,7 +721,7 @@ struct EpiChain {
     if (col + 3 < Nprev) {        // fast path: whole group inside the hidden part
       const size_t o = (size_t)row * Npp + col;
       float q[4] = {x.d.x * v[0] * s, x.d.y * v[1] * s, x.d.z * v[2] * s, x.d.w * v[3] * s};
-      *reinterpret_cast<float4*>(QTprev + o) = make_float4(q[0], q[1], q[2], q[3]);
+      if (QTprev) *reinterpret_cast<float4*>(QTprev + o) = make_float4(q[0], q[1], q[2], q[3]);
       split16_put4(q16, (size_t)row, col, q);
       return;
     }
@@ -720,10 +730,10 @@ struct EpiChain {
       int c = col + i;
       if (c < Nprev) {
         float qv = D1prev[(size_t)row * Npp + c] * v[i] * s;
-        QTprev[(size_t)row * Npp + c] = qv;
+        if (QTprev) QTprev[(size_t)row * Npp + c] = qv;
         split16_put(q16, (size_t)row, c, qv);
       } else {
-        if (c < Npp) { QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
+        if (c < Npp) { if (QTprev) QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
         int e = c - Nprev;
         if (e < E) GE[(size_t)row * EP + e] += v[i] * kSqrtHalf;
       }
@@ -768,7 +778,7 @@ struct EpiColor0 {
       z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
       v[i] = fmaxf(z, 0.f);
     }
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
   AVC_EPI_DIRECT
@@ -784,24 +794,35 @@ struct EpiRelu {
     AVC_EPI_UNPACK;
     v[0] = fmaxf(v[0] + x.b.x, 0.f); v[1] = fmaxf(v[1] + x.b.y, 0.f);
     v[2] = fmaxf(v[2] + x.b.z, 0.f); v[3] = fmaxf(v[3] + x.b.w, 0.f);
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
   AVC_EPI_DIRECT
 };
 
-// colour dgrad: out = acc * [h > 0]
+// colour dgrad: out = acc * [h > 0].  The mask comes from the fp32 activation Hm or, when Hm is NULL, from the hi
+// half of its split (h >= 0 after the ReLU, so h > 0 <=> the bf16 is not +-0).  OUT (fp32 copy) may be NULL.
 struct EpiDgradRelu {
-  const float* Hm; float* OUT; int ld; Split16 o16;
-  struct Aux { float4 h; };
+  const float* Hm; const __nv_bfloat16* Hhi; float* OUT; int ld; Split16 o16;
+  struct Aux { uint4 raw; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
-    return {*reinterpret_cast<const float4*>(Hm + (size_t)row * ld + col)};
+    if (Hm) return {*reinterpret_cast<const uint4*>(Hm + (size_t)row * ld + col)};
+    const uint2 h = *reinterpret_cast<const uint2*>(Hhi + (size_t)row * o16.ld + col);
+    return {make_uint4(h.x, h.y, 0u, 0u)};
   }
   __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    const float4 h = x.h;
-    v[0] = h.x > 0.f ? v[0] : 0.f; v[1] = h.y > 0.f ? v[1] : 0.f; v[2] = h.z > 0.f ? v[2] : 0.f; v[3] = h.w > 0.f ? v[3] : 0.f;
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) = make_float4(v[0], v[1], v[2], v[3]);
+    bool on[4];
+    if (Hm) {
+      on[0] = __uint_as_float(x.raw.x) > 0.f; on[1] = __uint_as_float(x.raw.y) > 0.f;
+      on[2] = __uint_as_float(x.raw.z) > 0.f; on[3] = __uint_as_float(x.raw.w) > 0.f;
+    } else {
+      on[0] = (x.raw.x & 0x00007fffu) != 0u; on[1] = (x.raw.x & 0x7fff0000u) != 0u;
+      on[2] = (x.raw.y & 0x00007fffu) != 0u; on[3] = (x.raw.y & 0x7fff0000u) != 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = on[i] ? v[i] : 0.f;
+    if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ld + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
   AVC_EPI_DIRECT
@@ -813,7 +834,7 @@ struct EpiStore {
     AVC_EPI_UNPACK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (col + i < N) ? v[i] : 0.f;
-    *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
+    if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }
 };
@@ -822,17 +843,33 @@ struct EpiStore {
 //   ubar_next[row][col] = sp'(z_l) * qbar * s_next            (col < N_l)
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
-  int N, Np; const float* D1; const float* QT; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
-  struct Aux { float4 d, qt; };
+  int N, Np; const float* D1; const float* QT; Split16 qt16; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
+  // qt_l comes from its fp32 copy QT or, when QT is NULL (tcgen05 engine), from the split hi + lo
+  struct Aux { float4 d; uint4 q; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
     const size_t o = (size_t)row * Np + clamp_group(col, N);
-    return {*reinterpret_cast<const float4*>(D1 + o), *reinterpret_cast<const float4*>(QT + o)};
+    Aux x;
+    x.d = *reinterpret_cast<const float4*>(D1 + o);
+    if (QT) {
+      x.q = *reinterpret_cast<const uint4*>(QT + o);
+    } else {
+      const size_t o16 = (size_t)row * qt16.ld + clamp_group(col, N);
+      const uint2 h = *reinterpret_cast<const uint2*>(qt16.hi + o16), l = *reinterpret_cast<const uint2*>(qt16.lo + o16);
+      x.q = make_uint4(h.x, h.y, l.x, l.y);
+    }
+    return x;
+  }
+  __device__ __forceinline__ float qt_at(int row, int c) const {
+    return QT ? QT[(size_t)row * Np + c] : split16_get(qt16, (size_t)row, c);
   }
   __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
     if (col + 3 < N) {
       const size_t o = (size_t)row * Np + col;
-      const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w}, qq[4] = {x.qt.x, x.qt.y, x.qt.z, x.qt.w};
+      const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w};
+      float qq[4];
+      if (QT) { qq[0] = __uint_as_float(x.q.x); qq[1] = __uint_as_float(x.q.y); qq[2] = __uint_as_float(x.q.z); qq[3] = __uint_as_float(x.q.w); }
+      else split16_get4(make_uint2(x.q.x, x.q.y), make_uint2(x.q.z, x.q.w), qq);
       float u[4], zb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -853,7 +890,7 @@ struct EpiChainBwd {
         float uv = s1 * v[i] * s_next;
         if (UNEXT) UNEXT[(size_t)row * ldu + c] = uv;
         split16_put(u16, (size_t)row, c, uv);
-        zb[i] = kBeta * (1.f - s1) * QT[(size_t)row * Np + c] * v[i];
+        zb[i] = kBeta * (1.f - s1) * qt_at(row, c) * v[i];
       } else {
         zb[i] = 0.f;
       }
@@ -867,7 +904,7 @@ struct EpiChainBwd {
 //   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev);  D1prev = softplus'(z_prev) stash
 struct EpiDgrad {
   int Nprev, Npp; float s; const float* D1prev; float* ZBARprev; const float* sdfbar; const float* wsdf;
-  float sdf_inv_scale; Split16 z16;
+  float sdf_inv_scale; Split16 z16; int store_f32;     // store_f32 = 0: only the split of the new zbar_prev is kept
   struct Aux { float4 d, zb; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
     const size_t o = (size_t)row * Npp + clamp_group(col, Nprev);
@@ -886,7 +923,7 @@ struct EpiDgrad {
         if (sdfbar) ab = fmaf(sb, wsdf[col + i], ab);
         r[i] = fmaf(dd[i], ab * s, zo[i]);
       }
-      *reinterpret_cast<float4*>(ZBARprev + o) = make_float4(r[0], r[1], r[2], r[3]);
+      if (store_f32) *reinterpret_cast<float4*>(ZBARprev + o) = make_float4(r[0], r[1], r[2], r[3]);
       split16_put4(z16, (size_t)row, col, r);
       return;
     }
@@ -898,7 +935,7 @@ struct EpiDgrad {
         if (sdfbar) ab = fmaf(sb, wsdf[c], ab);
         size_t o = (size_t)row * Npp + c;
         float zv = fmaf(D1prev[o], ab * s, ZBARprev[o]);
-        ZBARprev[o] = zv;
+        if (store_f32) ZBARprev[o] = zv;
         split16_put(z16, (size_t)row, c, zv);
       }
     }

@@ -33,13 +33,28 @@ import torch  # noqa: E402
 METRIC = "appearance-optim steps/sec (512 rays x 128 samples, CLIP loss)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
 # (r1_ncu_full_gemm_tc_*.txt); None where no capture of a full-size launch exists yet
-TRAFFIC_PER_LAUNCH = {"void avc::tc::gemm_tc_tn_kernel": 138.8e6, "void avc::tc::gemm_tc_nt_kernel": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r1_ncu_full_*.txt); for the NT
+# kernel: mean over the 33 full-size (65,536-point) launches of one step
+TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 138.8e6, "avc::tc::gemm_tc_nt_kernel": None}
 N_RAYS, CANVAS = 512, 224
 SDF_KW = dict(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
               geometric_init=True, weight_norm=True)
 COL_KW = dict(d_feature=256, mode="no_view_dir", d_in=6, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
               multires_view=0, squeeze_out=True, extra_color=True)
 REN_KW = dict(n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4, perturb=1.0, extra_color=True)
+
+
+def nt_designed_bytes_per_step():
+    """HBM bytes the NT launches of one step move BY DESIGN (unfused layers: every linear reads its split operand and
+    its stashed epilogue operands and writes its outputs once), B2 config, in units of one 256-wide fp32 row (1 KB):
+    fine pass per point: value 8 layers (reads 7.16, writes sp' stash + split 16), features 2, gradient chain 7 x 3
+    + 1.3, colour 4 x 2 + 1, colour dgrad 3 x 2.5 + 1 + 2, second-order sweep 8 x 5, value dgrad 8 x 4;
+    placement passes per point: 8 layers, split in / split out (15.16)."""
+    fine = 23.16 + 2 + 21 + 1.3 + 9 + 8.5 + 2 + 40 + 32
+    place = 15.16
+    p_fine = N_RAYS * (REN_KW["n_samples"] + REN_KW["n_importance"])
+    p_place = N_RAYS * (REN_KW["n_samples"] + 3 * REN_KW["n_importance"] // 4)
+    return 1024.0 * (fine * p_fine + place * p_place)
 
 
 def algorithmic_flops_per_step():
@@ -132,6 +147,15 @@ def build_world(device, engine):
     return sp, cp, clip_sd, text, ren, tower
 
 
+def kernel_key(name):
+    """'void avc::tc::gemm_tc_nt_kernel<128, 3, ...>(...)' -> 'avc::tc::gemm_tc_nt_kernel';
+    'void (anonymous namespace)::k_gemm16<EpiFc>(...)' -> 'k_gemm16'."""
+    import re
+    n = re.sub(r"^void\s+", "", name).replace("(anonymous namespace)::", "")
+    m = re.match(r"[A-Za-z_][A-Za-z0-9_:]*", n)
+    return m.group(0) if m else n
+
+
 def count_my_launches(fn):
     """Kernels of libavc_b200.so launched by one call of fn (torch.profiler / CUPTI), by name."""
     try:
@@ -146,7 +170,7 @@ def count_my_launches(fn):
                 n = ev.name
                 if "avc::" in n or "k_gemm16" in n or "(anonymous namespace)::k_" in n or n.startswith("k_"):
                     mine += 1
-                    key = n.split("<")[0].split("(")[0]
+                    key = kernel_key(n)
                     t = table.setdefault(key, [0, 0.0])
                     t[0] += 1
                     t[1] += ev.device_time if hasattr(ev, "device_time") else getattr(ev, "cuda_time", 0.0)
@@ -291,8 +315,8 @@ def run_native(args):
         # dominant kernel: algorithmic FLOP its launches execute per step / the sum of their device durations in the
         # profiled step (CUPTI kernel records taken live in this process, not under ncu)
         kern_us = {k: v for k, v in table.items() if isinstance(v, list)}
-        dom_flops = {"void avc::tc::gemm_tc_nt_kernel": nt_flops, "void avc::tc::gemm_tc_tn_kernel": tn_flops,
-                     "void avc::gemm_nt_kernel": nt_flops, "avc::gemm_tn_kernel": tn_flops}.get(dom)
+        dom_flops = {"avc::tc::gemm_tc_nt_kernel": nt_flops, "avc::tc::gemm_tc_tn_kernel": tn_flops,
+                     "avc::gemm_nt_kernel": nt_flops, "avc::gemm_tn_kernel": tn_flops}.get(dom)
         if dom_flops is not None and dom in kern_us and kern_us[dom][1] > 0:
             n_launch, dom_us = kern_us[dom]
             achieved = dom_flops / (dom_us * 1e-6) / 1e12
@@ -324,6 +348,14 @@ def run_native(args):
                                   "split: NT tiles 4.875 F_sdf + 2 F_col per point, TN tiles 2 F_sdf + F_col) / sum of "
                                   "their device durations (CUPTI, live); peak = " + peak_src + "; the kernel runs 3 "
                                   "bf16 MMAs per product (two-term split), so its ceiling is peak/3",
+                         "hbm_view": (lambda b, us: {"designed_bytes_per_step": b, "kernel_us_per_step": us,
+                                                     "achieved_GBps": b / (us * 1e-6) / 1e9 if us else None,
+                                                     "peak_GBps": peak_hbm,
+                                                     "frac": (b / (us * 1e-6) / 1e9 / peak_hbm) if us else None,
+                                                     "note": "the layers are not fused, so the NT launches are bound by "
+                                                             "the activation traffic they move by design (operands in, "
+                                                             "stash + split out), not by the tensor pipe"})(
+                             nt_designed_bytes_per_step(), kern_us.get("avc::tc::gemm_tc_nt_kernel", [0, 0.0])[1]),
                          "step_level": {"achieved": achieved_step, "frac": achieved_step / peak_tf,
                                         "ms_render_fwd_bwd": ms_render,
                                         "note": "all MLP FLOP/step (0.577 T) / CUDA-event time of render fwd+bwd"},
