@@ -57,8 +57,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <typename Epi>
 __global__ void __launch_bounds__(128)
 k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
-         int k_per_split, Epi epi) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+         int k_per_split, Epi epi, int early_trigger) {
+  // early_trigger: let the successor kernel start launching at once.  Otherwise it is released after the main loop,
+  // so that its CTAs (which only spin in griddepcontrol.wait) do not take SM slots from this kernel's later waves.
+  if (early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) unsigned char g_smem[];
   __half (*sA)[GBM][GBK + GPAD] = reinterpret_cast<__half (*)[GBM][GBK + GPAD]>(g_smem);
   __half (*sW)[GBN][GBK + GPAD] =
@@ -138,6 +140,7 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
     }
   }
   cp_async_wait<0>();
+  if (!early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int r0 = m0 + warp * 16 + (lane >> 2);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -159,7 +162,9 @@ int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw,
     AVC_CUDA_TRY(cudaFuncSetAttribute(k_gemm16<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
     attr_set = true;
   }
-  AVC_CUDA_TRY(launch_pdl(k_gemm16<Epi>, dim3(grid), dim3(128), G_SMEM, st, A, lda, Wt, ldw, M, N, K, kper, epi));
+  static int early = -1;      // AVC_CLIP_EARLY_TRIGGER=1: release the dependent kernel at the top (tuning knob)
+  if (early < 0) { const char* e = getenv("AVC_CLIP_EARLY_TRIGGER"); early = (e && atoi(e) == 1) ? 1 : 0; }
+  AVC_CUDA_TRY(launch_pdl(k_gemm16<Epi>, dim3(grid), dim3(128), G_SMEM, st, A, lda, Wt, ldw, M, N, K, kper, epi, early));
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -911,6 +916,9 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
   AVC_LAUNCH_TRY();
   // w.dtmp is the split-K accumulator of the two Wd-wide input-gradient GEMMs of a layer; it is cleared once here and
   // then by the LayerNorm backward that consumes it (no memset nodes inside the dependent-launch chain)
+  static int memset_nodes = -1;   // AVC_CLIP_MEMSET=1: clear w.dtmp with a memset node before each accumulating GEMM
+  if (memset_nodes < 0) { const char* e = getenv("AVC_CLIP_MEMSET"); memset_nodes = (e && atoi(e) == 1) ? 1 : 0; }
+  const int zdy = memset_nodes ? 0 : 1;
   AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
   for (int l = cfg->layers - 1; l >= 0; --l) {
     const avc_clip_layer_weights& lw = wt->layer[l];
@@ -925,9 +933,10 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     }
     { EpiDfc e{fcp, w.d16b, mlp};
       AVC_TRY(gemm16(st, w.d16a, Wd, (const __half*)lw.w_proj_t, Wd, M, mlp, Wd, 1, e)); }
+    if (memset_nodes) AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16b, mlp, (const __half*)lw.w_fc_t, mlp, M, Wd, mlp, 4, e)); }
-    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, 1));
+    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, zdy));
     AVC_LAUNCH_TRY();
     // ---- attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in))))
     { EpiStoreUnscale e{w.dO, Wd, w.scale};
@@ -936,9 +945,10 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
     AVC_LAUNCH_TRY();
     AVC_CUDA_TRY(launch_pdl(k_to_half_rowscaled, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, nullptr));
     AVC_LAUNCH_TRY();
+    if (memset_nodes) AVC_CUDA_TRY(cudaMemsetAsync(w.dtmp, 0, sizeof(float) * (size_t)M * Wd, st));
     { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
       AVC_TRY(gemm16(st, w.d16a, 3 * Wd, (const __half*)lw.w_qkv_t, 3 * Wd, M, Wd, 3 * Wd, 3, e)); }
-    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, 1));
+    AVC_CUDA_TRY(launch_pdl(k_layernorm_bwd, dim3(ceil_div(M, 8)), dim3(256), 0, st, xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, zdy));
     AVC_LAUNCH_TRY();
   }
   // ln_pre, patch embedding, pre-processing

@@ -58,6 +58,11 @@ inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t
 
 // -------------------------------------------------------------------------------- packing
 int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStream_t st) {
+  static_assert(kMaxJobs >= 2 * kMaxLin + 4, "job table too small");
+  PackJobs jobs;
+  jobs.n = 0;
+  int maxN = 1;
+  auto add = [&](const PackJob& j) { jobs.j[jobs.n++] = j; if (j.N > maxN) maxN = j.N; };
   for (int l = 0; l <= pl.L; ++l) {
     const LinDim& d = pl.sdf[l];
     PackJob j;
@@ -75,7 +80,7 @@ int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStrea
       j.row_shift = 1; j.bias_shift = 1;
       j.row0 = pack + pl.pk_wsdf; j.row0_b = pack + pl.pk_bsdf;
     }
-    k_pack_linear<<<d.N, 128, 0, st>>>(j);
+    add(j);
   }
   for (int l = 0; l < pl.Lc; ++l) {
     const LinDim& d = pl.col[l];
@@ -96,7 +101,7 @@ int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStrea
       j.WT[0] = pack + d.pk_WT; j.ldwt[0] = pl.Hc;
     }
     j.bias = pack + d.pk_b;
-    k_pack_linear<<<d.N, 128, 0, st>>>(j);
+    add(j);
   }
   for (int h = 0; h < 2; ++h) {   // colour head lin{Lc} -> rows 0..2, extra_lin -> rows 3..5 of W6
     const LinDim& d = h == 0 ? pl.col[pl.Lc] : pl.extra;
@@ -108,8 +113,9 @@ int pack_weights(const NeusPlan& pl, const float* params, float* pack, cudaStrea
     j.W[0] = pack + pl.pk_W6; j.ldw[0] = pl.Hc;
     j.bias = pack + pl.pk_b6;
     j.dst_row_off = 3 * h;
-    k_pack_linear<<<3, 128, 0, st>>>(j);
+    add(j);
   }
+  k_pack_linear<<<dim3(maxN, jobs.n), 128, 0, st>>>(jobs);
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -317,9 +323,10 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
 // -------------------------------------------------------------------------------- backward
 template <int NI>
 int thin_tn(cudaStream_t st, const float* S, int lds, float s_scale, const float* Hm, int ldh, int NC, int64_t P,
-            float* out, int si, int sc, float* bout) {
+            float* out, int si, int sc, float* bout, int split = NI, float* out2 = nullptr, float* bout2 = nullptr) {
   const int rows = 128;
-  k_thin_tn<NI><<<blocks_for(P, rows), 256, 0, st>>>(S, lds, s_scale, Hm, ldh, NC, P, rows, out, si, sc, bout);
+  k_thin_tn<NI><<<blocks_for(P, rows), 256, 0, st>>>(S, lds, s_scale, Hm, ldh, NC, P, rows, out, si, sc, bout, split,
+                                                     out2, bout2);
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -354,8 +361,9 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
   {
     const LinDim& dh = pl.col[pl.Lc];
     const LinDim& dx = pl.extra;
-    AVC_TRY(thin_tn<3>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b));
-    AVC_TRY(thin_tn<3>(st, w.y6bar + 3, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dx.off_v, pl.Hc, 1, wbar + dx.off_b));
+    // both heads read the same activation: one pass, rows 0..2 -> lin{Lc}, rows 3..5 -> extra_lin
+    AVC_TRY(thin_tn<6>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b, 3,
+                       wbar + dx.off_v, wbar + dx.off_b));
     k_heads_dgrad<<<blocks_for(P * pl.Hc / 4, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0],
                                                               w.cbar16[0]);
     AVC_LAUNCH_TRY();
@@ -394,8 +402,10 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
   int ucur = 0;
   {
     const LinDim& d0 = pl.sdf[0];
-    k_dge<<<blocks_for(P, 128), 128, 0, st>>>(w.cin, w.nbar, pl.EP, pl.E, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P,
-                                              w.ubar[0], d0.Kp, w.gebar, with_ld(w.ubar16[0], d0.Kp));
+    // tcgen05 engine: ubar_0 is only consumed as a split operand
+    k_dge<<<blocks_for(P * 8, 256), 256, 0, st>>>(w.cin, w.nbar, pl.EP, pl.E, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P,
+                                                  pl.cfg.engine == 1 ? nullptr : w.ubar[0], d0.Kp, w.gebar,
+                                                  with_ld(w.ubar16[0], d0.Kp));
     AVC_LAUNCH_TRY();
   }
   for (int l = 0; l <= pl.L; ++l) {
@@ -459,13 +469,18 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
 
 int weight_norm_backward_all(const NeusPlan& pl, const float* params, const float* wbar, float* grads,
                              cudaStream_t st) {
+  WnJobs jobs;
+  jobs.n = 0;
+  int maxN = 1;
   auto one = [&](const LinDim& d) {
-    k_wn_backward<<<d.N, 128, 0, st>>>(params + d.off_v, params + d.off_g, wbar + d.off_v, wbar + d.off_b, d.N, d.K,
-                                       grads + d.off_g, grads + d.off_v, grads + d.off_b);
+    jobs.j[jobs.n++] = WnJob{params + d.off_v, params + d.off_g, wbar + d.off_v, wbar + d.off_b, d.N, d.K,
+                             grads + d.off_g, grads + d.off_v, grads + d.off_b};
+    if (d.N > maxN) maxN = d.N;
   };
   for (int l = 0; l <= pl.L; ++l) one(pl.sdf[l]);
   for (int l = 0; l <= pl.Lc; ++l) one(pl.col[l]);
   one(pl.extra);
+  k_wn_backward<<<dim3(maxN, jobs.n), 128, 0, st>>>(jobs);
   AVC_LAUNCH_TRY();
   return 0;
 }

@@ -91,7 +91,12 @@ struct PackJob {
   int dst_row_off;           // added to (n - row_shift): packs lin{Lc} and extra_lin into W6
 };
 
-__global__ void __launch_bounds__(128) k_pack_linear(PackJob j) {
+// All linears of a call are packed by ONE launch: blockIdx.y selects the job, blockIdx.x the output row.
+constexpr int kMaxJobs = 36;
+struct PackJobs { int n; PackJob j[kMaxJobs]; };
+
+__global__ void __launch_bounds__(128) k_pack_linear(const __grid_constant__ PackJobs jobs) {
+  const PackJob& j = jobs.j[blockIdx.y];
   const int n = blockIdx.x;
   if (n >= j.N) return;
   const float* vr = j.v + (size_t)n * j.K;
@@ -122,10 +127,16 @@ __global__ void __launch_bounds__(128) k_pack_linear(PackJob j) {
 
 // Weight-norm backward: Wbar (dense, in the v slot of `wbar`) -> gbar, vbar; bias grads copied.
 //   gbar = sum_k Wbar * vhat ; vbar = g/||v|| (Wbar - gbar vhat)        (vhat = v/||v||)
+struct WnJob { const float* v; const float* g; const float* Wbar; const float* bbar; int N, K; float* gg; float* gv; float* gb; };
+struct WnJobs { int n; WnJob j[kMaxJobs]; };
+
 __global__ void __launch_bounds__(128)
-k_wn_backward(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ Wbar,
-              const float* __restrict__ bbar, int N, int K, float* __restrict__ gg, float* __restrict__ gv,
-              float* __restrict__ gb) {
+k_wn_backward(const __grid_constant__ WnJobs jobs) {
+  const WnJob& J = jobs.j[blockIdx.y];
+  const float* __restrict__ v = J.v; const float* __restrict__ g = J.g; const float* __restrict__ Wbar = J.Wbar;
+  const float* __restrict__ bbar = J.bbar;
+  const int N = J.N, K = J.K;
+  float* __restrict__ gg = J.gg; float* __restrict__ gv = J.gv; float* __restrict__ gb = J.gb;
   const int n = blockIdx.x;
   if (n >= N) return;
   const float* vr = v + (size_t)n * K;
@@ -457,11 +468,13 @@ struct OutNbarAdd { // nbar[p][0..2] += d loss / d normal coming through colour 
 };
 
 // out[i*si + c*sc] += sum_p S[p*lds + i] * Hm[p*ldh + c]   (i < NI, c < NC);  optional s_scale on S;
-// optional bout[i] += sum_p S[p,i].  Blocks split the rows; threads own columns.
+// optional bout[i] += sum_p S[p,i].  Rows i >= split go to (out2, bout2) with index i - split (two linears that share
+// the activation Hm, e.g. the two colour heads, in one pass over it).  Blocks split the rows; threads own columns.
 template <int NI>
 __global__ void __launch_bounds__(256)
 k_thin_tn(const float* __restrict__ S, int lds, float s_scale, const float* __restrict__ Hm, int ldh, int NC,
-          int64_t P, int rows_per_block, float* __restrict__ out, int si, int sc, float* __restrict__ bout) {
+          int64_t P, int rows_per_block, float* __restrict__ out, int si, int sc, float* __restrict__ bout,
+          int split, float* __restrict__ out2, float* __restrict__ bout2) {
   __shared__ float sS[64][NI];
   const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t p1 = min(P, p0 + (int64_t)rows_per_block);
@@ -480,21 +493,39 @@ k_thin_tn(const float* __restrict__ S, int lds, float s_scale, const float* __re
       }
       __syncthreads();
       if (c < NC) {
-        for (int rr = 0; rr < nr; ++rr) {
-          float h = Hm[(size_t)(pb + rr) * ldh + c];
+        const float* hp = Hm + (size_t)pb * ldh + c;
+        int rr = 0;
+        for (; rr + 8 <= nr; rr += 8) {          // 8 independent loads in flight per thread
+          float h[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) h[u] = hp[(size_t)(rr + u) * ldh];
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int i = 0; i < NI; ++i) acc[i] = fmaf(sS[rr + u][i], h[u], acc[i]);
+        }
+        for (; rr < nr; ++rr) {
+          float h = hp[(size_t)rr * ldh];
 #pragma unroll
           for (int i = 0; i < NI; ++i) acc[i] = fmaf(sS[rr][i], h, acc[i]);
         }
       }
-      if (bout && cb == 0 && threadIdx.x < NI)
+      if ((bout || bout2) && cb == 0 && threadIdx.x < NI)
         for (int rr = 0; rr < nr; ++rr) bacc += sS[rr][threadIdx.x];
     }
     if (c < NC) {
 #pragma unroll
-      for (int i = 0; i < NI; ++i) atomicAdd(out + (size_t)i * si + (size_t)c * sc, acc[i]);
+      for (int i = 0; i < NI; ++i) {
+        float* o = (i < split) ? out + (size_t)i * si : out2 + (size_t)(i - split) * si;
+        atomicAdd(o + (size_t)c * sc, acc[i]);
+      }
     }
   }
-  if (bout && threadIdx.x < NI) atomicAdd(bout + threadIdx.x, bacc);
+  if (threadIdx.x < NI) {
+    const int i = threadIdx.x;
+    if (i < split) { if (bout) atomicAdd(bout + i, bacc); }
+    else if (bout2) atomicAdd(bout2 + (i - split), bacc);
+  }
 }
 
 // out[c] += scale * sum_p X[p*ld + c], c < NC
@@ -571,32 +602,38 @@ __global__ void k_normal(const float* __restrict__ ge, int EP, int multires, flo
   if (grad_out) { grad_out[p * 3 + 0] = n[0]; grad_out[p * 3 + 1] = n[1]; grad_out[p * 3 + 2] = n[2]; }
 }
 
-// gebar = D(y) nbar -> ubar0[p][EP] (padding zeroed) and gebar[p][EP].
+// gebar = D(y) nbar -> ubar0[p][ldu] (padding zeroed; the fp32 copy may be NULL) and gebar[p][EP].  8 lanes per
+// point as in encode_group: lane 0 writes the identity columns and the padding, lanes 1..7 one frequency each
+// (6 adjacent columns), so the lanes of a point cover its row with adjacent pieces.
 __global__ void k_dge(const float* __restrict__ cin, const float* __restrict__ nbar, int EP, int E, int multires,
                       float scale, int64_t P, float* __restrict__ ubar0, int ldu, float* __restrict__ gebar,
                       Split16 u16) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = t >> 3;
+  const int gl = (int)(t & 7);
   if (p >= P) return;
   const float* c = cin + (size_t)p * 8;
   const float nb[3] = {nbar[p * 4 + 0], nbar[p * 4 + 1], nbar[p * 4 + 2]};
-  float* u = ubar0 + (size_t)p * ldu;
+  float* u = ubar0 ? ubar0 + (size_t)p * ldu : nullptr;
   float* g = gebar + (size_t)p * EP;
-  auto put = [&](int col, float v) { u[col] = v; g[col] = v; split16_put(u16, (size_t)p, col, v); };
+  auto put = [&](int col, float v) { if (u) u[col] = v; g[col] = v; split16_put(u16, (size_t)p, col, v); };
+  if (gl == 0) {
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float y = c[a] * scale;
-    put(a, nb[a]);
-    float f = 1.f;
-    for (int k = 0; k < multires; ++k) {
+    for (int a = 0; a < 3; ++a) put(a, nb[a]);
+    for (int col = E; col < EP; ++col) put(col, 0.f);
+    for (int col = EP; col < ldu; ++col) { if (u) u[col] = 0.f; split16_put(u16, (size_t)p, col, 0.f); }
+    return;
+  }
+  for (int k = gl - 1; k < multires; k += 7) {
+    const float f = ldexpf(1.f, k);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
       float sn, cs;
-      sincosf(y * f, &sn, &cs);
+      sincosf(c[a] * scale * f, &sn, &cs);
       put(3 + 6 * k + a, f * cs * nb[a]);
       put(6 + 6 * k + a, -f * sn * nb[a]);
-      f *= 2.f;
     }
   }
-  for (int col = E; col < EP; ++col) put(col, 0.f);
-  for (int col = EP; col < ldu; ++col) { u[col] = 0.f; split16_put(u16, (size_t)p, col, 0.f); }
 }
 
 // ubar[p][col0 + e] = gebar[p][e] / sqrt(2)   (the encoding half of a skip layer's input adjoint)
