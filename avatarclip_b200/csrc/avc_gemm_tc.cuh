@@ -182,15 +182,22 @@ constexpr int kEpiWarps = 8;
 // NT kernel: EW epilogue warps (EW/4 per TMEM lane quarter) and PFB registers per thread of prefetched epilogue
 // operands are template parameters; the launcher uses 16 warps / 32 registers (see launch_gemm_tc_nt).
 
-template <int BN, int NPROD, int EW = 8>
+// RESB: the CTA keeps its whole B panel (BN rows x up to kResK k-blocks, hi and lo) resident in shared memory and only
+// streams A: with the panel re-fetched for every 128-row tile the operand traffic L2 -> SM (262 KB per 128 x 128 tile)
+// was what bounded the launches with a light epilogue; resident, it is half of that.
+constexpr int kResK = 4;          // k-blocks (of 64) a resident panel holds: K <= 256
+template <int BN, int NPROD, int EW = 8, bool RESB = false>
 struct TcCfg {
   static constexpr int A_BYTES = kBM * kBK * 2;                    // one (hi or lo) A slab: 16 KB
   static constexpr int B_BYTES = BN * kBK * 2;
   static constexpr int NOP = (NPROD == 3) ? 2 : 1;                 // slabs per operand (hi, lo)
-  static constexpr int STAGE_BYTES = NOP * (A_BYTES + B_BYTES);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES);
   static constexpr int EPI_BYTES = EW * 32 * 16 * 4;       // per-warp 32x16 fp32 transpose buffers (XOR-swizzled)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
+  static constexpr int BRES_BYTES = RESB ? kResK * NOP * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = RESB ? NOP * A_BYTES : NOP * (A_BYTES + B_BYTES);
+  static constexpr int kBudget = 232448 - 1024 - 256 - EPI_BYTES - BRES_BYTES;
+  static constexpr int STAGES = RESB ? (kBudget / STAGE_BYTES >= 4 ? 4 : kBudget / STAGE_BYTES)
+                                     : ((200 * 1024) / STAGE_BYTES >= 4 ? 4 : ((200 * 1024) / STAGE_BYTES));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BRES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_BYTES;
   static_assert(STAGES >= 2, "tile too large for shared memory");
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -244,31 +251,39 @@ struct EpiTraits<E, std::void_t<typename E::Aux>> {
 // Persistent: gridDim.x CTAs (<= one per SM) walk the output tiles t = blockIdx.x, +gridDim.x, ...  The accumulator
 // is double buffered in TMEM (2 x BN columns) so the epilogue of tile i runs while the TMA/MMA warps already work
 // on tile i+1:  tfull[b] (MMA -> epilogue, tcgen05.commit)  /  tempty[b] (epilogue -> MMA, one arrive per warp).
-template <int BN, int NPROD, int EW, int PFB, typename Epi>
+template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                   int M, int N, int K, Epi epi) {
-  using Cfg = TcCfg<BN, NPROD, EW>;
+  using Cfg = TcCfg<BN, NPROD, EW, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
-  uint64_t* bars = (uint64_t*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 4);
-  float* epi_stage = (float*)(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  constexpr int kOpBytes = Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES;     // stages, then the resident B panel
+  uint64_t* bars = (uint64_t*)(smem + kOpBytes);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 5);
+  float* epi_stage = (float*)(smem + kOpBytes + 256);
   const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bres_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull0 = empty0 + 8 * Cfg::STAGES,
-                 tempty0 = tfull0 + 16;
+                 tempty0 = tfull0 + 16, bfull = tempty0 + 16;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
-  const int ntiles = ((M + kBM - 1) / kBM) * tiles_n;
+  const int tiles_m = (M + kBM - 1) / kBM;
   const int nk = (K + kBK - 1) / kBK;
+  // A CTA owns ONE column tile (n0 fixed: its B panel can stay resident) and walks the row tiles m_first, +m_stride, ..;
+  // neighbouring CTAs work on the same row tile at the same time (A is read from HBM once, from L2 after that).
+  // The host makes gridDim.x a multiple of tiles_n.
+  const int n0 = (int)(blockIdx.x % tiles_n) * BN;
+  const int m_first = (int)(blockIdx.x / tiles_n), m_stride = (int)(gridDim.x / tiles_n);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
     if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b2 = 0; b2 < 2; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, EW); }
+    mbar_init(bfull, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
@@ -279,19 +294,27 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      if (RESB) {     // the B panel of this CTA's column tile, once
+        mbar_expect_tx(bfull, (uint32_t)(nk * Cfg::NOP * Cfg::B_BYTES));
+        for (int kb = 0; kb < nk; ++kb) {
+          const uint32_t dst = bres_base + kb * (Cfg::NOP * Cfg::B_BYTES);
+          tma_load_2d(dst, &mapBhi, kb * kBK, n0, bfull);
+          if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull);
+        }
+      }
       int it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+      for (int mt = m_first; mt < tiles_m; mt += m_stride) {
+        const int m0 = mt * kBM;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % Cfg::STAGES;
           mbar_wait(empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
           mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
           tma_load_2d(st, &mapAhi, kb * kBK, m0, full0 + 8 * s);
-          tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES, &mapBhi, kb * kBK, n0, full0 + 8 * s);
-          if (NPROD == 3) {
-            tma_load_2d(st + Cfg::A_BYTES, &mapAlo, kb * kBK, m0, full0 + 8 * s);
-            tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, full0 + 8 * s);
+          if (NPROD == 3) tma_load_2d(st + Cfg::A_BYTES, &mapAlo, kb * kBK, m0, full0 + 8 * s);
+          if (!RESB) {
+            tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES, &mapBhi, kb * kBK, n0, full0 + 8 * s);
+            if (NPROD == 3) tma_load_2d(st + Cfg::NOP * Cfg::A_BYTES + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, full0 + 8 * s);
           }
         }
       }
@@ -300,8 +323,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+      if (RESB) { mbar_wait(bfull, 0); tc_fence_after(); }
       int it = 0, lt = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
         const uint32_t buf = lt & 1;
         mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         tc_fence_after();
@@ -311,7 +335,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
           tc_fence_after();
           const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
-          const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+          const uint32_t b_hi = RESB ? bres_base + kb * (Cfg::NOP * Cfg::B_BYTES) : a_hi + Cfg::NOP * Cfg::A_BYTES;
+          const uint32_t b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
           for (int k4 = 0; k4 < kBK / 16; ++k4) {
             // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B
@@ -350,20 +375,19 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const uint32_t stage = smem_u32(epi_stage) + (uint32_t)(warp - 2) * 2048u;
     const uint32_t st_row = stage + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
     const uint32_t ld_addr = stage + (uint32_t)ri * 64u + (uint32_t)(((lane & 3) ^ ((ri >> 1) & 3)) * 16);
-    const int col_last = (N - 1) & ~3, row_last = M - 1, tile_last = ntiles - 1;
+    const int col_last = (N - 1) & ~3, row_last = M - 1;
     Aux aux[NPF][4];
-    auto issue = [&](Aux (&dst)[4], int tile, int sb) {
-      tile = min(tile, tile_last);
-      const int row = (tile / tiles_n) * kBM + q * 32 + ri;
-      const int col = min((tile % tiles_n) * BN + (cw + sb * (EW / 4)) * 16 + cg, col_last);
+    auto issue = [&](Aux (&dst)[4], int mt, int sb) {
+      const int row = min(mt, tiles_m - 1) * kBM + q * 32 + ri;
+      const int col = min(n0 + (cw + sb * (EW / 4)) * 16 + cg, col_last);
 #pragma unroll
       for (int p = 0; p < 4; ++p) dst[p] = Tr::prefetch(epi, min(row + 8 * p, row_last), col);
     };
 #pragma unroll
-    for (int s = 0; s < NPF; ++s) issue(aux[s], blockIdx.x, s);
+    for (int s = 0; s < NPF; ++s) issue(aux[s], m_first, s);
     int lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      const int m0 = (t / tiles_n) * kBM, n0 = (t % tiles_n) * BN;
+    for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
+      const int m0 = mt * kBM;
       const uint32_t buf = lt & 1;
       mbar_wait(tfull0 + 8 * buf, (lt >> 1) & 1);
       tc_fence_after();
@@ -390,7 +414,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           __syncwarp();
         }
         // refill the slot just consumed: NPF sub-blocks ahead in this warp's (tile, sub-block) sequence
-        issue(aux[sb % NPF], t + ((sb + NPF) / NSUB) * gridDim.x, (sb + NPF) % NSUB);
+        issue(aux[sb % NPF], mt + ((sb + NPF) / NSUB) * m_stride, (sb + NPF) % NSUB);
       }
       tc_fence_before();
       __syncwarp();
@@ -405,10 +429,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   }
 }
 
-template <int BN, int NPROD, int EW, int PFB, typename Epi>
+template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
                                        const Epi& epi) {
-  using Cfg = TcCfg<BN, NPROD, EW>;
+  using Cfg = TcCfg<BN, NPROD, EW, RESB>;
   CUtensorMap mAh, mAl, mBh, mBl;
   AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
   AVC_TRY(make_map_bf16_cached(&mBh, B.hi, (uint64_t)N, (uint64_t)K, (uint64_t)B.ld, kBK, BN));
@@ -418,7 +442,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   } else {
     mAl = mAh; mBl = mBh;
   }
-  auto kern = gemm_tc_nt_kernel<BN, NPROD, EW, PFB, Epi>;
+  auto kern = gemm_tc_nt_kernel<BN, NPROD, EW, PFB, RESB, Epi>;
   static bool attr_set = false;    // per template instantiation
   if (!attr_set) {
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -430,8 +454,12 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
     AVC_CUDA_TRY(cudaGetDevice(&dev));
     AVC_CUDA_TRY(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int ntiles = ceil_div(M, kBM) * ceil_div(N, BN);
-  dim3 grid(ntiles < num_sms ? ntiles : num_sms);      // persistent: at most one CTA per SM
+  const int tiles_n = ceil_div(N, BN);
+  const int ntiles = ceil_div(M, kBM) * tiles_n;
+  int g = ntiles < num_sms ? ntiles : num_sms;         // persistent: at most one CTA per SM ...
+  g = (g / tiles_n) * tiles_n;                         // ... and a whole number of CTAs per column tile
+  if (g < tiles_n) return AVC_E_BADCFG;
+  dim3 grid(g);
   kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
   AVC_LAUNCH_TRY();
   return 0;
@@ -445,8 +473,15 @@ static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, co
   if (M <= 0 || N <= 0) return 0;
   // 16 epilogue warps, one (32-byte operands) or two (16-byte operands) sub-blocks of prefetch.  Measured per step
   // (73 launches, B200): 16 warps / 32 regs 3.01 ms, 16 / 16 3.02 ms, 8 warps / 64 regs 3.32 ms, 8 / 32 3.34 ms.
-  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, Epi>(st, M, N, K, A, B, epi);
-  return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, Epi>(st, M, N, K, A, B, epi);
+  // K <= 256: the B panel stays resident in shared memory (RESB); longer reductions stream both operands.
+  static int resb = -1;       // AVC_NT_RESB=0 forces the streaming variant (tuning knob)
+  if (resb < 0) { const char* e = getenv("AVC_NT_RESB"); resb = (e && atoi(e) == 0) ? 0 : 1; }
+  if (resb && K <= kResK * kBK) {
+    if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi);
+    return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi);
+  }
+  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi);
+  return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel
