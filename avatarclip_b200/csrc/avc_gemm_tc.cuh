@@ -55,6 +55,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+// TMA prefetch of one box into L2 (no shared memory, no barrier): decouples the HBM latency of the A stream from the
+// depth of the shared-memory ring
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -68,6 +73,13 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// One lane of a converged warp (elect.sync): code under `if (elect_one_sync())` is known to run on exactly one
+// thread, so the uniform-datapath instructions in it (UTCHMMA, UTCBAR) need no per-instruction election.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 / fp16 inputs, fp32 accumulate)
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -255,18 +267,21 @@ template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                  int M, int N, int K, Epi epi) {
+                  int M, int N, int K, Epi epi, int l2pf) {
   using Cfg = TcCfg<BN, NPROD, EW, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
   constexpr int kOpBytes = Cfg::STAGES * Cfg::STAGE_BYTES + Cfg::BRES_BYTES;     // stages, then the resident B panel
   uint64_t* bars = (uint64_t*)(smem + kOpBytes);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 5);
+  // accumulators: NBUF x BN TMEM columns (all 512 for BN = 128), so the TMA/MMA side can run up to NBUF - 1 tiles
+  // ahead of the epilogue instead of one
+  constexpr int NBUF = (512 / BN) > 4 ? 4 : (512 / BN);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 2 * NBUF + 1);
   float* epi_stage = (float*)(smem + kOpBytes + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bres_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * Cfg::STAGES, tfull0 = empty0 + 8 * Cfg::STAGES,
-                 tempty0 = tfull0 + 16, bfull = tempty0 + 16;
+                 tempty0 = tfull0 + 8 * NBUF, bfull = tempty0 + 8 * NBUF;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + BN - 1) / BN;
@@ -282,11 +297,11 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     tma_prefetch_desc(&mapAhi); tma_prefetch_desc(&mapBhi);
     if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int b2 = 0; b2 < 2; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, EW); }
+    for (int b2 = 0; b2 < NBUF; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, EW); }
     mbar_init(bfull, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 2 * BN);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), NBUF * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -302,10 +317,23 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull);
         }
       }
+      // Optional (AVC_NT_L2PF=1, kernel argument l2pf): pull the A boxes of the NEXT row tile into L2 while this one is
+      // loaded, so that the ring's loads see L2 latency.  Measured on B200: no change (2.77 vs 2.76 ms per step), i.e.
+      // the depth of the A ring is not what bounds these launches; off by default.
+      if (l2pf && m_first < tiles_m)
+        for (int kb = 0; kb < nk; ++kb) {
+          tma_prefetch_2d(&mapAhi, kb * kBK, m_first * kBM);
+          if (NPROD == 3) tma_prefetch_2d(&mapAlo, kb * kBK, m_first * kBM);
+        }
       int it = 0;
       for (int mt = m_first; mt < tiles_m; mt += m_stride) {
         const int m0 = mt * kBM;
+        const bool pf = l2pf && (mt + m_stride < tiles_m);
         for (int kb = 0; kb < nk; ++kb, ++it) {
+          if (pf) {
+            tma_prefetch_2d(&mapAhi, kb * kBK, m0 + m_stride * kBM);
+            if (NPROD == 3) tma_prefetch_2d(&mapAlo, kb * kBK, m0 + m_stride * kBM);
+          }
           const int s = it % Cfg::STAGES;
           mbar_wait(empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
@@ -321,41 +349,42 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-      if (RESB) { mbar_wait(bfull, 0); tc_fence_after(); }
-      int it = 0, lt = 0;
-      for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
-        const uint32_t buf = lt & 1;
-        mbar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+    // The whole warp walks the loop converged (all lanes poll the barriers); one elected lane issues the MMAs.  The
+    // issue rate matters: 48 MMAs of 64 tensor-cycles each per 128 x 128 x 256 tile leave ~64 cycles per instruction,
+    // so the descriptors are derived by adding constants to one base per operand and k-block.
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    if (RESB) { mbar_wait(bfull, 0); tc_fence_after(); }
+    int it = 0, lt = 0;
+    for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
+      const uint32_t buf = lt % NBUF;
+      mbar_wait(tempty0 + 8 * buf, ((lt / NBUF) & 1) ^ 1);   // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        const int s = it % Cfg::STAGES;
+        mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % Cfg::STAGES;
-          mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
+        if (elect_one_sync()) {
+          const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_hi = RESB ? bres_base + kb * (Cfg::NOP * Cfg::B_BYTES) : a_hi + Cfg::NOP * Cfg::A_BYTES;
-          const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+          // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B = +2 in the
+          // descriptor's start-address field (no carry out of the field: shared addresses stay below 2^18)
+          const uint64_t da = make_smem_desc(a_hi, 0, 1024), db = make_smem_desc(b_hi, 0, 1024);
+          constexpr uint64_t kLoA = (uint64_t)(Cfg::A_BYTES >> 4), kLoB = (uint64_t)(Cfg::B_BYTES >> 4);
 #pragma unroll
           for (int k4 = 0; k4 < kBK / 16; ++k4) {
-            // K-major SWIZZLE_128B: 8-row groups are 1024 B apart (SBO); a K step of 16 elements is +32 B
-            const uint64_t dah = make_smem_desc(a_hi + k4 * 32, 0, 1024);
-            const uint64_t dbh = make_smem_desc(b_hi + k4 * 32, 0, 1024);
-            umma_f16(d_tmem, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+            umma_f16(d_tmem, da + 2 * k4, db + 2 * k4, idesc, (kb | k4) ? 1u : 0u);
             if (NPROD == 3) {
-              const uint64_t dal = make_smem_desc(a_lo + k4 * 32, 0, 1024);
-              const uint64_t dbl = make_smem_desc(b_lo + k4 * 32, 0, 1024);
-              umma_f16(d_tmem, dah, dbl, idesc, 1u);
-              umma_f16(d_tmem, dal, dbh, idesc, 1u);
+              umma_f16(d_tmem, da + 2 * k4, db + kLoB + 2 * k4, idesc, 1u);
+              umma_f16(d_tmem, da + kLoA + 2 * k4, db + 2 * k4, idesc, 1u);
             }
           }
           umma_commit(empty0 + 8 * s);      // frees this smem stage once the MMAs above have read it
+          if (kb == nk - 1) umma_commit(tfull0 + 8 * buf);      // accumulator complete
         }
-        umma_commit(tfull0 + 8 * buf);      // accumulator complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     using Tr = EpiTraits<Epi>;
     using Aux = typename Tr::Aux;
@@ -388,8 +417,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     int lt = 0;
     for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
       const int m0 = mt * kBM;
-      const uint32_t buf = lt & 1;
-      mbar_wait(tfull0 + 8 * buf, (lt >> 1) & 1);
+      const uint32_t buf = lt % NBUF;
+      mbar_wait(tfull0 + 8 * buf, (lt / NBUF) & 1);
       tc_fence_after();
       const int row0 = m0 + q * 32;
       const int nrows = min(32, M - row0);
@@ -425,7 +454,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, NBUF * BN);
   }
 }
 
@@ -460,7 +489,9 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   g = (g / tiles_n) * tiles_n;                         // ... and a whole number of CTAs per column tile
   if (g < tiles_n) return AVC_E_BADCFG;
   dim3 grid(g);
-  kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi);
+  static int l2pf = -1;       // AVC_NT_L2PF=1: TMA-prefetch the next row tile's A boxes into L2 (measured: no gain)
+  if (l2pf < 0) { const char* e = getenv("AVC_NT_L2PF"); l2pf = (e && atoi(e) == 1) ? 1 : 0; }
+  kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi, l2pf);
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -570,38 +601,38 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
-      constexpr uint32_t idesc1 = make_idesc_bf16(kBM, 16, 1, 1);
-      const uint32_t ones_addr = smem_u32(ones_tile);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % Cfg::STAGES;
-        mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES, a_lo = a_hi + Cfg::A_BYTES;
-        const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
+    // converged warp, one elected lane issues (see the NT kernel)
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 1, 1);
+    constexpr uint32_t idesc1 = make_idesc_bf16(kBM, 16, 1, 1);
+    const uint32_t ones_addr = smem_u32(ones_tile);
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % Cfg::STAGES;
+      mbar_wait(full0 + 8 * s, (kb / Cfg::STAGES) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+        const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES;
+        // MN-major: a K step of 16 p-rows is +2048 B = +128 in the descriptor's start-address field
+        const uint64_t da = make_smem_desc(a_hi, Cfg::BLK, 1024), db = make_smem_desc(b_hi, Cfg::BLK, 1024);
+        const uint64_t dones = make_smem_desc(ones_addr, Cfg::BLK, 1024);
+        constexpr uint64_t kLoA = (uint64_t)(Cfg::A_BYTES >> 4), kLoB = (uint64_t)(Cfg::B_BYTES >> 4);
 #pragma unroll
         for (int k4 = 0; k4 < kBK / 16; ++k4) {
-          const uint64_t dah = make_smem_desc(a_hi + k4 * 2048, Cfg::BLK, 1024);
-          const uint64_t dbh = make_smem_desc(b_hi + k4 * 2048, Cfg::BLK, 1024);
-          umma_f16(tmem_base, dah, dbh, idesc, (kb | k4) ? 1u : 0u);
+          umma_f16(tmem_base, da + 128 * k4, db + 128 * k4, idesc, (kb | k4) ? 1u : 0u);
           if (NPROD == 3) {
-            const uint64_t dal = make_smem_desc(a_lo + k4 * 2048, Cfg::BLK, 1024);
-            const uint64_t dbl = make_smem_desc(b_lo + k4 * 2048, Cfg::BLK, 1024);
-            umma_f16(tmem_base, dah, dbl, idesc, 1u);
-            umma_f16(tmem_base, dal, dbh, idesc, 1u);
+            umma_f16(tmem_base, da + 128 * k4, db + kLoB + 128 * k4, idesc, 1u);
+            umma_f16(tmem_base, da + kLoA + 128 * k4, db + 128 * k4, idesc, 1u);
           }
           if (do_colsum) {      // D2[128 x 16] += A^T . ones : every column of D2 is the column sum of A
-            const uint64_t dones = make_smem_desc(ones_addr, Cfg::BLK, 1024);
-            umma_f16(tmem_base + BN, dah, dones, idesc1, (kb | k4) ? 1u : 0u);
-            if (NPROD == 3) umma_f16(tmem_base + BN, make_smem_desc(a_lo + k4 * 2048, Cfg::BLK, 1024), dones, idesc1, 1u);
+            umma_f16(tmem_base + BN, da + 128 * k4, dones, idesc1, (kb | k4) ? 1u : 0u);
+            if (NPROD == 3) umma_f16(tmem_base + BN, da + kLoA + 128 * k4, dones, idesc1, 1u);
           }
         }
         umma_commit(empty0 + 8 * s);
+        if (kb == nk - 1) umma_commit(tfull);
       }
-      umma_commit(tfull);
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;
     mbar_wait(tfull, 0);
