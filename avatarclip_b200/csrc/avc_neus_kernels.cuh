@@ -772,7 +772,8 @@ struct EpiChain {
       } else {
         if (c < Npp) { if (QTprev) QTprev[(size_t)row * Npp + c] = 0.f; split16_put(q16, (size_t)row, c, 0.f); }
         int e = c - Nprev;
-        if (e < E) GE[(size_t)row * EP + e] += v[i] * kSqrtHalf;
+        // exclusive element, result unused: compiles to a fire-and-forget RED instead of a dependent load + store
+        if (e < E) atomicAdd(GE + (size_t)row * EP + e, v[i] * kSqrtHalf);
       }
     }
   }
@@ -884,13 +885,13 @@ struct EpiChainBwd {
   // qt_l comes from its fp32 copy QT or, when QT is NULL (tcgen05 engine), from the split hi + lo
   struct Aux { float4 d; uint4 q; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
-    const size_t o = (size_t)row * Np + clamp_group(col, N);
+    const size_t o = (size_t)row * Np + clamp_group(col, Np);
     Aux x;
     x.d = *reinterpret_cast<const float4*>(D1 + o);
     if (QT) {
       x.q = *reinterpret_cast<const uint4*>(QT + o);
     } else {
-      const size_t o16 = (size_t)row * qt16.ld + clamp_group(col, N);
+      const size_t o16 = (size_t)row * qt16.ld + clamp_group(col, Np);
       const uint2 h = *reinterpret_cast<const uint2*>(qt16.hi + o16), l = *reinterpret_cast<const uint2*>(qt16.lo + o16);
       x.q = make_uint4(h.x, h.y, l.x, l.y);
     }
@@ -901,7 +902,9 @@ struct EpiChainBwd {
   }
   __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    if (col + 3 < N) {
+    // whole group inside the PADDED width: the padding of the sp' stash and of qt is zero (EpiValue / EpiChain), so the
+    // vector path yields the zeros the padding of ubar / zbar must hold
+    if (col + 3 < Np) {
       const size_t o = (size_t)row * Np + col;
       const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w};
       float qq[4];
@@ -944,13 +947,13 @@ struct EpiDgrad {
   float sdf_inv_scale; Split16 z16; int store_f32;     // store_f32 = 0: only the split of the new zbar_prev is kept
   struct Aux { float4 d, zb; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
-    const size_t o = (size_t)row * Npp + clamp_group(col, Nprev);
+    const size_t o = (size_t)row * Npp + clamp_group(col, Npp);
     return {*reinterpret_cast<const float4*>(D1prev + o), *reinterpret_cast<const float4*>(ZBARprev + o)};
   }
   __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
     float sb = sdfbar ? sdfbar[row] * sdf_inv_scale : 0.f;
-    if (col + 3 < Nprev) {
+    if (col + 3 < Npp) {      // padded width: sp' stash and zbar padding are zero, so is the result there
       const size_t o = (size_t)row * Npp + col;
       const float dd[4] = {x.d.x, x.d.y, x.d.z, x.d.w}, zo[4] = {x.zb.x, x.zb.y, x.zb.z, x.zb.w};
       float r[4];
