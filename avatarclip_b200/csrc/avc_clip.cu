@@ -325,10 +325,15 @@ k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict_
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + (size_t)row * Wd;
-  float xv[kLnMax];
+  float xv[kLnMax], gv[kLnMax], bv[kLnMax];      // gamma / beta are fetched with the row, not after the reductions
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMax; ++i) { int c = lane + 32 * i; xv[i] = (c < Wd) ? xr[c] : 0.f; s += xv[i]; }
+  for (int i = 0; i < kLnMax; ++i) {
+    int c = lane + 32 * i;
+    bool ok = c < Wd;
+    xv[i] = ok ? xr[c] : 0.f; gv[i] = ok ? g[c] : 0.f; bv[i] = ok ? b[c] : 0.f;
+    s += xv[i];
+  }
   float mean = warp_sum(s) / (float)Wd;
   float v = 0.f;
 #pragma unroll
@@ -338,7 +343,7 @@ k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict_
   for (int i = 0; i < kLnMax; ++i) {
     int c = lane + 32 * i;
     if (c < Wd) {
-      float yv = (xv[i] - mean) * rstd * g[c] + b[c];
+      float yv = (xv[i] - mean) * rstd * gv[i] + bv[i];
       if (y32) y32[(size_t)row * Wd + c] = yv;
       if (y16) y16[(size_t)row * Wd + c] = __float2half_rn(yv);
       if (save_x) save_x[(size_t)row * Wd + c] = xv[i];

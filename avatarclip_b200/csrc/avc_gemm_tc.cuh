@@ -276,7 +276,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
   // accumulators: NBUF x BN TMEM columns (all 512 for BN = 128), so the TMA/MMA side can run up to NBUF - 1 tiles
   // ahead of the epilogue instead of one
   constexpr int NBUF = (512 / BN) > 4 ? 4 : (512 / BN);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 2 * NBUF + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * Cfg::STAGES + 2 * NBUF + kResK);
   float* epi_stage = (float*)(smem + kOpBytes + 256);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bres_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -298,7 +298,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     if (NPROD == 3) { tma_prefetch_desc(&mapAlo); tma_prefetch_desc(&mapBlo); }
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int b2 = 0; b2 < NBUF; ++b2) { mbar_init(tfull0 + 8 * b2, 1); mbar_init(tempty0 + 8 * b2, EW); }
-    mbar_init(bfull, 1);
+    for (int kb = 0; kb < kResK; ++kb) mbar_init(bfull + 8 * kb, 1);     // one per k-block of the resident B panel
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), NBUF * BN);
@@ -309,14 +309,6 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      if (RESB) {     // the B panel of this CTA's column tile, once
-        mbar_expect_tx(bfull, (uint32_t)(nk * Cfg::NOP * Cfg::B_BYTES));
-        for (int kb = 0; kb < nk; ++kb) {
-          const uint32_t dst = bres_base + kb * (Cfg::NOP * Cfg::B_BYTES);
-          tma_load_2d(dst, &mapBhi, kb * kBK, n0, bfull);
-          if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull);
-        }
-      }
       // Optional (AVC_NT_L2PF=1, kernel argument l2pf): pull the A boxes of the NEXT row tile into L2 while this one is
       // loaded, so that the ring's loads see L2 latency.  Measured on B200: no change (2.77 vs 2.76 ms per step), i.e.
       // the depth of the A ring is not what bounds these launches; off by default.
@@ -333,6 +325,12 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           if (pf) {
             tma_prefetch_2d(&mapAhi, kb * kBK, m0 + m_stride * kBM);
             if (NPROD == 3) tma_prefetch_2d(&mapAlo, kb * kBK, m0 + m_stride * kBM);
+          }
+          if (RESB && mt == m_first) {     // first row tile: k-block kb of the resident B panel goes out just before A's
+            const uint32_t dst = bres_base + kb * (Cfg::NOP * Cfg::B_BYTES);
+            mbar_expect_tx(bfull + 8 * kb, (uint32_t)(Cfg::NOP * Cfg::B_BYTES));
+            tma_load_2d(dst, &mapBhi, kb * kBK, n0, bfull + 8 * kb);
+            if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull + 8 * kb);
           }
           const int s = it % Cfg::STAGES;
           mbar_wait(empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
@@ -353,7 +351,6 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     // issue rate matters: 48 MMAs of 64 tensor-cycles each per 128 x 128 x 256 tile leave ~64 cycles per instruction,
     // so the descriptors are derived by adding constants to one base per operand and k-block.
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
-    if (RESB) { mbar_wait(bfull, 0); tc_fence_after(); }
     int it = 0, lt = 0;
     for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
       const uint32_t buf = lt % NBUF;
@@ -362,6 +359,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
       const uint32_t d_tmem = tmem_base + buf * BN;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % Cfg::STAGES;
+        if (RESB && lt == 0) mbar_wait(bfull + 8 * kb, 0);      // this k-block of the B panel has landed (first tile only)
         mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
         tc_fence_after();
         if (elect_one_sync()) {

@@ -67,3 +67,25 @@ def test_two_rank_view_sharding_equals_gradient_accumulation(tmp_path):
     want = sum(_flat_grad(orc, make_view(ad.view_index(0, r, 2), n_rays=40, H=48, W=48, seed=0)) for r in range(2)) / 2
     assert torch.allclose(got, want, rtol=1e-5, atol=1e-7)
     assert ad.view_index(3, 1, 4) == 13
+
+
+def test_host_view_packs_into_one_buffer():
+    """HostView.pack(): every tensor becomes a view of one contiguous buffer (a step's inputs are a single H2D copy) and
+    the layout is a pure function of the shapes, so views of equal shape can refresh the same device buffer."""
+    from avatarclip_b200.workload import VIEW_FIELDS, make_view
+    a = make_view(0, n_rays=40, H=16, W=16, seed=3, bg_choice=1)
+    b = make_view(5, n_rays=40, H=16, W=16, seed=3, bg_choice=2)
+    assert a.flat is not None and a.flat.dtype == torch.uint8
+    la, ta = a.layout()
+    lb, tb = b.layout()
+    assert la == lb and ta == tb == a.flat.numel()
+    base = a.flat.data_ptr()
+    for name, off, shape, dtype, nb in la:
+        t = getattr(a, name)
+        assert t.data_ptr() == base + off and off % 256 == 0 and tuple(t.shape) == shape
+    assert a.h2d_bytes() <= ta
+    assert torch.allclose(a.scalars[:3], torch.as_tensor(a.light_dir, dtype=torch.float32))
+    assert abs(float(a.scalars[3]) - a.ambience) < 1e-7
+    c = make_view(0, n_rays=40, H=16, W=16, seed=3, bg_choice=3)          # no background tensors: another layout
+    assert c.layout()[0] != la
+    assert set(n for n, *_ in c.layout()[0]) <= set(VIEW_FIELDS)
