@@ -40,7 +40,8 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 // ------------------------------------------------------------------------------------------------
 // fp16 tensor-core GEMM  C[M,N] = A[M,K] . W[N,K]^T  (mma.sync m16n8k16, fp32 accumulate).
 // CTA: 128 threads, tile 64 x 32, BK = 64, 3-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
-// Epilogue functor: epi(row, col, v0, v1, ksplit_index) for two consecutive columns.
+// Epilogue functor: pre = epi.prefetch(row, col, ksplit_index) before the main loop, then epi(row, col, v0, v1,
+// ksplit_index, pre) for two consecutive columns.
 // ------------------------------------------------------------------------------------------------
 constexpr int GBM = 64, GBN = 32, GBK = 64, GST = 6, GPAD = 8;
 constexpr int G_SMEM = GST * (GBM + GBN) * (GBK + GPAD) * 2;   // 82,944 B of dynamic shared memory
@@ -107,6 +108,16 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
     if (s < nk) issue(s, s);
     cp_async_commit();
   }
+  // epilogue operands (bias, saved pre-activation, row scale) are fetched now, behind the operand stream, instead of as
+  // a dependent load phase after the main loop
+  const int er0 = m0 + warp * 16 + (lane >> 2);
+  float2 epre[4][2];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int col = n0 + t * 8 + (lane & 3) * 2;
+    epre[t][0] = (er0 < M) ? epi.prefetch(er0, col, (int)blockIdx.z) : make_float2(0.f, 0.f);
+    epre[t][1] = (er0 + 8 < M) ? epi.prefetch(er0 + 8, col, (int)blockIdx.z) : make_float2(0.f, 0.f);
+  }
   for (int kt = 0; kt < nk; ++kt) {
     cp_async_wait<GST - 2>();
     __syncthreads();
@@ -145,8 +156,8 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     int col = n0 + t * 8 + (lane & 3) * 2;
-    if (r0 < M) epi(r0, col, acc[t][0], acc[t][1], (int)blockIdx.z);
-    if (r0 + 8 < M) epi(r0 + 8, col, acc[t][2], acc[t][3], (int)blockIdx.z);
+    if (r0 < M) epi(r0, col, acc[t][0], acc[t][1], (int)blockIdx.z, epre[t][0]);
+    if (r0 + 8 < M) epi(r0 + 8, col, acc[t][2], acc[t][3], (int)blockIdx.z, epre[t][1]);
   }
 }
 
@@ -172,7 +183,8 @@ int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw,
 // ---- epilogues -----------------------------------------------------------------------------------
 struct EpiPatch {   // token row b*T + 1 + p  +=  acc   (rows pre-initialised with the positional embedding; split-K)
   float* x; int T, Wd, np;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+  __device__ float2 prefetch(int, int, int) const { return make_float2(0.f, 0.f); }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2) const {
     int b = row / np, p = row - b * np;
     size_t o = ((size_t)b * T + 1 + p) * Wd + col;
     atomicAdd(x + o, v0);
@@ -181,23 +193,27 @@ struct EpiPatch {   // token row b*T + 1 + p  +=  acc   (rows pre-initialised wi
 };
 struct EpiBiasStore {   // out = acc + b
   float* out; int ld; const float* bias;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
-    out[(size_t)row * ld + col] = v0 + bias[col];
-    out[(size_t)row * ld + col + 1] = v1 + bias[col + 1];
+  __device__ float2 prefetch(int, int col, int) const { return make_float2(bias[col], bias[col + 1]); }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
+    out[(size_t)row * ld + col] = v0 + p.x;
+    out[(size_t)row * ld + col + 1] = v1 + p.y;
   }
 };
 struct EpiResidual {    // x += acc (+ bias once): split-K partials meet in fp32 atomics
   float* x; int ld; const float* bias;
-  __device__ void operator()(int row, int col, float v0, float v1, int ks) const {
-    if (ks == 0) { v0 += bias[col]; v1 += bias[col + 1]; }
-    atomicAdd(x + (size_t)row * ld + col, v0);
-    atomicAdd(x + (size_t)row * ld + col + 1, v1);
+  __device__ float2 prefetch(int, int col, int ks) const {
+    return ks == 0 ? make_float2(bias[col], bias[col + 1]) : make_float2(0.f, 0.f);
+  }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
+    atomicAdd(x + (size_t)row * ld + col, v0 + p.x);
+    atomicAdd(x + (size_t)row * ld + col + 1, v1 + p.y);
   }
 };
 struct EpiFc {          // pre = acc + b ; g = QuickGELU(pre) = pre * sigmoid(1.702 pre)
   float* pre; __half* g; int ld; const float* bias;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
-    float p0 = v0 + bias[col], p1 = v1 + bias[col + 1];
+  __device__ float2 prefetch(int, int col, int) const { return make_float2(bias[col], bias[col + 1]); }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
+    float p0 = v0 + p.x, p1 = v1 + p.y;
     size_t o = (size_t)row * ld + col;
     pre[o] = p0; pre[o + 1] = p1;
     *reinterpret_cast<__half2*>(g + o) = __floats2half2_rn(p0 * sigmoidf_acc(1.702f * p0), p1 * sigmoidf_acc(1.702f * p1));
@@ -205,9 +221,12 @@ struct EpiFc {          // pre = acc + b ; g = QuickGELU(pre) = pre * sigmoid(1.
 };
 struct EpiDfc {         // (row-scaled) dpre = acc * QuickGELU'(pre) -> fp16 operand of the next GEMM
   const float* pre; __half* out; int ld;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
+  __device__ float2 prefetch(int row, int col, int) const {
+    return *reinterpret_cast<const float2*>(pre + (size_t)row * ld + col);
+  }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
     size_t o = (size_t)row * ld + col;
-    float p0 = pre[o], p1 = pre[o + 1];
+    float p0 = p.x, p1 = p.y;
     float s0 = sigmoidf_acc(1.702f * p0), s1 = sigmoidf_acc(1.702f * p1);
     float d0 = v0 * (s0 + 1.702f * p0 * s0 * (1.f - s0));
     float d1 = v1 * (s1 + 1.702f * p1 * s1 * (1.f - s1));
@@ -216,16 +235,18 @@ struct EpiDfc {         // (row-scaled) dpre = acc * QuickGELU'(pre) -> fp16 ope
 };
 struct EpiAccumUnscale {  // dst += acc / rowscale   (split-K)
   float* dst; int ld; const float* rowscale;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
-    float inv = 1.0f / rowscale[row];
+  __device__ float2 prefetch(int row, int, int) const { return make_float2(rowscale[row], 0.f); }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
+    float inv = 1.0f / p.x;
     atomicAdd(dst + (size_t)row * ld + col, v0 * inv);
     atomicAdd(dst + (size_t)row * ld + col + 1, v1 * inv);
   }
 };
 struct EpiStoreUnscale {  // dst = acc / rowscale
   float* dst; int ld; const float* rowscale;
-  __device__ void operator()(int row, int col, float v0, float v1, int) const {
-    float inv = 1.0f / rowscale[row];
+  __device__ float2 prefetch(int row, int, int) const { return make_float2(rowscale[row], 0.f); }
+  __device__ void operator()(int row, int col, float v0, float v1, int, float2 p) const {
+    float inv = 1.0f / p.x;
     dst[(size_t)row * ld + col] = v0 * inv;
     dst[(size_t)row * ld + col + 1] = v1 * inv;
   }
@@ -460,12 +481,30 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
   float* S = v + AT * AP;         // [T][AT+1]
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
-    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
-    const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
-    *reinterpret_cast<float4*>(q + t * AP + d) = *reinterpret_cast<const float4*>(r);
-    *reinterpret_cast<float4*>(k + t * AP + d) = *reinterpret_cast<const float4*>(r + Wd);
-    *reinterpret_cast<float4*>(v + t * AP + d) = *reinterpret_cast<const float4*>(r + 2 * Wd);
+  {   // all global loads of the thread first (one latency, not one per loop trip), then the shared-memory stores
+    constexpr int NIT = (AT * (AD / 4) + 511) / 512;
+    float4 rq[NIT], rk[NIT], rv[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * 512;
+      if (i < T * (AD / 4)) {
+        const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
+        const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
+        rq[j] = *reinterpret_cast<const float4*>(r);
+        rk[j] = *reinterpret_cast<const float4*>(r + Wd);
+        rv[j] = *reinterpret_cast<const float4*>(r + 2 * Wd);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * 512;
+      if (i < T * (AD / 4)) {
+        const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
+        *reinterpret_cast<float4*>(q + t * AP + d) = rq[j];
+        *reinterpret_cast<float4*>(k + t * AP + d) = rk[j];
+        *reinterpret_cast<float4*>(v + t * AP + d) = rv[j];
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
@@ -519,14 +558,32 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
   float* dS = Pm + AT * (AT + 1);
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
-    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
-    const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
-    *reinterpret_cast<float4*>(q + t * AP + d) = *reinterpret_cast<const float4*>(r);
-    *reinterpret_cast<float4*>(k + t * AP + d) = *reinterpret_cast<const float4*>(r + Wd);
-    *reinterpret_cast<float4*>(v + t * AP + d) = *reinterpret_cast<const float4*>(r + 2 * Wd);
-    *reinterpret_cast<float4*>(dO_s + t * AP + d) =
-        *reinterpret_cast<const float4*>(dO + ((size_t)b * T + t) * Wd + h * AD + d);
+  {   // all global loads first, then the shared-memory stores (see k_attention)
+    constexpr int NIT = (AT * (AD / 4) + 511) / 512;
+    float4 rq[NIT], rk[NIT], rv[NIT], ro[NIT];
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * 512;
+      if (i < T * (AD / 4)) {
+        const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
+        const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
+        rq[j] = *reinterpret_cast<const float4*>(r);
+        rk[j] = *reinterpret_cast<const float4*>(r + Wd);
+        rv[j] = *reinterpret_cast<const float4*>(r + 2 * Wd);
+        ro[j] = *reinterpret_cast<const float4*>(dO + ((size_t)b * T + t) * Wd + h * AD + d);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NIT; ++j) {
+      const int i = threadIdx.x + j * 512;
+      if (i < T * (AD / 4)) {
+        const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
+        *reinterpret_cast<float4*>(q + t * AP + d) = rq[j];
+        *reinterpret_cast<float4*>(k + t * AP + d) = rk[j];
+        *reinterpret_cast<float4*>(v + t * AP + d) = rv[j];
+        *reinterpret_cast<float4*>(dO_s + t * AP + d) = ro[j];
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
