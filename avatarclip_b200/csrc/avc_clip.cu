@@ -393,7 +393,6 @@ k_layernorm_bwd(const float* __restrict__ x, float* __restrict__ dy, int M, int 
     bool ok = c < Wd;
     xv[i] = ok ? xr[c] : 0.f;
     dg[i] = ok ? dr[c] * g[c] : 0.f;
-    if (ok && zero_dy) dr[c] = 0.f;      // dy is the split-K accumulator of the next GEMM: hand it back cleared
     ov[i] = (ok && accumulate) ? o[c] : 0.f;
     s += xv[i];
   }
@@ -418,6 +417,7 @@ k_layernorm_bwd(const float* __restrict__ x, float* __restrict__ dy, int M, int 
       float r = ov[i] + rstd * (dg[i] - a - xh * bq);
       ov[i] = r;
       o[c] = r;
+      if (zero_dy) dr[c] = 0.f;          // dy is the split-K accumulator of the next GEMM: hand it back cleared
       mx = fmaxf(mx, fabsf(r));
     }
   }
@@ -445,8 +445,24 @@ k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __h
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const float* s = src + (size_t)(row_map ? row_map[row] : row) * ld_src;
+  // Rows up to 32 * 4 * kRsMax = 2304 floats (3 x 768, the widest operand) are held in registers: ONE batch of
+  // independent 16-byte loads instead of a loop of dependent round trips, and no second pass over memory.
+  constexpr int kRsMax = 18;
+  const bool cached = (N <= 128 * kRsMax) && (N % 4 == 0) && (ld_src % 4 == 0);
+  float4 rv[kRsMax];
   float mx = 0.f;
-  for (int c = lane; c < N; c += 32) mx = fmaxf(mx, fabsf(s[c]));
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kRsMax; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      rv[i] = (c < N) ? *reinterpret_cast<const float4*>(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kRsMax; ++i)
+      mx = fmaxf(mx, fmaxf(fmaxf(fabsf(rv[i].x), fabsf(rv[i].y)), fmaxf(fabsf(rv[i].z), fabsf(rv[i].w))));
+  } else {
+    for (int c = lane; c < N; c += 32) mx = fmaxf(mx, fabsf(s[c]));
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sc = 1.f;
@@ -455,7 +471,20 @@ k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __h
     frexpf(mx, &e);               // mx = m * 2^e, m in [0.5, 1)
     sc = ldexpf(1.f, 1 - e);      // mx * sc in [1, 2)
   }
-  for (int c = lane; c < N; c += 32) dst[(size_t)row * N + c] = __float2half_rn(s[c] * sc);
+  if (cached) {
+#pragma unroll
+    for (int i = 0; i < kRsMax; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < N) {
+        __half2 h0 = __floats2half2_rn(rv[i].x * sc, rv[i].y * sc), h1 = __floats2half2_rn(rv[i].z * sc, rv[i].w * sc);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(dst + (size_t)row * N + c) = pk;
+      }
+    }
+  } else {
+    for (int c = lane; c < N; c += 32) dst[(size_t)row * N + c] = __float2half_rn(s[c] * sc);
+  }
   if (lane == 0) scale[row] = sc;
 }
 

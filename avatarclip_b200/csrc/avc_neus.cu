@@ -295,7 +295,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
     const LinDim& c0 = pl.col[0];
     // tcgen05 engine: the fp32 copy of a hidden colour activation is only read by the heads (layer Lc)
     const bool tc1 = pl.cfg.engine == 1;
-    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0x, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc, w.ch16[1]};
+    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0xT, pl.Hc, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc, w.ch16[1]};
     AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
     for (int l = 1; l < pl.Lc; ++l) {
       const LinDim& c = pl.col[l];

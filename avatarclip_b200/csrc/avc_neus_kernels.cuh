@@ -798,24 +798,26 @@ struct EpiGe {
 };
 
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
+// WxT = the 6 point / normal columns of W0, transposed: [6][ldt] (one float4 per input for 4 output columns)
 struct EpiColor0 {
-  const float* bias; const float* cin; const float* Wx; float* OUT; int ldo; Split16 o16;
+  const float* bias; const float* cin; const float* WxT; int ldt; float* OUT; int ldo; Split16 o16;
   struct Aux { float4 c0, c1; };
   __device__ __forceinline__ Aux prefetch(int row, int) const {
     return {*reinterpret_cast<const float4*>(cin + (size_t)row * 8), *reinterpret_cast<const float4*>(cin + (size_t)row * 8 + 4)};
   }
   __device__ __forceinline__ void operator()(int row, int col, float4 a, const Aux& x) const {
     AVC_EPI_UNPACK;
-    const float4 c0 = x.c0, c1 = x.c1;
+    const float cj[6] = {x.c0.x, x.c0.y, x.c0.z, x.c0.w, x.c1.x, x.c1.y};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 w0 = *reinterpret_cast<const float4*>(Wx + (size_t)(col + i) * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(Wx + (size_t)(col + i) * 8 + 4);
-      float z = v[i] + bias[col + i];
-      z = fmaf(c0.x, w0.x, z); z = fmaf(c0.y, w0.y, z); z = fmaf(c0.z, w0.z, z);
-      z = fmaf(c0.w, w0.w, z); z = fmaf(c1.x, w1.x, z); z = fmaf(c1.y, w1.y, z);
-      v[i] = fmaxf(z, 0.f);
+    for (int i = 0; i < 4; ++i) v[i] += bias[col + i];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 w = *reinterpret_cast<const float4*>(WxT + (size_t)j * ldt + col);
+      v[0] = fmaf(cj[j], w.x, v[0]); v[1] = fmaf(cj[j], w.y, v[1]);
+      v[2] = fmaf(cj[j], w.z, v[2]); v[3] = fmaf(cj[j], w.w, v[3]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
     if (OUT) *reinterpret_cast<float4*>(OUT + (size_t)row * ldo + col) = make_float4(v[0], v[1], v[2], v[3]);
     split16_put4(o16, (size_t)row, col, v);
   }

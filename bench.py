@@ -395,6 +395,7 @@ def subsample_view(hv, n):
     m = torch.zeros_like(hv.in_mask)
     m[v.pix.long()] = 1
     v.in_mask = m
+    v.flat = None          # the tensors above are no longer views of the packed buffer
     return v
 
 
