@@ -31,11 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 METRIC = "appearance-optim steps/sec (512 rays x 128 samples, CLIP loss)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures under profiles/
-# (r1_ncu_full_gemm_tc_*.txt); None where no capture of a full-size launch exists yet
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r1_ncu_full_*.txt); for the NT
-# kernel: mean over the 33 full-size (65,536-point) launches of one step
-TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 138.8e6, "avc::tc::gemm_tc_nt_kernel": None}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu (profiles/r1_launches_tcgen05_engine.txt): mean over the
+# 73 NT / 21 TN launches of one step (NT: 7.99 GB per step; the launches of the fine pass move 87-350 MB each)
+TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 128.6e6, "avc::tc::gemm_tc_nt_kernel": 109.4e6}
 N_RAYS, CANVAS = 512, 224
 SDF_KW = dict(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
               geometric_init=True, weight_norm=True)
