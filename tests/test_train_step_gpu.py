@@ -10,7 +10,7 @@ from oracle.train_step import OracleTrainer
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, n_rays, H, bg_choice, seed=0):
+def _setup(case, n_rays, H, bg_choice, seed=0, engine=0):
     from avatarclip_b200.clip_vit import ClipImageTower
     from avatarclip_b200.trainer import AppearanceTrainer, DeviceView
     from avatarclip_b200.workload import make_view
@@ -19,7 +19,7 @@ def _setup(case, n_rays, H, bg_choice, seed=0):
     sp, cp = U.synth_state(sdf_kw, col_kw, seed)
     clip_sd = cv.random_vit_state(seed=seed)
     text = torch.randn(2, 512, generator=torch.Generator().manual_seed(seed + 5))
-    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda")
+    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda", engine=engine)
     tower = ClipImageTower(clip_sd, device="cuda")
     tr = AppearanceTrainer(ren, tower, text, lr=5e-4)
     orc = OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text, lr=5e-4)
@@ -106,3 +106,31 @@ def test_graph_replay_matches_eager_steps():
     dv.upload(hv2)
     b = tr.replay(dv, lr=0.0).item()
     assert a != b
+
+
+def test_fused_step_tcgen05_engine_matches_oracle():
+    """The fused step with the tcgen05 engine (what bench.py runs): loss and flat gradient against the CPU oracle step on
+    the shipped-size networks (widths are multiples of 8, as engine 1 requires)."""
+    tr, orc, hv, dv, mods = _setup("shipped", 96, 80, 3, engine=1)
+    grad = tr.forward_backward(dv).clone()
+    loss_p = tr.loss_value().item()
+    total, aux = orc.loss(hv)
+    params = [v for _, v in orc.named_params()]
+    gs = torch.autograd.grad(total, params, allow_unused=True)
+    loss_o = total.item()
+    print(f"engine 1: loss product {loss_p:.6f} oracle {loss_o:.6f}")
+    assert abs(loss_p - loss_o) / abs(loss_o) < 1e-3
+    named = {}
+    for (p, o, m) in tr.fp.slots:
+        for pre, mod in (("sdf.", mods[0]), ("col.", mods[1]), ("var.", mods[2])):
+            for k, q in mod.named_parameters():
+                if q is p:
+                    named[pre + k] = grad[o:o + m].view(p.shape).cpu()
+    diff2, ref2 = 0.0, 0.0
+    for (k, v), g in zip(orc.named_params(), gs):
+        g = torch.zeros_like(v) if g is None else g
+        diff2 += (named[k] - g).double().pow(2).sum().item()
+        ref2 += g.double().pow(2).sum().item()
+    rel_l2 = (diff2 / ref2) ** 0.5
+    print(f"engine 1: flat-gradient rel-L2 err {rel_l2:.3e}")
+    assert rel_l2 < 2e-2
