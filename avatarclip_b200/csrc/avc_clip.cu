@@ -6,8 +6,9 @@
 // non-linearities' inputs (LayerNorm inputs, q/k/v, the c_fc pre-activation).
 //
 // Shapes: M = B*T token rows (T = 50), width 768.  Every GEMM here has M <= 128*k rows and streams its
-// fp16 weight matrix exactly once: they are weight-bandwidth bound, not FLOP bound, so the tiles are
-// small (64 x 32 per CTA), deep (3-stage cp.async) and split over K where N alone cannot fill the SMs.
+// fp16 weight matrix exactly once: by bytes they are weight-bandwidth bound, in practice latency bound (~200 dependent
+// kernels per step), so the tiles are small (64 x 32 per CTA), deep (6-stage cp.async), split over K where N alone
+// cannot fill the SMs, and every kernel issues all its global loads in one batch.
 #include <cuda_fp16.h>
 
 #include "avc_common.cuh"
@@ -39,7 +40,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 // ------------------------------------------------------------------------------------------------
 // fp16 tensor-core GEMM  C[M,N] = A[M,K] . W[N,K]^T  (mma.sync m16n8k16, fp32 accumulate).
-// CTA: 128 threads, tile 64 x 32, BK = 64, 3-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
+// CTA: 128 threads, tile 64 x 32, BK = 64, 6-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
 // Epilogue functor: pre = epi.prefetch(row, col, ksplit_index) before the main loop, then epi(row, col, v0, v1,
 // ksplit_index, pre) for two consecutive columns.
 // ------------------------------------------------------------------------------------------------

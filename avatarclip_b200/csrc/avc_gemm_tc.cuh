@@ -9,9 +9,11 @@
 //   gemm_tc_nt : C[m,n] = sum_k A[m,k] B[n,k]     A:[M,lda] B:[N,ldb], both K-contiguous (K-major operands)
 //   gemm_tc_tn : C[i,j] += sum_p A[p,i] B[p,j]    reduction over rows (weight gradients; MN-major operands)
 //
-// Kernel shape (both): 192 threads = warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer,
-// warps 2-5 epilogue (TMEM lane quarter = warp_id % 4).  Tile 128 x BN, K step 64 (one 128-byte swizzle atom),
-// multi-stage shared-memory ring with full/empty mbarriers, accumulator hand-off through tcgen05.commit.
+// Kernel shape: warp 0 TMA producer, warp 1 TMEM owner + one elect.sync lane issuing the MMAs, the remaining warps
+// the epilogue (TMEM lane quarter = warp_id % 4).  NT: persistent, 576 threads (16 epilogue warps), tile 128 x 64/128,
+// 4 TMEM accumulator buffers, B panel resident in shared memory when K <= 256.  TN: 320 threads (8 epilogue warps), one
+// tile per CTA, split over the reduction dimension.  K step 64 (one 128-byte swizzle atom), shared-memory ring with
+// full/empty mbarriers, accumulator hand-off through tcgen05.commit.
 #pragma once
 #include <type_traits>
 #include <cuda.h>
@@ -260,9 +262,10 @@ struct EpiTraits<E, std::void_t<typename E::Aux>> {
   static __device__ __forceinline__ void apply(const E& e, int r, int c, float4 a, const Aux& x) { e(r, c, a, x); }
 };
 
-// Persistent: gridDim.x CTAs (<= one per SM) walk the output tiles t = blockIdx.x, +gridDim.x, ...  The accumulator
-// is double buffered in TMEM (2 x BN columns) so the epilogue of tile i runs while the TMA/MMA warps already work
-// on tile i+1:  tfull[b] (MMA -> epilogue, tcgen05.commit)  /  tempty[b] (epilogue -> MMA, one arrive per warp).
+// Persistent: gridDim.x CTAs (<= one per SM, a multiple of the number of column tiles); a CTA keeps one column tile
+// and walks the row tiles m_first, +m_stride, ...  The accumulator is multi-buffered in TMEM (NBUF x BN columns) so
+// the epilogue of tile i runs while the TMA/MMA warps already work on the next tiles:
+// tfull[b] (MMA -> epilogue, tcgen05.commit)  /  tempty[b] (epilogue -> MMA, one arrive per warp).
 template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
