@@ -32,8 +32,18 @@ relative to ``/root/reference/AvatarGen/AppearanceGen``):
                             (``drive.py:51-160``); **parity unpinned** beyond
                             the reference-import check (no SMPL model on disk).
 
-Pinning status: the NeuS half is pinned against the *unmodified reference
-modules imported from /root/reference* (``oracle/pin_against_reference.py``
-generates ``tests/golden/*.pt`` from the reference itself and the CPU tests
-compare the restatement with those files).
+Pinning status:
+* the NeuS half is pinned against the *unmodified reference modules imported
+  from /root/reference* (``oracle/pin_against_reference.py`` generates
+  ``tests/golden/neus_*.pt`` from the reference itself);
+* ``oracle.lbs`` against the reference's ``my_lbs`` run in place
+  (``oracle/pin_lbs.py`` -> ``tests/golden/lbs_small.pt``);
+* ``oracle.loss`` (loss stage main.py:417-534, schedules :571-586, ``lookat`` /
+  ``sphere_coord``, ``gen_rays_pose`` / ``gen_rays_silhouettes`` /
+  ``near_far_from_sphere``) against the reference's own SOURCE LINES, cut out of
+  the files and executed in place (``oracle/pin_loss_stage.py`` ->
+  ``tests/golden/loss_stage.pt``): main.py and models/{utils,dataset}.py do not
+  import here, their arithmetic is plain torch / numpy;
+* the CPU tests compare the restatement with those files on every run.
+Still unpinned: the CLIP tower itself (third-party, weights not on disk).
 """

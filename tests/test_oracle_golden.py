@@ -60,3 +60,60 @@ def test_lbs_restatement_matches_reference_golden():
     v, j = lbs.my_lbs(**g["inputs"])
     assert (v - g["verts"]).abs().max().item() < 1e-6
     assert (j - g["joints"]).abs().max().item() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Loss stage / ray generators: golden vectors written by oracle/pin_loss_stage.py, which EXECUTES the reference's own
+# source lines (main.py:417-534, models/dataset.py:252-293,331-342) in the build container.
+def _loss_golden():
+    return torch.load(os.path.join(GOLDEN, "loss_stage.pt"), map_location="cpu", weights_only=False)
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_loss_stage_restatement_matches_reference_lines(case):
+    from oracle import clip_vit as cv
+    from oracle import loss as ol
+    c = _loss_golden()["cases"][case]
+    H, choice = c["H"], c["choice_i"]
+    igr_w, mask_w, clip_w = c["weights"]
+    leaves = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in c["render_out"].items()}
+    mask = (c["mask"] > 0.5).float() if mask_w > 0.0 else torch.ones_like(c["mask"])          # main.py:407-410
+    st = ol.shading_and_losses(leaves, c["dilated_mask"], H, H, c["true_rgb"], mask, c["light_dir"].float(), c["ambience"],
+                               choice, c["background_rgb"] if choice in (1, 2) else None, igr_w, mask_w)
+    clip_state = cv.random_vit_state(seed=c["clip_seed"])
+    c_tex = cv.clip_cosine(clip_state, st["texture_canvas"], c["text"])
+    c_sh = cv.clip_cosine(clip_state, st["shading_canvas"], c["text"])
+    loss = ol.total_loss(st, c_tex, c_sh, clip_w)
+    ref = c["ref"]
+    got = {"loss": loss, "color_fine_loss": st["color_loss"], "mask_loss": st["mask_loss"], "eikonal_loss": st["eikonal_loss"],
+           "psnr": st["psnr"], "cosine": c_tex, "cosine_shading": c_sh,
+           "texture_shading": st["texture_canvas"].reshape(-1, 3), "rand_shading_rgb": st["shading_canvas"].reshape(-1, 3)}
+    for k, v in got.items():
+        assert _rel(v.detach(), ref[k]) < 5e-6, k
+    names = ["color_fine", "extra_color_fine", "gradients", "weights", "weight_sum", "gradient_error"]
+    grads = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)
+    for k, g in zip(names, grads):
+        g = torch.zeros_like(leaves[k]) if g is None else g
+        assert _rel(g, c["ref_grads"][k]) < 5e-5, k
+
+
+def test_ray_generators_match_reference_lines():
+    import numpy as np
+    from oracle import loss as ol
+    from oracle import neus as on
+    r = _loss_golden()["rays"]
+    Wc = r["canvas"]
+    o_all, v_all = ol.pinhole_rays(r["pose"], Wc, Wc)
+    dm = r["dilated_mask"]
+    assert int(dm.sum()) == r["rays_o"].shape[0] <= r["max_ray_num"] * 1.05
+    assert _rel(v_all[dm], r["rays_d"]) < 1e-6 and _rel(o_all[dm], r["rays_o"]) == 0.0
+    near, far = on.near_far_from_sphere(r["rays_o"], r["rays_d"])
+    assert _rel(near, r["near"]) < 1e-6 and _rel(far, r["far"]) < 1e-6
+    # the synthetic workload generator follows the same formulas (avatarclip_b200/workload.py cites dataset.py:259-268)
+    from avatarclip_b200.workload import lookat
+    assert np.allclose(lookat((0.4, 0.1, 1.5), (0.0, 0.0, 0.0)), ol.lookat((0.4, 0.1, 1.5), (0.0, 0.0, 0.0)))
