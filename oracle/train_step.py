@@ -21,8 +21,9 @@ class OracleTrainer:
                  sdf_state: Dict[str, torch.Tensor], col_state: Dict[str, torch.Tensor], variance: float,
                  clip_state: Dict[str, torch.Tensor], text_emb: torch.Tensor, lr: float = 5e-4,
                  igr_weight: float = 0.1, mask_weight: float = 0.5, clip_weight: float = 1.0,
-                 dtype=torch.float32):
+                 dtype=torch.float32, clip_conf: clip_vit.ViTConf = None):
         self.sconf, self.cconf, self.rconf = sconf, cconf, rconf
+        self.clip_conf = clip_conf if clip_conf is not None else clip_vit.ViTConf()
         self.dtype = dtype
         self.sp = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in sdf_state.items()}
         self.cp = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in col_state.items()}
@@ -60,8 +61,8 @@ class OracleTrainer:
                                          torch.as_tensor(view.light_dir, dtype=dt), view.ambience,
                                          background_choice=view.bg_choice, background_rgb=cbg,
                                          igr_weight=igr, mask_weight=mw)
-        cos_t = clip_vit.clip_cosine(self.clip_state, stage["texture_canvas"], self.text[0])
-        cos_s = clip_vit.clip_cosine(self.clip_state, stage["shading_canvas"], self.text[1])
+        cos_t = clip_vit.clip_cosine(self.clip_state, stage["texture_canvas"], self.text[0], self.clip_conf)
+        cos_s = clip_vit.clip_cosine(self.clip_state, stage["shading_canvas"], self.text[1], self.clip_conf)
         total = oloss.total_loss(stage, cos_t, cos_s, cw)
         return total, {"out": out, "stage": stage, "cos": torch.stack([cos_t, cos_s])}
 

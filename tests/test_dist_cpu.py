@@ -23,12 +23,7 @@ def _tiny_world():
     vconf = cv.ViTConf(image_size=64, patch=32, width=64, layers=2, heads=1, mlp=128, out_dim=32)
     clip_sd = cv.random_vit_state(vconf, seed=0)
     text = torch.randn(2, 32, generator=torch.Generator().manual_seed(1))
-    orc = OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text)
-    # route the oracle's CLIP calls through the tiny tower
-    import oracle.clip_vit as ocv
-    orig = ocv.clip_cosine
-    ocv.clip_cosine = lambda sd, canvas, t, conf=vconf: orig(sd, canvas, t, vconf)
-    return orc
+    return OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text, clip_conf=vconf)     # a tiny CLIP tower
 
 
 def _flat_grad(orc, view):
