@@ -12,6 +12,21 @@ import torch
 from . import _lib
 
 
+def silhouette_canvas(mask: torch.Tensor, max_ray_num: int, full: int = 256):
+    """Host part of ``gen_rays_silhouettes`` (dataset.py:253-258, 269-271): dilate the template silhouette 10 times with
+    the full 3 x 3 structure (``ndimage.generate_binary_structure(2, 2)``), pick the square canvas whose masked pixel
+    count is about ``max_ray_num`` (never above ``full``), and resize the dilated mask to it (nearest, as
+    ``F.interpolate``'s default).  ``mask``: [full, full], non-zero = inside.  Returns (canvas, bool [canvas, canvas]).
+    Ten 3 x 3 max-pools are the ten binary dilations (outside the image counts as background in both)."""
+    m = (torch.as_tensor(mask) != 0).float().reshape(1, 1, full, full)
+    for _ in range(10):
+        m = torch.nn.functional.max_pool2d(m, kernel_size=3, stride=1, padding=1)
+    current_ratio = float(m.sum()) / float(full * full)
+    canvas = min(full, int(math.sqrt(max_ray_num / current_ratio)))
+    resized = torch.nn.functional.interpolate(m, size=(canvas, canvas)).reshape(canvas, canvas)
+    return canvas, resized > 0
+
+
 class RayGenerator:
     def __init__(self, H: int = 256, W: int = 256, camera_angle_x: float = math.pi / 3, device="cuda"):
         self.H, self.W = int(H), int(W)
@@ -46,3 +61,13 @@ class RayGenerator:
         pix = torch.nonzero(dilated_mask.reshape(-1).to(self.device), as_tuple=False).reshape(-1).to(torch.int32)
         ro, rd, near, far = self._call(pose, canvas, canvas, pix)
         return ro, rd, near, far, pix
+
+    def gen_rays_silhouettes(self, pose, max_ray_num: int, mask: torch.Tensor):
+        """dataset.py:252-275: rays of the dilated-silhouette pixels on a canvas sized for ~max_ray_num rays.
+        Returns (rays_o [R,3], rays_d [R,3], W, dilated_mask bool [W,W]) like the reference, plus near / far / pix."""
+        if float((torch.as_tensor(mask) != 0).sum()) == 0:            # :253-254
+            ro, rd, near, far = self.gen_rays_pose(pose, resolution_level=4)
+            return ro, rd, ro.shape[1], None, near, far, None
+        canvas, dm = silhouette_canvas(mask, max_ray_num, self.H)
+        ro, rd, near, far, pix = self.gen_rays_pixels(pose, canvas, dm)
+        return ro, rd, canvas, dm, near, far, pix

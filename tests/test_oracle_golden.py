@@ -117,3 +117,17 @@ def test_ray_generators_match_reference_lines():
     # the synthetic workload generator follows the same formulas (avatarclip_b200/workload.py cites dataset.py:259-268)
     from avatarclip_b200.workload import lookat
     assert np.allclose(lookat((0.4, 0.1, 1.5), (0.0, 0.0, 0.0)), ol.lookat((0.4, 0.1, 1.5), (0.0, 0.0, 0.0)))
+
+
+def test_silhouette_canvas_host_logic_matches_reference_lines():
+    """avatarclip_b200.dataset.silhouette_canvas (dilation x10, canvas sizing, nearest resize) against what the
+    reference's gen_rays_silhouettes produced for the same silhouette (golden written by oracle/pin_loss_stage.py)."""
+    import numpy as np
+    from avatarclip_b200.dataset import silhouette_canvas
+    r = _loss_golden()["rays"]
+    cy, cx = r["sil_center"]
+    yy, xx = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    sil = (((yy - cy) ** 2 + (xx - cx) ** 2) < r["sil_radius"] ** 2).astype(np.float32)
+    canvas, dm = silhouette_canvas(torch.from_numpy(sil), r["max_ray_num"])
+    assert canvas == r["canvas"]
+    assert torch.equal(dm, r["dilated_mask"])
