@@ -166,7 +166,7 @@ k_shade_bwd(avc_loss_inputs in, const float* __restrict__ d_canvases, const floa
   for (int c = 0; c < 3; ++c) {
     float ex = in.extra_color_fine[(size_t)r * 3 + c];
     float prod = ex * s.shade2;
-    float inr = (prod > 0.f && prod < 1.f) ? 1.f : 0.f;                // clamp(0,1) backward
+    float inr = (prod >= 0.f && prod <= 1.f) ? 1.f : 0.f;              // clamp(0,1) backward: inclusive, like torch
     dex[c] = dt[c] * inr * s.shade2;
     if (!s.low) d_shade += dt[c] * inr * ex;                           // shade2 = shade unless low
     if (s.low) dex[c] += ds[c]; else d_shade += ds[c];                 // rand_shading_rgb
@@ -175,7 +175,7 @@ k_shade_bwd(avc_loss_inputs in, const float* __restrict__ d_canvases, const floa
     dcol[c] = sg * m / mask_sum;
   }
   // shade = amb + (1-amb) * clamp(dot, 0, 1) ; dot = nh . lh ; nh = n / (|n| + 1e-7)
-  float d_dot = (!s.nan_ && s.dot > 0.f && s.dot < 1.f) ? d_shade * (1.f - s.amb) : 0.f;
+  float d_dot = (!s.nan_ && s.dot >= 0.f && s.dot <= 1.f) ? d_shade * (1.f - s.amb) : 0.f;
   float dnh[3] = {d_dot * s.lh[0], d_dot * s.lh[1], d_dot * s.lh[2]};
   float ndn = s.n[0] * dnh[0] + s.n[1] * dnh[1] + s.n[2] * dnh[2];
   float re = s.r + 1e-7f;
@@ -196,7 +196,7 @@ k_shade_bwd(avc_loss_inputs in, const float* __restrict__ d_canvases, const floa
 #pragma unroll
     for (int c = 0; c < 3; ++c) { gc[c] = dcol[c]; ge[c] = dex[c]; }
     float dws = 0.f;
-    if (wsum > 1e-3f && wsum < 1.0f - 1e-3f)                            // clip backward
+    if (wsum >= 1e-3f && wsum <= 1.0f - 1e-3f)                          // clip backward (inclusive bounds, like torch)
       dws = (-(m / wsum) + (1.f - m) / (1.f - wsum)) / (float)HW * in.mask_weight;
     const_cast<float*>(cot.weight_sum)[r] = dws;
     if (r == 0) const_cast<float*>(cot.gradient_error)[0] = in.igr_weight;

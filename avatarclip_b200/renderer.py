@@ -138,8 +138,11 @@ class _RenderFn(torch.autograd.Function):
     AccumulateGrad nodes are needed per step."""
 
     @staticmethod
-    def forward(ctx, renderer, hook, rays_o, rays_d, near, far, jitter, background, bg_kind, cos_anneal, z_in):
-        need_grad = hook.requires_grad and torch.is_grad_enabled()
+    def forward(ctx, renderer, hook, rays_o, rays_d, near, far, jitter, background, bg_kind, cos_anneal, z_in,
+                need_grad):
+        # ``need_grad`` is decided by the caller: inside Function.forward grad mode is always off.  With it the forward
+        # stash lives in a workspace OWNED by this autograd node (a later render / sdf_query cannot overwrite it
+        # before backward runs, e.g. when several views are accumulated before one backward()).
         out, ws, chunk = render_forward_raw(renderer, rays_o, rays_d, near, far, jitter, background, bg_kind,
                                             cos_anneal, z_in, keep_ws=need_grad)
         ctx.renderer, ctx.out, ctx.ws, ctx.chunk = renderer, out, ws, chunk
@@ -162,7 +165,8 @@ class _RenderFn(torch.autograd.Function):
         for p, view in zip(fp.params(), fp.grad_views(grad)):
             if p.requires_grad:
                 p.grad = view if p.grad is None else p.grad + view
-        return (None,) * 11
+        ctx.ws = ctx.out = None                      # release the node-owned stash as soon as it was consumed
+        return (None,) * 12
 
 
 class NeuSRenderer:
@@ -269,7 +273,9 @@ class NeuSRenderer:
         z_in = self._prep(z_vals, (R, self.n_samples + self.n_importance)) if z_vals is not None else None
         hook = self._hook if self._hook.device == dev else self._make_hook(dev)
         hook.requires_grad_(any(p.requires_grad for p in fp.params()))
-        outs = _RenderFn.apply(self, hook, rays_o, rays_d, near_t, far_t, jit, bg, bg_kind, float(cos_anneal_ratio), z_in)
+        need_grad = bool(torch.is_grad_enabled() and hook.requires_grad)
+        outs = _RenderFn.apply(self, hook, rays_o, rays_d, near_t, far_t, jit, bg, bg_kind, float(cos_anneal_ratio), z_in,
+                               need_grad)
         ret = dict(zip(_OUT_KEYS, outs[:len(_OUT_KEYS)]))
         ret["z_vals"] = outs[-1]
         return ret

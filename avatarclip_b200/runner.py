@@ -71,6 +71,7 @@ class Runner:
         self.trainer = None
         self.clip_tower = None
         self.encoded_text = None
+        self._pending_optimizer_state = None
         pretrain = c.get_string("train.pretrain", default=None)
         if pretrain is not None and os.path.exists(pretrain):
             logging.info("Load pretrain: %s", pretrain)
@@ -120,8 +121,12 @@ class Runner:
                 raise RuntimeError("call init_clip() first (main.py:970-972)")
             self.trainer = AppearanceTrainer(self.renderer, self.clip_tower, self.encoded_text, lr=self.learning_rate,
                                              igr_weight=self.igr_weight, mask_weight=self.mask_weight,
-                                             clip_weight=self.clip_weight or 1.0, device=self.device)
+                                             clip_weight=1.0 if self.clip_weight is None else self.clip_weight,
+                                             device=self.device)
             self.trainer.iter_step = self.iter_step
+            if self._pending_optimizer_state is not None:      # checkpoint loaded before init_clip() (the CLI order)
+                self._load_optimizer_state_dict(self._pending_optimizer_state)
+                self._pending_optimizer_state = None
         return self.trainer
 
     # ------------------------------------------------------------------ train_clip (main.py:337-566)
@@ -175,9 +180,15 @@ class Runner:
         return {"state": state, "param_groups": [group]}
 
     def _load_optimizer_state_dict(self, sd):
-        tr = self._ensure_trainer() if self.clip_tower is not None else None
-        if tr is None or not sd.get("state"):
+        """optimizer.load_state_dict of main.py:606 for the fused Adam: per-parameter moments -> the flat moment vectors.
+        When the trainer does not exist yet (``Runner(..., is_continue=True)`` runs before ``init_clip``, main.py:963-972)
+        the state is kept and applied as soon as the trainer is built."""
+        if not sd or not sd.get("state"):
             return
+        if self.trainer is None:
+            self._pending_optimizer_state = sd
+            return
+        tr = self.trainer
         params = list(self.sdf_network.parameters()) + list(self.deviation_network.parameters()) + \
             list(self.color_network.parameters())
         slot = {id(p): (o, m) for p, o, m in tr.fp.slots}

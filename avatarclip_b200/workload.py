@@ -150,3 +150,83 @@ def make_view(index: int, n_rays: int = 512, H: int = 224, W: int = 224, seed: i
                   torch.from_numpy(dm.reshape(-1).astype(np.uint8)), true_rgb, mask, ray_bg, canvas_bg, bg_choice,
                   light.astype(np.float32), float(rng.uniform(0, 0.2)), H, W)
     return hv.pack(pin=pin)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Synthetic weights (seeded) for measurements: neither the real ViT-B-32.pt nor a trained B2-sized NeuS exists on disk
+# ------------------------------------------------------------------------------------------------------------------
+B2_SDF_KW = dict(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                 geometric_init=True, weight_norm=True)
+B2_COL_KW = dict(d_feature=256, mode="no_view_dir", d_in=6, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
+                 multires_view=0, squeeze_out=True, extra_color=True)
+B2_REN_KW = dict(n_samples=64, n_importance=64, n_outside=0, up_sample_steps=4, perturb=1.0, extra_color=True)
+# the networks of every shipped conf (confs/examples/*.conf; pretrained_models/zero_beta_stand_pose.pth)
+S_SDF_KW = dict(B2_SDF_KW, n_layers=4)
+S_COL_KW = dict(B2_COL_KW, n_layers=2)
+S_REN_KW = dict(B2_REN_KW, n_samples=32, n_importance=32)
+
+
+def synth_states(sdf_kw: dict, col_kw: dict, seed: int = 0, tame: bool = True):
+    """(sdf_state, col_state): the product modules' own constructors (geometric init of models/fields.py:45-63, bit
+    identical to the reference under the same torch seed) run under ``torch.manual_seed(seed)``.  ``tame`` damps the raw
+    sin/cos columns when the skip concat feeds the LAST linear so that the field stays SDF-like (DESIGN.md "parity
+    definition") and perturbs every direction matrix a little (so no gradient is exactly zero)."""
+    from .fields import RenderingNetwork, SDFNetwork
+    with torch.random.fork_rng(devices=[]):
+        torch.manual_seed(seed)
+        sdf = SDFNetwork(**sdf_kw)
+        col = RenderingNetwork(**col_kw)
+        sp = {k: v.detach().clone() for k, v in sdf.state_dict().items()}
+        cp = {k: v.detach().clone() for k, v in col.state_dict().items()}
+        if tame:
+            L = sdf_kw["n_layers"]
+            d_enc = 3 * (1 + 2 * sdf_kw["multires"])
+            if L in tuple(sdf_kw["skip_in"]):
+                sp[f"lin{L}.weight_v"][:, -(d_enc - 3):] *= 0.02
+                sp[f"lin{L}.weight_g"] = sp[f"lin{L}.weight_v"].norm(dim=1, keepdim=True)
+            for k in sp:
+                if k.endswith("weight_v"):
+                    sp[k] = sp[k] + 0.01 * torch.randn(sp[k].shape)
+    return sp, cp
+
+
+def random_vit_state(seed: int = 0, width: int = 768, layers: int = 12, patch: int = 32, tokens: int = 50,
+                     mlp: int = 3072, out_dim: int = 512):
+    """Seeded random CLIP ViT-B/32 visual state dict (openai/CLIP key names, ``visual.`` prefix stripped) with the
+    initialisation scales of openai/CLIP, values rounded to fp16 (``clip.load`` keeps fp16 weights on CUDA)."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=1.0: torch.randn(*s, generator=g) * std
+    W = width
+    sd = {"conv1.weight": rn(W, 3, patch, patch, std=(3 * patch * patch) ** -0.5),
+          "class_embedding": rn(W, std=W ** -0.5), "positional_embedding": rn(tokens, W, std=W ** -0.5)}
+    for name in ("ln_pre", "ln_post"):
+        sd[f"{name}.weight"] = 1.0 + 0.05 * rn(W)
+        sd[f"{name}.bias"] = 0.05 * rn(W)
+    proj_std, attn_std, fc_std = (W ** -0.5) * ((2 * layers) ** -0.5), W ** -0.5, (2 * W) ** -0.5
+    for i in range(layers):
+        p = f"transformer.resblocks.{i}."
+        for ln in ("ln_1", "ln_2"):
+            sd[p + ln + ".weight"] = 1.0 + 0.05 * rn(W)
+            sd[p + ln + ".bias"] = 0.05 * rn(W)
+        sd[p + "attn.in_proj_weight"] = rn(3 * W, W, std=attn_std)
+        sd[p + "attn.in_proj_bias"] = 0.02 * rn(3 * W)
+        sd[p + "attn.out_proj.weight"] = rn(W, W, std=proj_std)
+        sd[p + "attn.out_proj.bias"] = 0.02 * rn(W)
+        sd[p + "mlp.c_fc.weight"] = rn(mlp, W, std=fc_std)
+        sd[p + "mlp.c_fc.bias"] = 0.02 * rn(mlp)
+        sd[p + "mlp.c_proj.weight"] = rn(W, mlp, std=proj_std)
+        sd[p + "mlp.c_proj.bias"] = 0.02 * rn(W)
+    sd["proj"] = rn(W, out_dim, std=W ** -0.5)
+    return {k: v.half().float() for k, v in sd.items()}
+
+
+def build_networks(sdf_kw, col_kw, ren_kw, sdf_state, col_state, variance, device, engine: int = 1, chunk: int = 4096):
+    """Product modules + renderer from state dicts -> (sdf, col, var, renderer)."""
+    from .fields import RenderingNetwork, SDFNetwork, SingleVarianceNetwork
+    from .renderer import NeuSRenderer
+    sdf, col, var = SDFNetwork(**sdf_kw), RenderingNetwork(**col_kw), SingleVarianceNetwork(float(variance))
+    sdf.load_state_dict(sdf_state)
+    col.load_state_dict(col_state, strict=False)
+    sdf, col, var = sdf.to(device), col.to(device), var.to(device)
+    ren = NeuSRenderer(None, sdf, var, col, engine=engine, max_rays_per_chunk=chunk, **ren_kw)
+    return sdf, col, var, ren

@@ -52,7 +52,7 @@ def import_reference():
     return ref_fields, ref_renderer
 
 
-def frontal_rays(n_side: int, eye=(0.0, 0.0, 2.0), fov=np.pi / 3, sub=None, seed=0):
+def frontal_rays(n_side: int, eye=(0.0, 0.0, 2.0), fov=np.pi / 3, sub=None, seed=0, window=1.0):
     """Pinhole rays looking down -z from ``eye`` (p = ((x-cx)/f, -(y-cy)/f, -1), normalised:
     models/dataset.py:277-293 with an identity rotation)."""
     W = H = n_side
@@ -64,6 +64,10 @@ def frontal_rays(n_side: int, eye=(0.0, 0.0, 2.0), fov=np.pi / 3, sub=None, seed
     p = torch.stack([(px - 0.5 * W) / f, -(py - 0.5 * H) / f, -torch.ones_like(px)], -1).float()
     d = (p / torch.linalg.norm(p, dim=-1, keepdim=True)).reshape(-1, 3)
     o = torch.tensor(eye, dtype=torch.float32)[None].expand_as(d).contiguous()
+    if window < 1.0:       # keep the central window of the image (where the body is)
+        lo, hi = 0.5 * (1 - window) * (W - 1), 0.5 * (1 + window) * (W - 1)
+        keep = ((px >= lo) & (px <= hi) & (py >= lo) & (py <= hi)).reshape(-1)
+        d, o = d[keep].contiguous(), o[keep].contiguous()
     if sub is not None:
         g = torch.Generator().manual_seed(seed)
         idx = torch.randperm(d.shape[0], generator=g)[:sub]
@@ -220,6 +224,27 @@ def main():
     g = torch.Generator().manual_seed(3)
     bg = torch.rand(96, 1, generator=g)
     run_case("small", sdf_kw, col_kw, ren_kw, 0.3, rays, jitter, bg, 1.0, state=state)
+
+    # ---- shipped full-size checkpoint (4x256 + 2x256 nets of confs/examples/*.conf; variance 0.6277 -> inv_s ~ 532):
+    # the configuration the reference actually trains, and the regime SURVEY Appendix C flags for reduced precision
+    state = torch.load(os.path.join(REF_AG, "pretrained_models", "zero_beta_stand_pose.pth"),
+                       map_location="cpu", weights_only=False)
+    sdf_kw = dict(d_in=3, d_out=257, d_hidden=256, n_layers=4, skip_in=[4], multires=6, bias=0.5,
+                  scale=1.0, geometric_init=True, weight_norm=True)
+    col_kw = dict(d_feature=256, mode="no_view_dir", d_in=6, d_out=3, d_hidden=256, n_layers=2,
+                  weight_norm=True, multires_view=0, squeeze_out=True, extra_color=True)
+    ren_kw = dict(n_samples=32, n_importance=32, n_outside=0, up_sample_steps=4, perturb=1.0,
+                  extra_color=True)
+    rays = frontal_rays(128, sub=128, seed=4, window=0.45)
+    torch.manual_seed(1234)
+    jitter = torch.rand([128, 1]) - 0.5
+    g = torch.Generator().manual_seed(5)
+    bg = torch.rand(128, 1, generator=g)
+    b = run_case("shipped", sdf_kw, col_kw, ren_kw, float(state["variance_network_fine"]["variance"]), rays, jitter,
+                 bg, 1.0, state=state)
+    print(f"[pin] shipped: variance {float(b['variance']):.4f} -> inv_s {float(torch.exp(10 * b['variance'])):.1f}; "
+          f"weight_sum mean {b['out']['weight_sum'].mean().item():.3f} "
+          f"({(b['out']['weight_sum'] > 0.5).float().mean().item() * 100:.0f}% of rays hit the body)")
 
     # ---- B2 sizing probe (assert-only)
     sdf_kw = dict(d_in=3, d_out=257, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5,

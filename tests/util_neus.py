@@ -16,6 +16,27 @@ COT_KEYS = ["color_fine", "extra_color_fine", "s_val", "cdf_fine", "weight_sum",
             "weights", "gradient_error"]
 
 
+def log_parity(name: str, rec: dict):
+    """Append one measured-parity record to gpurun_out/r2_parity.jsonl (merged into profiles/ by tools/collect_parity.py):
+    the tests assert bars, this file keeps the numbers actually measured on the GPU box."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "r2_parity.jsonl"), "a") as f:
+            f.write(json.dumps(dict(test=name, **rec)) + "\n")
+    except OSError:
+        pass
+
+
+def flat_rel_l2(got: Dict[str, torch.Tensor], ref: Dict[str, torch.Tensor]) -> float:
+    """rel-L2 error of the concatenated parameter gradient."""
+    num = sum((got[k].double().cpu() - ref[k].double().cpu()).pow(2).sum().item() for k in ref)
+    den = sum(ref[k].double().pow(2).sum().item() for k in ref)
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 def confs_from_kw(sdf_kw, col_kw, ren_kw):
     sconf = neus.SDFConf(**{k: (tuple(v) if k == "skip_in" else v) for k, v in sdf_kw.items()})
     return sconf, neus.ColorConf(**col_kw), neus.RenderConf(**ren_kw)
@@ -171,6 +192,16 @@ def run_case_gpu_vs_oracle(name: str, device="cuda", engine=0, seed=0, bg_kind="
     rep["grad_err"] = {k: rel_to_max(pgrads[k], ograds[k]) for k in ograds}
     rep["worst_out"] = max(rep["out_err"].values())
     rep["worst_grad"] = max(rep["grad_err"].values())
-    rep["ok"] = (rep["worst_out"] < 1e-3 and rep["worst_grad"] < 5e-3 and rep["placement_frac_3e-3"] >= 0.97
-                 and rep["full_render_frac_rays_1e-3"] >= 0.95)
+    rep["grad_rel_l2"] = flat_rel_l2(pgrads, ograds)
+    rep["engine"] = engine
+    # bars (north_star: 1e-3 relative on the rendered outputs; gradients: VERDICT r1 asks <= 1e-3 rel-L2):
+    #   fine pass on identical depths: every output within OUT_BAR (rel-to-max), flat gradient within 1e-3 rel-L2;
+    #   full pipeline (own placement): >= 99 % of rays within 1e-3 in colour, >= 97 % within 3e-3 in depth -- the
+    #   remainder are inverse-CDF bin flips, which the reference's own fp32 vs fp64 runs also show.
+    out_bar = 1e-4 if engine == 0 else 1e-3
+    rep["ok"] = (rep["worst_out"] < out_bar and rep["grad_rel_l2"] < 1e-3 and rep["placement_frac_3e-3"] >= 0.97
+                 and rep["full_render_frac_rays_1e-3"] >= 0.99)
+    log_parity("run_case", {k: rep[k] for k in ("case", "engine", "R", "worst_out", "worst_grad", "grad_rel_l2",
+                                                "placement_frac_3e-3", "placement_max_dz",
+                                                "full_render_frac_rays_1e-3")})
     return rep
