@@ -686,14 +686,21 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
   return 0;
 }
 
+// The C ABI carries betas as float; the reference's betas are the Python doubles 0.9 / 0.999.  Recover the short decimal
+// the float was rounded from (6 significant digits) so that `1 - beta` and the bias corrections match torch's doubles.
+static double round_beta(float b) { return (double)((long long)((double)b * 1e6 + 0.5)) / 1e6; }
+
 int avc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, int64_t step, float grad_scale, avc_stream_t stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq) return AVC_E_NULL;
   if (n <= 0 || step < 1) return AVC_E_SIZE;
-  double bc1 = 1.0 - pow((double)beta1, (double)step);
-  double bc2 = 1.0 - pow((double)beta2, (double)step);
-  k_adam<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                               eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  // Python floats are doubles: torch sees beta = 0.9 / 0.999 exactly as the decimal literals, not their float roundings
+  const double b1 = round_beta(beta1), b2 = round_beta(beta2);
+  double bc1 = 1.0 - pow(b1, (double)step);
+  double bc2 = 1.0 - pow(b2, (double)step);
+  k_adam<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, (float)b1,
+                                                               (float)b2, eps, (float)bc1, (float)sqrt(bc2), grad_scale,
+                                                               (float)(1.0 - b1), (float)(1.0 - b2));
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -703,9 +710,10 @@ int avc_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
   if (!params || !grads || !exp_avg || !exp_avg_sq || !state) return AVC_E_NULL;
   if (n <= 0) return AVC_E_SIZE;
   cudaStream_t st = (cudaStream_t)stream;
-  k_adam_state<<<1, 32, 0, st>>>(state, beta1, beta2);
-  k_adam_dev<<<blocks_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, beta1, beta2, eps,
-                                                 grad_scale);
+  const double b1 = round_beta(beta1), b2 = round_beta(beta2);
+  k_adam_state<<<1, 32, 0, st>>>(state, b1, b2);
+  k_adam_dev<<<blocks_for(n, 256), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, n, state, (float)b1, (float)b2, eps,
+                                                 grad_scale, (float)(1.0 - b1), (float)(1.0 - b2));
   AVC_LAUNCH_TRY();
   return 0;
 }

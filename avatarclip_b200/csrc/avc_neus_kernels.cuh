@@ -1296,35 +1296,37 @@ k_variance_grad(const float* __restrict__ params, int64_t off_var, const float* 
 // Fused Adam (torch.optim.Adam defaults; main.py:145,536-538).
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                        float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
-                       float bc2_sqrt, float gscale) {
+                       float bc2_sqrt, float gscale, float omb1, float omb2) {
+  // omb1 / omb2 = (float)(1 - (double)beta): torch evaluates `1 - beta` in double before the cast (a float 1 - 0.999f is
+  // 1.3e-5 off), lerp(m, g, 1 - b1) and v * b2 + (1 - b2) * g * g
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float gi = g[i] * gscale;
-  float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
-  float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
+  float mi = m[i] = m[i] + omb1 * (gi - m[i]);
+  float vi = v[i] = b2 * v[i] + omb2 * gi * gi;
   float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
 // Device-state variant for CUDA-graph replay: state[0] = steps so far, state[1] = lr, state[2] = 1 - b1^t, state[3] =
 // sqrt(1 - b2^t).
-__global__ void k_adam_state(float* __restrict__ state, float b1, float b2) {
+__global__ void k_adam_state(float* __restrict__ state, double b1d, double b2d) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     float t = state[0] + 1.0f;
     state[0] = t;
-    state[2] = 1.0f - powf(b1, t);
-    state[3] = sqrtf(1.0f - powf(b2, t));
+    state[2] = (float)(1.0 - pow((double)b1d, (double)t));
+    state[3] = (float)sqrt(1.0 - pow((double)b2d, (double)t));
   }
 }
 __global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                            float* __restrict__ v, int64_t n, const float* __restrict__ state, float b1, float b2,
-                           float eps, float gscale) {
+                           float eps, float gscale, float omb1, float omb2) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float lr = state[1], bc1 = state[2], bc2_sqrt = state[3];
   float gi = g[i] * gscale;
-  float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
-  float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
+  float mi = m[i] = m[i] + omb1 * (gi - m[i]);
+  float vi = v[i] = b2 * v[i] + omb2 * gi * gi;
   float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] -= (lr / bc1) * (mi / denom);
 }

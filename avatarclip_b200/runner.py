@@ -187,6 +187,8 @@ class Runner:
             return
         if self.trainer is None:
             self._pending_optimizer_state = sd
+            if self.clip_tower is not None:
+                self._ensure_trainer()                 # builds the trainer and applies the pending state
             return
         tr = self.trainer
         params = list(self.sdf_network.parameters()) + list(self.deviation_network.parameters()) + \

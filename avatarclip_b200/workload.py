@@ -230,3 +230,31 @@ def build_networks(sdf_kw, col_kw, ren_kw, sdf_state, col_state, variance, devic
     sdf, col, var = sdf.to(device), col.to(device), var.to(device)
     ren = NeuSRenderer(None, sdf, var, col, engine=engine, max_rays_per_chunk=chunk, **ren_kw)
     return sdf, col, var, ren
+
+
+def synthetic_body_mesh(n_lat: int = 24, n_lon: int = 32):
+    """A procedural stand-in for the SMPL template (the real one is licence-gated and lives under /root/reference only):
+    a union of ellipsoids -- torso, head, two arms, two legs -- inside the unit sphere.  Built y-up / facing +z (the
+    NeuS world frame) and returned in the frame of ``Runner.v`` (the posed SMPL output whose root orientation makes it
+    z-up: render_one_batch maps it back with (x, y, z) -> (x, z, -y), models/utils.py:115-119), i.e. as (x, -z, y).
+    Returns (verts [V,3] float32, faces [F,3] int32); 24 x 32 -> 9 216 triangles."""
+    parts = [((0.0, 0.10, 0.0), (0.17, 0.30, 0.11)), ((0.0, 0.55, 0.01), (0.09, 0.11, 0.10)),
+             ((-0.30, 0.20, 0.0), (0.05, 0.26, 0.05)), ((0.30, 0.20, 0.0), (0.05, 0.26, 0.05)),
+             ((-0.09, -0.50, 0.0), (0.07, 0.36, 0.07)), ((0.09, -0.50, 0.0), (0.07, 0.36, 0.07))]
+    vs, fs, base = [], [], 0
+    th = np.linspace(0.0, np.pi, n_lat + 1)
+    ph = np.linspace(0.0, 2 * np.pi, n_lon, endpoint=False)
+    for c, r in parts:
+        T, P = np.meshgrid(th, ph, indexing="ij")
+        v = np.stack([c[0] + r[0] * np.sin(T) * np.cos(P), c[1] + r[1] * np.cos(T), c[2] + r[2] * np.sin(T) * np.sin(P)], -1)
+        vs.append(v.reshape(-1, 3))
+        for i in range(n_lat):
+            for j in range(n_lon):
+                a, b = base + i * n_lon + j, base + i * n_lon + (j + 1) % n_lon
+                c2, d = a + n_lon, b + n_lon
+                fs.append([a, c2, b])
+                fs.append([b, c2, d])
+        base += (n_lat + 1) * n_lon
+    v = np.concatenate(vs)
+    v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], 1)
+    return v.astype(np.float32), np.asarray(fs, dtype=np.int32)

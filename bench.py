@@ -212,7 +212,7 @@ def run_native(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     pg = None
-    out = StdoutToStderr()      # native-library chatter (NCCL INFO) goes to stderr, the JSON line to the real stdout
+    real_stdout = StdoutToStderr()      # native-library chatter (NCCL INFO) goes to stderr, the JSON line to the real stdout
     if world > 1:
         import torch.distributed as dist
         # NCCL_DEBUG is left as the caller set it (INFO when unset, so the communicator's rank count is on record)
@@ -420,7 +420,7 @@ def run_native(args):
             line["parity"] = parity
             if args.ref_gpu:
                 line["ref_gpu"] = reference_gpu(sp, cp, clip_sd, text, device, steps=max(5, min(K, 20)))
-        out.emit(json.dumps(line))
+        real_stdout.emit(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
 

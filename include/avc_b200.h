@@ -296,6 +296,36 @@ int avc_tc_gemm_nt_test(const float* A, const float* B, int64_t M, int32_t N, in
 int avc_tc_gemm_tn_test(const float* A, const float* B, int64_t P, int32_t N1, int32_t N2, int32_t nprod,
                         float* C, float* colsum, void* workspace, size_t workspace_bytes, avc_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Per-step view preparation of Runner.train_clip, all on the device.
+ *
+ * avc_raster_template replaces render_one_batch (models/utils.py:108-125 -> neural_renderer Renderer(camera_mode=
+ * 'look'), image_size 256, 2x anti-aliasing, white textures, ambient 0.5 + directional 0.5 along +y, fill_back):
+ * verts [V][3] (SMPL frame; the (x, z, -y) re-orientation of utils.py:115-119 happens inside), faces [F][3] int32,
+ * eye / at [3] HOST pointers; rgb_out [n][n][3] already flipped like utils.py:124; mask_out [n][n] = (rgb != 0)
+ * (main.py:361-364).  avc_dilate_count = ndimage.binary_dilation(mask, 3x3 full structure, iterations) and the
+ * pixel count that sizes the canvas (models/dataset.py:255-258).  avc_mask_compact = nearest resize of the dilated
+ * mask to W x W (F.interpolate default) + the row-major list of its True pixels (dataset.py:269-273); pix holds at
+ * most `cap` entries, count_out the true count.  avc_view_targets = main.py:375-380,407-410 (nearest resize of the
+ * template render, mask = channel 0 != 0, or all ones when threshold_mask == 0 i.e. mask_weight == 0).
+ * avc_background_field = main.py:392-402: kind 1 clamp(N(0.5, 0.2), 0, 1) per pixel, kind 2 the 0.2 / 0.8
+ * chessboard of chess_len-pixel squares blurred by GaussianBlur(kernel (5, 9), sigma); optional gather to the rays
+ * (main.py:412-413).  avc_uniform_fill: counter-based U[lo, hi) draws (per-ray jitter, renderer.py:317-319).
+ * ------------------------------------------------------------------------------------------ */
+int avc_raster_workspace_bytes(int32_t V, int32_t image_size, int32_t supersample, size_t* bytes);
+int avc_raster_template(const float* verts, const int32_t* faces, int32_t V, int32_t F, const float* eye,
+                        const float* at, int32_t image_size, int32_t supersample, float* rgb_out, uint8_t* mask_out,
+                        void* workspace, size_t workspace_bytes, avc_stream_t stream);
+int avc_dilate_count(const uint8_t* mask, int32_t n, int32_t iterations, uint8_t* dilated, int32_t* count_out,
+                     avc_stream_t stream);
+int avc_mask_compact(const uint8_t* dilated, int32_t n, int32_t W, int32_t cap, uint8_t* in_mask, int32_t* pix,
+                     int32_t* count_out, avc_stream_t stream);
+int avc_view_targets(const float* rgb, int32_t n, int32_t W, int32_t threshold_mask, float* true_rgb, float* mask,
+                     avc_stream_t stream);
+int avc_background_field(int32_t kind, int32_t H, int32_t W, uint32_t seed, int32_t chess_len, float sigma,
+                         float* canvas_bg, const int32_t* pix, int32_t R, float* ray_bg, avc_stream_t stream);
+int avc_uniform_fill(uint32_t seed, int32_t n, float lo, float hi, float* out, avc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
