@@ -74,6 +74,11 @@ def lib():
     L.avc_neus_render_bwd.argtypes = [P(NeusCfg), vp, vp, vp, vp, C.c_int, f32, i64, P(NeusOutputs),
                                       P(NeusCotangents), vp, vp, sz, i64, i32, vp]
     L.avc_neus_sdf_query.argtypes = [P(NeusCfg), vp, vp, i64, vp, vp, sz, vp]
+    L.avc_neus_sdf_eval.argtypes = [P(NeusCfg), vp, vp, i64, vp, vp, vp, sz, vp]
+    L.avc_neus_sdf_eval.restype = C.c_int
+    L.avc_march_count.argtypes = [vp, i32, i32, i32, f32, vp, vp]
+    L.avc_march_emit.argtypes = [vp, i32, i32, i32, f32, vp, vp, vp, vp]
+    L.avc_march_count.restype = L.avc_march_emit.restype = C.c_int
     L.avc_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, i64, f32, vp]
     L.avc_adam_step_dev.argtypes = [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, vp]
     L.avc_adam_step_dev.restype = C.c_int

@@ -193,6 +193,37 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
   return 0;
 }
 
+// -------------------------------------------------------------------------------- gradient chain
+// d sdf / d x by the reverse sweep of Appendix B (no second forward): needs the sp' stash of value_chain(stash = true)
+// and cin[p][0:3] = x.  Writes the raw gradient into cin[p][3:6] and, optionally, grad_out [P][3].
+int gradient_chain(const NeusPlan& pl, const NeusWs& w, int64_t P, float* grad_out, cudaStream_t st) {
+  const float* pack = w.pack;
+  const LinDim& dL = pl.sdf[pl.L];
+  const LinDim& dp = pl.sdf[pl.L - 1];
+  // tcgen05 engine: qt_l is only ever consumed as a split operand (gradient chain, second-order sweep, dW)
+  const bool tc1 = pl.cfg.engine == 1;
+  int64_t tot = P * (int64_t)(dp.Np / 4 > pl.EP ? dp.Np / 4 : pl.EP);   // threads: 4 qt columns each, 1 ge entry each
+  k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
+                                                      w.z[pl.L - 1], dp.N, dp.Np, P, tc1 ? nullptr : w.qt[pl.L - 1], w.ge,
+                                                      w.qt16[pl.L - 1]);
+  AVC_LAUNCH_TRY();
+  for (int l = pl.L - 1; l >= 1; --l) {
+    const LinDim& d = pl.sdf[l];
+    const LinDim& dq = pl.sdf[l - 1];
+    EpiChain e;
+    e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
+    e.D1prev = w.z[l - 1]; e.QTprev = tc1 ? nullptr : w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
+    e.q16 = w.qt16[l - 1];
+    AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
+  }
+  const LinDim& d0 = pl.sdf[0];
+  EpiGe eg{w.ge, pl.EP, pl.E};
+  AVC_TRY(gemm_nt(pl, w, st, P, pl.E, d0.N, w.qt[0], d0.Np, w.qt16[0], d0.pk_WT, d0.Np, eg));
+  k_normal<<<blocks_for(P, 128), 128, 0, st>>>(w.ge, pl.EP, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P, w.cin, grad_out);
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
 // -------------------------------------------------------------------------------- placement
 int place_samples(const NeusPlan& pl, const NeusWs& w, const float* rays_o, const float* rays_d, const float* near,
                   const float* far, const float* jitter, int Rc, float* z_out_raymajor, cudaStream_t st) {
@@ -263,33 +294,7 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
                                                     write_outputs ? io.out.inside_sphere : nullptr, t);
   AVC_LAUNCH_TRY();
   AVC_TRY(value_chain(pl, w, P, true, true, w.sdf, st));
-  // ---- gradient chain
-  {
-    const LinDim& dL = pl.sdf[pl.L];
-    const LinDim& dp = pl.sdf[pl.L - 1];
-    // tcgen05 engine: qt_l is only ever consumed as a split operand (gradient chain, second-order sweep, dW)
-    const bool tc1 = pl.cfg.engine == 1;
-    int64_t tot = P * (int64_t)(dp.Np / 4 > pl.EP ? dp.Np / 4 : pl.EP);   // threads: 4 qt columns each, 1 ge entry each
-    k_chain_start<<<blocks_for(tot, 256), 256, 0, st>>>(pack + pl.pk_wsdf, dL.K, dL.skip ? 1 : 0, pl.E, pl.EP,
-                                                        w.z[pl.L - 1], dp.N, dp.Np, P, tc1 ? nullptr : w.qt[pl.L - 1], w.ge,
-                                                        w.qt16[pl.L - 1]);
-    AVC_LAUNCH_TRY();
-    for (int l = pl.L - 1; l >= 1; --l) {
-      const LinDim& d = pl.sdf[l];
-      const LinDim& dq = pl.sdf[l - 1];
-      EpiChain e;
-      e.Nprev = dq.N; e.Npp = dq.Np; e.s = d.skip ? kSqrtHalf : 1.f;
-      e.D1prev = w.z[l - 1]; e.QTprev = tc1 ? nullptr : w.qt[l - 1]; e.GE = w.ge; e.EP = pl.EP; e.E = pl.E;
-      e.q16 = w.qt16[l - 1];
-      AVC_TRY(gemm_nt(pl, w, st, P, d.K, d.N, w.qt[l], d.Np, w.qt16[l], d.pk_WT, d.Np, e));
-    }
-    const LinDim& d0 = pl.sdf[0];
-    EpiGe eg{w.ge, pl.EP, pl.E};
-    AVC_TRY(gemm_nt(pl, w, st, P, pl.E, d0.N, w.qt[0], d0.Np, w.qt16[0], d0.pk_WT, d0.Np, eg));
-    k_normal<<<blocks_for(P, 128), 128, 0, st>>>(w.ge, pl.EP, pl.cfg.sdf_multires, pl.cfg.sdf_scale, P, w.cin,
-                                                 write_outputs ? io.out.gradients : nullptr);
-    AVC_LAUNCH_TRY();
-  }
+  AVC_TRY(gradient_chain(pl, w, P, write_outputs ? io.out.gradients : nullptr, st));
   // ---- colour net
   {
     const LinDim& c0 = pl.col[0];
@@ -682,6 +687,69 @@ int avc_neus_sdf_query(const avc_neus_cfg* cfg, const float* params, const float
                                                         pl.EP, t);
     AVC_LAUNCH_TRY();
     AVC_TRY(value_chain(pl, w, n, false, false, sdf_out + p0, st));
+  }
+  return 0;
+}
+
+// SDFNetwork.forward / .sdf_hidden_appearance / .gradient (models/fields.py:72-107) on arbitrary points: convenience
+// evaluators of the boundary (not on the training path).  Always the exact-fp32 tiles (engine 0).
+namespace {
+__global__ void k_points_to_cin(const float* __restrict__ pts, int64_t P, float* __restrict__ cin) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float4* c = reinterpret_cast<float4*>(cin + (size_t)p * 8);
+  c[0] = make_float4(pts[p * 3], pts[p * 3 + 1], pts[p * 3 + 2], 0.f);
+  c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__global__ void k_assemble_sdf_feat(const float* __restrict__ sdf, const float* __restrict__ feat, int Fp, int F, int64_t P,
+                                    float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * (F + 1)) return;
+  int64_t p = i / (F + 1);
+  int c = (int)(i - p * (F + 1));
+  out[i] = c == 0 ? sdf[p] : feat[(size_t)p * Fp + (c - 1)];
+}
+}  // namespace
+
+int avc_neus_sdf_eval(const avc_neus_cfg* cfg_in, const float* params, const float* pts, int64_t P, float* sdf_feat_out,
+                      float* grad_out, void* workspace, size_t workspace_bytes, avc_stream_t stream) {
+  if (!cfg_in || !params || !pts || !workspace) return AVC_E_NULL;
+  if (!sdf_feat_out && !grad_out) return AVC_E_NULL;
+  if (P <= 0) return AVC_E_SIZE;
+  avc_neus_cfg cfg = *cfg_in;
+  cfg.engine = 0;
+  NeusPlan pl;
+  AVC_TRY(build_plan(&cfg, &pl));
+  size_t one = 0;
+  AVC_TRY(avc_neus_workspace_bytes(&cfg, 1, &one));
+  NeusWs w;
+  int64_t Rc = 1;
+  {
+    NeusWs w2; carve_ws(pl, 2, nullptr, &w2);
+    size_t per = w2.bytes - one;
+    if (workspace_bytes < one) return AVC_E_SIZE;
+    Rc = 1 + (int64_t)((workspace_bytes - one) / (per ? per : 1));
+    while (Rc > 1) { carve_ws(pl, Rc, nullptr, &w); if (w.bytes <= workspace_bytes) break; --Rc; }
+  }
+  carve_ws(pl, Rc, workspace, &w);
+  if (w.bytes > workspace_bytes) return AVC_E_SIZE;
+  cudaStream_t st = (cudaStream_t)stream;
+  AVC_TRY(prepare_weights(pl, w, params, st));
+  const int64_t cap = Rc * pl.S;
+  EncodeTargets t = make_targets(pl, w);
+  for (int64_t p0 = 0; p0 < P; p0 += cap) {
+    int64_t n = (P - p0) < cap ? (P - p0) : cap;
+    k_encode_points<<<blocks_for(n * 8, 256), 256, 0, st>>>(pts + p0 * 3, n, pl.cfg.sdf_scale, pl.cfg.sdf_multires, pl.E,
+                                                        pl.EP, t);
+    k_points_to_cin<<<blocks_for(n, 256), 256, 0, st>>>(pts + p0 * 3, n, w.cin);
+    AVC_LAUNCH_TRY();
+    AVC_TRY(value_chain(pl, w, n, grad_out != nullptr, sdf_feat_out != nullptr, w.sdf, st));
+    if (sdf_feat_out) {
+      k_assemble_sdf_feat<<<blocks_for(n * (pl.F + 1), 256), 256, 0, st>>>(w.sdf, w.feat, pl.Fp, pl.F, n,
+                                                                          sdf_feat_out + p0 * (pl.F + 1));
+      AVC_LAUNCH_TRY();
+    }
+    if (grad_out) AVC_TRY(gradient_chain(pl, w, n, grad_out + p0 * 3, st));
   }
   return 0;
 }

@@ -93,8 +93,17 @@ class SDFNetwork(nn.Module):
         return self._binding().sdf_query(x)
 
     def forward(self, inputs):
-        raise NotImplementedError("feature-vector output is only produced inside NeuSRenderer.render; "
-                                  "use .sdf(x) for signed distances")
+        """models/fields.py:72-88: [P,3] -> [P, d_out] = (sdf, feature vector)."""
+        return self._binding().sdf_eval(inputs, want_features=True, want_gradient=False)[0]
+
+    def sdf_hidden_appearance(self, x):
+        """models/fields.py:93-94."""
+        return self.forward(x)
+
+    def gradient(self, x):
+        """models/fields.py:96-107: d sdf / d x, [P,3] -> [P,1,3] (evaluated analytically by the reverse sweep of
+        SURVEY Appendix B; inference only -- training differentiates through NeuSRenderer.render)."""
+        return self._binding().sdf_eval(x, want_features=False, want_gradient=True)[1].unsqueeze(1)
 
 
 class RenderingNetwork(nn.Module):

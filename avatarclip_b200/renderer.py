@@ -296,6 +296,61 @@ class NeuSRenderer:
                    "avc_neus_sdf_query")
         return out
 
+    def sdf_eval(self, pts: torch.Tensor, want_features: bool = True, want_gradient: bool = False):
+        """SDFNetwork.forward (models/fields.py:72-88) and/or SDFNetwork.gradient (:96-107) on [P,3] points ->
+        ([P, d_out] = (sdf, features) or None, [P,3] raw gradient or None).  Inference only (no autograd)."""
+        if not pts.is_cuda:
+            raise _lib.AvcError("avatarclip_b200 has no CPU path: points must live on a CUDA device")
+        fp = self._ensure_flat(pts.device)
+        pts = self._prep(pts, (-1, 3))
+        P = pts.shape[0]
+        S = self.cfg.n_samples + self.cfg.n_importance
+        out = torch.empty(P, self.cfg.sdf_d_out, dtype=torch.float32, device=pts.device) if want_features else None
+        grad = torch.empty(P, 3, dtype=torch.float32, device=pts.device) if want_gradient else None
+        cfg0 = NeusCfg.from_buffer_copy(self.cfg)
+        cfg0.engine = 0
+        size = C.c_size_t()
+        chunk = max(1, min(self.max_rays_per_chunk, (P + S - 1) // S))
+        _lib.check(_lib.lib().avc_neus_workspace_bytes(C.byref(cfg0), chunk, C.byref(size)), "avc_neus_workspace_bytes")
+        ws = torch.empty(size.value, dtype=torch.uint8, device=pts.device)
+        _lib.check(_lib.lib().avc_neus_sdf_eval(C.byref(self.cfg), _lib.ptr(fp.flat), _lib.ptr(pts), P, _lib.ptr(out),
+                                                _lib.ptr(grad), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "avc_neus_sdf_eval")
+        return out, grad
+
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        """models/renderer.py:399-404 (-> extract_geometry :27-36): the iso-surface {-sdf = threshold} of the
+        resolution^3 grid over the bounding box.  Returns (vertices [V,3] float, triangles [T,3] int) as numpy arrays in
+        world coordinates like the reference.  The reference triangulates with PyMCubes; here csrc/avc_mesh.cu runs
+        marching tetrahedra on the device (same surface, different triangulation; normals point out of the body)."""
+        import numpy as np
+        L = _lib.lib()
+        u = self.extract_fields(bound_min, bound_max, resolution).contiguous()
+        dev = u.device
+        N = int(resolution)
+        counts = torch.empty((N - 1) ** 3, dtype=torch.int32, device=dev)
+        _lib.check(L.avc_march_count(_lib.ptr(u), N, N, N, float(threshold), _lib.ptr(counts), _lib.stream_ptr()),
+                   "avc_march_count")
+        incl = torch.cumsum(counts, 0, dtype=torch.int64)
+        T = int(incl[-1].item()) if incl.numel() else 0
+        if T == 0:
+            return np.zeros((0, 3), dtype=np.float64), np.zeros((0, 3), dtype=np.int64)
+        offsets = (incl - counts).to(torch.int32)
+        verts = torch.empty(T * 3, 3, dtype=torch.float32, device=dev)
+        keys = torch.empty(T * 3, dtype=torch.int64, device=dev)
+        _lib.check(L.avc_march_emit(_lib.ptr(u), N, N, N, float(threshold), _lib.ptr(offsets), _lib.ptr(verts),
+                                    _lib.ptr(keys), _lib.stream_ptr()), "avc_march_emit")
+        uniq, inv = torch.unique(keys, return_inverse=True)                  # weld vertices that sit on the same grid edge
+        welded = torch.empty(uniq.numel(), 3, dtype=torch.float32, device=dev)
+        welded[inv] = verts
+        tri = inv.reshape(T, 3)
+        good = (tri[:, 0] != tri[:, 1]) & (tri[:, 1] != tri[:, 2]) & (tri[:, 0] != tri[:, 2])   # crossings exactly on a grid point
+        tri = tri[good]
+        b_min = torch.as_tensor(np.asarray(bound_min, dtype=np.float32), device=dev)
+        b_max = torch.as_tensor(np.asarray(bound_max, dtype=np.float32), device=dev)
+        vertices = welded / (N - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]          # renderer.py:33-35
+        return vertices.double().cpu().numpy(), tri.cpu().numpy()
+
     def extract_fields(self, bound_min, bound_max, resolution):
         """models/renderer.py:10-25 with query_func = -sdf, evaluated in slabs on the device."""
         dev = self._flat.flat.device if self._flat is not None else torch.device("cuda")

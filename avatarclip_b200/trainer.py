@@ -132,6 +132,12 @@ class AppearanceTrainer:
         mark("render_bwd")
         return self.grad
 
+    def set_text(self, emb: torch.Tensor):
+        """Select the cached text embedding(s) of the coming step (main.py:499-507: body / face / back prompt) by
+        copying into the resident [2,512] buffer (addresses stay fixed: valid under CUDA-graph replay)."""
+        e = emb.detach().float().reshape(-1, self.text.shape[1]).to(self.device)
+        self.text.copy_(e.expand(2, -1) if e.shape[0] == 1 else e)
+
     def loss_value(self) -> torch.Tensor:
         """Total loss of main.py:528-534 as a device scalar (one tiny kernel; read it with .item() to sync)."""
         return self.scalars[losses.S_BASE] + ((1.0 - self.cos) * self.clip_weight).sum()

@@ -246,6 +246,12 @@ int avc_loss_stage_fwd(const avc_loss_inputs* in, float* canvases, float* scalar
 int avc_loss_stage_bwd(const avc_loss_inputs* in, const float* d_canvases, const float* scalars,
                        const avc_neus_cotangents* cot_out, avc_stream_t stream);
 
+/* SDFNetwork.forward / .sdf_hidden_appearance / .gradient (models/fields.py:72-107) on P arbitrary points (boundary
+ * convenience, exact-fp32 tiles regardless of cfg->engine): sdf_feat_out [P][d_out] = (sdf, feature vector) or NULL;
+ * grad_out [P][3] = d sdf / d x (raw, un-normalised) or NULL.  Workspace: as avc_neus_sdf_query. */
+int avc_neus_sdf_eval(const avc_neus_cfg* cfg, const float* params, const float* pts, int64_t P, float* sdf_feat_out,
+                      float* grad_out, void* workspace, size_t workspace_bytes, avc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Fused Adam over the flat parameter vector (torch.optim.Adam defaults, main.py:145,536-538):
  * p -= lr * mhat / (sqrt(vhat) + eps); `step` is the 1-based step count; grad_scale multiplies g
@@ -325,6 +331,19 @@ int avc_view_targets(const float* rgb, int32_t n, int32_t W, int32_t threshold_m
 int avc_background_field(int32_t kind, int32_t H, int32_t W, uint32_t seed, int32_t chess_len, float sigma,
                          float* canvas_bg, const int32_t* pix, int32_t R, float* ray_bg, avc_stream_t stream);
 int avc_uniform_fill(uint32_t seed, int32_t n, float lo, float hi, float* out, avc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Iso-surface extraction for NeuSRenderer.extract_geometry (models/renderer.py:27-36,399-404; the reference calls
+ * PyMCubes' marching_cubes, third-party, absent).  Marching tetrahedra over the [nx][ny][nz] field u (= -sdf):
+ * avc_march_count writes the number of triangles of every grid cube ((nx-1)(ny-1)(nz-1) ints, x-major like the
+ * field); the caller turns them into exclusive offsets; avc_march_emit writes 3 vertices per triangle in INDEX
+ * coordinates (the caller rescales like renderer.py:33-35) and, per vertex, a 64-bit key of the grid edge it lies
+ * on (for welding).  Triangles are oriented with normals towards decreasing u.
+ * ------------------------------------------------------------------------------------------ */
+int avc_march_count(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, int32_t* counts,
+                    avc_stream_t stream);
+int avc_march_emit(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, const int32_t* offsets,
+                   float* verts, int64_t* keys, avc_stream_t stream);
 
 #ifdef __cplusplus
 }

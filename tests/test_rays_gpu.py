@@ -17,7 +17,8 @@ def test_gen_rays_matches_oracle(canvas):
     g = torch.Generator().manual_seed(canvas)
     mask = torch.rand(canvas, canvas, generator=g) < 0.3
     rg = RayGenerator()
-    ro, rd, nr, fr, pix = rg.gen_rays_pixels(pose, canvas, mask)
+    pix = torch.nonzero(mask.reshape(-1).cuda(), as_tuple=False).reshape(-1).to(torch.int32)
+    ro, rd, nr, fr = rg.rays(pose, canvas, canvas, pix)
     sel = mask.reshape(-1)
     assert torch.equal(pix.cpu().long(), torch.nonzero(sel).reshape(-1))
     assert (rd.cpu() - d.reshape(-1, 3)[sel]).abs().max().item() < 2e-6

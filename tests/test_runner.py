@@ -1,4 +1,7 @@
-"""Runner mirror: conf-driven construction, LR schedule, checkpoint layout (CPU) and a short train_clip run (GPU)."""
+"""Runner mirror: conf-driven construction, LR schedule, checkpoint layout (CPU); the real train_clip loop (per-step
+draws, device view preparation with lookahead, prompt selection, resume in the CLI order), --mode train on a hand-off
+directory, validation image / mesh outputs (GPU)."""
+import json
 import os
 
 import numpy as np
@@ -11,16 +14,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CONF = os.path.join(HERE, "runner_conf_sample.conf")
 
 
-def _runner(tmp_path, device):
+def _conf_text(tmp_path, data_dir=None):
+    text = open(CONF).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "exp"))
+    if data_dir is not None:
+        text = text.replace("./data/zero_beta_tpose_render", str(data_dir))
+    p = tmp_path / "run.conf"
+    p.write_text(text)
+    return str(p)
+
+
+def _runner(tmp_path, device, mode="train_clip", data_dir=None, is_continue=False):
     from avatarclip_b200.runner import Runner
-    r = Runner(CONF, mode="train_clip", case="smpl", device=device)
-    r.base_exp_dir = str(tmp_path / "exp")
-    return r
+    return Runner(_conf_text(tmp_path, data_dir), mode=mode, case="smpl", device=device, is_continue=is_continue)
 
 
 def test_runner_construction_schedule_and_checkpoint_layout(tmp_path):
-    r = _runner(tmp_path, "cpu")
-    assert r.conf["general.base_exp_dir"] == "./exp/smpl/demo"          # CASE_NAME substitution (main.py:41)
+    r = _runner(tmp_path, "cpu", mode="validate")
+    assert r.use_face_prompt and r.use_back_prompt and r.head_height == 0.55 and r.seed == 11
     for it in (0, 100, 499, 500, 5000, 99999):
         r.iter_step = it
         want = 5e-4 * ol.learning_rate_factor(it, 500.0, 100000, 0.05)
@@ -35,35 +45,120 @@ def test_runner_construction_schedule_and_checkpoint_layout(tmp_path):
     # the reference's optimizer (main.py:141-145) accepts the stored optimizer state
     params = list(r.sdf_network.parameters()) + list(r.deviation_network.parameters()) + list(r.color_network.parameters())
     torch.optim.Adam(params, lr=5e-4).load_state_dict(ck["optimizer"])
-    r2 = _runner(tmp_path, "cpu")
+    r2 = _runner(tmp_path, "cpu", mode="validate")
     r2.load_checkpoint(path)
     assert r2.iter_step == 7
     for a, b in zip(r.sdf_network.parameters(), r2.sdf_network.parameters()):
         assert torch.equal(a, b)
 
 
+def _clip_args():
+    from avatarclip_b200.workload import random_vit_state
+    g = torch.Generator().manual_seed(0)
+    return random_vit_state(seed=0), torch.randn(1, 512, generator=g), torch.randn(1, 512, generator=g), \
+        torch.randn(1, 512, generator=g)
+
+
 @pytest.mark.gpu
-def test_runner_train_clip_runs_and_resumes(tmp_path):
-    from oracle import clip_vit as cv
+def test_runner_train_clip_real_loop_and_cli_order_resume(tmp_path):
+    """train_clip with NO view_source: cameras from the seeded sampler, template rasterised and silhouette rays prepared
+    on the device one step ahead, face / back prompts selected per step; then resume like the CLI does
+    (Runner(is_continue=True) BEFORE init_clip -- ADVICE r1: the Adam moments must survive)."""
+    from avatarclip_b200.workload import synthetic_body_mesh
+    sd, text, face, back = _clip_args()
+    v, f = synthetic_body_mesh(12, 16)
     r = _runner(tmp_path, "cuda")
-    text = torch.randn(1, 512, generator=torch.Generator().manual_seed(0))
-    r.init_clip(cv.random_vit_state(seed=0), text)
-    r.init_smpl()
+    r.init_clip(sd, text, face, back)
+    r.init_smpl(v, f)
+    used = []
+    orig = r._ensure_trainer().set_text
+    r.trainer.set_text = lambda e: (used.append(e.data_ptr()), orig(e))[1]
     logs = []
     before = r.sdf_network.lin1.weight_v.detach().clone()
     r.report_freq = 2
-    assert r.train_clip(max_steps=4, log=logs.append) == 4
-    assert not torch.equal(before, r.sdf_network.lin1.weight_v)         # parameters moved
+    assert r.train_clip(max_steps=6, log=logs.append, validate=False) == 6
+    assert not torch.equal(before, r.sdf_network.lin1.weight_v)
     assert any("loss" in str(l) for l in logs)
+    assert used[0] == r.encoded_face_text.data_ptr() and used[4] == r.encoded_face_text.data_ptr()   # iter_i % 4 == 0
+    assert all(u in (r.encoded_text.data_ptr(), r.encoded_back_text.data_ptr()) for i, u in enumerate(used) if i % 4)
     path = r.save_checkpoint()
     ck = torch.load(path, weights_only=False)
-    params = list(r.sdf_network.parameters()) + list(r.deviation_network.parameters()) + list(r.color_network.parameters())
-    opt = torch.optim.Adam(params, lr=5e-4)
-    opt.load_state_dict(ck["optimizer"])                                # reference-format Adam state
-    assert len(ck["optimizer"]["state"]) == len(params)
-    r2 = _runner(tmp_path, "cuda")
-    r2.init_clip(cv.random_vit_state(seed=0), text)
-    r2.load_checkpoint(path)
-    assert r2.iter_step == 4 and torch.equal(r2.trainer.exp_avg, r.trainer.exp_avg)
+    assert len(ck["optimizer"]["state"]) == len(r._all_params())
+    torch.optim.Adam(r._all_params(), lr=5e-4).load_state_dict(ck["optimizer"])       # reference-format Adam state
+    # CLI order: constructor (loads the checkpoint) first, init_clip afterwards
+    r2 = _runner(tmp_path, "cuda", is_continue=True)
+    assert r2.iter_step == 6 and r2.trainer is None and r2._pending_optimizer_state is not None
+    r2.init_clip(sd, text, face, back)
+    tr2 = r2._ensure_trainer()
+    assert tr2.iter_step == 6 and torch.equal(tr2.exp_avg, r.trainer.exp_avg) and torch.equal(tr2.exp_avg_sq, r.trainer.exp_avg_sq)
+    assert float(tr2.exp_avg.abs().max()) > 0
     img = r2.render_image(ol.lookat([0.0, 0.0, 1.6], [0.0, 0.0, 0.0]), resolution_level=8)
     assert img.shape == (32, 32, 3) and torch.isfinite(img).all()
+
+
+@pytest.mark.gpu
+def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path):
+    """ShapeGen hand-off (108 rendered views + transforms_train.json) -> SMPL_Dataset -> --mode train (NeuS pre-fit
+    through the autograd seam + torch.optim.Adam) -> validate_image PNGs and validate_mesh PLY."""
+    from avatarclip_b200.handoff import read_ply, render_coarse_shape
+    from avatarclip_b200.workload import synthetic_body_mesh
+    v, f = synthetic_body_mesh(12, 16)
+    data_dir = tmp_path / "render"
+    render_coarse_shape(v, f, str(data_dir), image_size=64)
+    meta = json.load(open(data_dir / "transforms_train.json"))
+    assert len(meta["frames"]) == 108 and abs(meta["camera_angle_x"] - np.pi / 3) < 1e-12
+    r = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir)
+    assert r.dataset.n_images == 108 and r.dataset.H == 64 and float(r.dataset.masks.mean()) > 0.01
+    r.batch_size = 256
+    losses = []
+    r.report_freq = 5
+    r.train(max_steps=30, log=lambda m: losses.append(m), validate=False)
+    vals = [float(str(m).split("loss = ")[1].split(" ")[0]) for m in losses if "loss = " in str(m)]
+    assert len(vals) == 6 and all(np.isfinite(vals)) and vals[-1] < vals[0]
+    img, extra, normal = r.validate_image(idx=3, resolution_level=2)
+    assert img.shape == (32, 32, 3)
+    assert os.path.exists(os.path.join(r.base_exp_dir, "validations_fine", "{:0>8d}_0_3.png".format(r.iter_step)))
+    assert os.path.exists(os.path.join(r.base_exp_dir, "normals", "{:0>8d}_0_3.png".format(r.iter_step)))
+    path = r.validate_mesh(resolution=48)
+    vv, ff, cc = read_ply(path)
+    assert vv.shape[0] > 100 and ff.shape[0] > 100 and cc.shape == (vv.shape[0], 3)
+    assert ff.max() < vv.shape[0] and np.abs(vv).max() <= 1.02
+    # resume --mode train with the torch optimizer state
+    ck = r.save_checkpoint()
+    r2 = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir, is_continue=True)
+    opt = r2._ensure_optimizer()
+    assert r2.iter_step == 30 and len(opt.state) == len(r2._all_params())
+
+
+@pytest.mark.gpu
+def test_extract_geometry_sphere_is_watertight_and_outward(tmp_path):
+    """Marching tetrahedra on the geometric-init SDF (a sphere of radius ~0.5): vertices on the iso-surface, every edge
+    shared by exactly two triangles, normals pointing out of the body; boundary evaluators against the oracle."""
+    import util_neus as U
+    from oracle import neus
+    sdf_kw, col_kw, ren_kw, _ = U.CASES["shipped"]
+    sconf, _, _ = U.confs_from_kw(sdf_kw, col_kw, ren_kw)
+    sp, cp = U.synth_state(sdf_kw, col_kw, 3, tame=False)
+    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda")
+    verts, tris = ren.extract_geometry([-1.01] * 3, [1.01] * 3, resolution=64, threshold=0.0)
+    assert verts.shape[0] > 500 and tris.shape[0] > 1000
+    s = neus.sdf_value(sp, sconf, torch.from_numpy(verts).float()).reshape(-1)
+    assert float(s.abs().max()) < 2e-3                      # linear interpolation on a 64^3 grid of a smooth field
+    e = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]])
+    key = np.sort(e, axis=1)
+    _, counts = np.unique(key[:, 0].astype(np.int64) * verts.shape[0] + key[:, 1], return_counts=True)
+    assert (counts == 2).all()
+    a, b, c = verts[tris[:, 0]], verts[tris[:, 1]], verts[tris[:, 2]]
+    n = np.cross(b - a, c - a)
+    assert ((n * (a + b + c)).sum(1) > 0).mean() > 0.999    # outward on a sphere centred at the origin
+    # SDFNetwork.forward / gradient (models/fields.py:72-107) against the oracle's autograd
+    pts = ((torch.rand(3000, 3) - 0.5) * 1.6)
+    out = sdf(pts.cuda()).cpu()
+    want = neus.sdf_forward(sp, sconf, pts)              # [P, d_out] = (sdf, features)
+    assert out.shape == (3000, sdf_kw["d_out"]) and U.rel_to_max(out, want) < 1e-5
+    assert U.rel_to_max(out[:, :1], neus.sdf_value(sp, sconf, pts)) < 1e-5
+    g = sdf.gradient(pts.cuda()).cpu()
+    p = pts.clone().requires_grad_(True)
+    (gw,) = torch.autograd.grad(neus.sdf_value(sp, sconf, p).sum(), p)
+    assert g.shape == (3000, 1, 3) and U.rel_to_max(g[:, 0], gw) < 1e-4
+    assert torch.equal(sdf.sdf_hidden_appearance(pts.cuda()).cpu(), out)
