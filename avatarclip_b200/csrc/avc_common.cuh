@@ -1,5 +1,6 @@
 // avc_common.cuh -- shared helpers for the sm_100a kernels of libavc_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -45,6 +46,29 @@ __device__ __forceinline__ float softplus100_d1(float z) {
   float e = expf(bz);
   return e / (e + 1.0f);
 }
+// softplus and softplus' of the same argument, sharing the exponential; branch free (the selects discard the inf / NaN
+// the discarded arm produces for large arguments).  FAST: SFU ex2 / lg2 / rcp;  else libm accuracy.
+template <bool FAST>
+__device__ __forceinline__ void softplus100_both(float z, float* h, float* d1) {
+  if (FAST) {
+    const float bz = z * kBeta;
+    const float e = __expf(bz);
+    const float t = 1.0f + e;
+    const bool big = bz > kThresh;
+    *h = big ? z : __logf(t) * (1.0f / kBeta);
+    *d1 = big ? 1.0f : __fdividef(e, t);
+  } else {
+    *h = softplus100(z);
+    *d1 = softplus100_d1(z);
+  }
+}
+
+// two floats -> packed bf16x2 bits (element 0 in the low half)
+__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);       // one F2FP.BF16.F32.PACK_AB
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

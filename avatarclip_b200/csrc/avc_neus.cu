@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "avc_chain.h"
 #include "avc_common.cuh"
 #include "avc_gemm_simt.cuh"
 #include "avc_gemm_tc.cuh"
@@ -159,8 +160,47 @@ EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
 // -------------------------------------------------------------------------------- value chain
 // in[0] (and the skip columns) must hold the encoding of Pn points.  stash: keep z[l].
 // Leaves in[L] ready; writes sdf[Pn] (thin) and, when want_feat, feat[Pn][Fp].
+// tcgen05 engine, no stash, no features (sample placement, sdf queries): the whole chain of a 128-point tile in ONE
+// kernel (avc_chain.cu), activations resident in shared memory.  Returns 1 when the fused kernel does not cover this
+// network shape (the caller then runs the layer-by-layer launches), 0 on success.
+int value_chain_fused(const NeusPlan& pl, const NeusWs& w, int64_t Pn, float* sdf_out, cudaStream_t st, int sdf_nz,
+                      int sdf_pitch) {
+  static int enabled = -1;      // AVC_FUSED_CHAIN=0: layer-by-layer launches (tuning / A-B knob)
+  if (enabled < 0) { const char* e = getenv("AVC_FUSED_CHAIN"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
+  if (!enabled || pl.L > chain::kMaxHidden) return 1;
+  chain::Args a;
+  memset(&a, 0, sizeof(a));
+  a.L = pl.L;
+  int n_skip = 0, ls = -1;
+  for (int l = 1; l <= pl.L; ++l)
+    if (pl.sdf[l].skip) { ++n_skip; ls = l; }
+  if (n_skip > 1) return 1;
+  for (int l = 0; l < pl.L; ++l) {
+    const LinDim& d = pl.sdf[l];
+    chain::Layer& y = a.lay[l];
+    y.w_hi = w.pk_hi + d.pk_W; y.w_lo = w.pk_lo + d.pk_W; y.ldw = d.Kp; y.N = d.N; y.K = d.K;
+    y.bias = w.pack + d.pk_b;
+    y.oscale = pl.sdf[l + 1].skip ? kSqrtHalf : 1.f;
+    y.next_skip_cols = (l + 1 < pl.L && pl.sdf[l + 1].skip) ? pl.E : 0;
+  }
+  a.a0_hi = w.in16[0].hi; a.a0_lo = w.in16[0].lo; a.ld0 = pl.sdf[0].Kp;
+  if (ls >= 0) {
+    a.skip_hi = w.in16[ls].hi; a.skip_lo = w.in16[ls].lo; a.skip_ld = pl.sdf[ls].Kp; a.skip_col0 = pl.sdf[ls].K - pl.E;
+  }
+  a.w_sdf = w.pack + pl.pk_wsdf; a.b_sdf = w.pack + pl.pk_bsdf; a.K_head = pl.sdf[pl.L].K;
+  a.head_skip_cols = pl.sdf[pl.L].skip ? pl.E : 0;
+  a.inv_scale = 1.0f / pl.cfg.sdf_scale;
+  a.sdf_out = sdf_out; a.nz = sdf_nz; a.pitch = sdf_pitch; a.P = Pn;
+  if (!chain::supported(a)) return 1;
+  return chain::launch(a, st);
+}
+
 int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, bool want_feat, float* sdf_out,
                 cudaStream_t st, int sdf_nz = 0, int sdf_pitch = 0) {
+  if (pl.cfg.engine == 1 && !stash && !want_feat) {
+    int r = value_chain_fused(pl, w, Pn, sdf_out, st, sdf_nz, sdf_pitch);
+    if (r != 1) return r;
+  }
   const float* pack = w.pack;
   for (int l = 0; l < pl.L; ++l) {
     const LinDim& d = pl.sdf[l];

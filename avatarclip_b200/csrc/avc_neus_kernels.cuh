@@ -31,10 +31,6 @@ __device__ __forceinline__ void split16_get4(uint2 hi, uint2 lo, float v[4]) {
 __device__ __forceinline__ float split16_get(const Split16& s, size_t row, int col) {
   return __bfloat162float(s.hi[row * s.ld + col]) + __bfloat162float(s.lo[row * s.ld + col]);
 }
-__device__ __forceinline__ uint32_t bf16x2_bits(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);       // one F2FP.BF16.F32.PACK_AB
-  return *reinterpret_cast<uint32_t*>(&t);
-}
 __device__ __forceinline__ void split16_put4(const Split16& s, size_t row, int col, const float v[4]) {
   if (!s.hi) return;
   const uint32_t h01 = bf16x2_bits(v[0], v[1]), h23 = bf16x2_bits(v[2], v[3]);
@@ -56,23 +52,6 @@ __device__ __forceinline__ float softplus100_d1_fast(float z) {
   float e = __expf(bz);
   return bz > kThresh ? 1.0f : __fdividef(e, e + 1.0f);
 }
-// softplus and softplus' of the same argument, sharing the exponential; branch free (the selects discard the inf / NaN
-// the discarded arm produces for large arguments).  FAST: SFU ex2 / lg2 / rcp;  else libm accuracy.
-template <bool FAST>
-__device__ __forceinline__ void softplus100_both(float z, float* h, float* d1) {
-  if (FAST) {
-    const float bz = z * kBeta;
-    const float e = __expf(bz);
-    const float t = 1.0f + e;
-    const bool big = bz > kThresh;
-    *h = big ? z : __logf(t) * (1.0f / kBeta);
-    *d1 = big ? 1.0f : __fdividef(e, t);
-  } else {
-    *h = softplus100(z);
-    *d1 = softplus100_d1(z);
-  }
-}
-
 // =============================================================================================
 // Weight packing: W = g * v / ||v||_row  (torch.nn.utils.weight_norm, models/fields.py:65-66,142-143)
 // One block per output row.  Destinations: up to two column segments, each written row-major

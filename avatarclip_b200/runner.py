@@ -106,6 +106,7 @@ class Runner:
         self.encoded_text = self.encoded_face_text = self.encoded_back_text = None
         self.v = self.f = None
         self._pending_optimizer_state = None
+        self.process_group, self.rank, self.world = None, 0, 1      # view-sharded multi-GPU: set_process_group()
         pretrain = c.get_string("train.pretrain", default=None)
         if pretrain is not None and os.path.exists(pretrain):
             logging.info("Load pretrain: %s", pretrain)
@@ -213,6 +214,15 @@ class Runner:
         self.v = torch.as_tensor(v, dtype=torch.float32).reshape(1, -1, 3).to(self.device)
         self.f = np.asarray(f.cpu() if torch.is_tensor(f) else f).astype(np.int64)
 
+    def set_process_group(self, pg):
+        """View-sharded data parallelism: rank r of N takes draw number step * N + r of the ONE seeded
+        stream (``StepSampler.draw_for_rank``), the flat gradient is all-reduced once per step inside the trainer."""
+        import torch.distributed as dist
+        self.process_group = pg
+        self.rank, self.world = (dist.get_rank(pg), dist.get_world_size(pg)) if pg is not None else (0, 1)
+        if self.trainer is not None:
+            self.trainer.pg, self.trainer.world = pg, self.world
+
     def _ensure_trainer(self):
         from .trainer import AppearanceTrainer
         if self.trainer is None:
@@ -221,7 +231,7 @@ class Runner:
             self.trainer = AppearanceTrainer(self.renderer, self.clip_tower, self.encoded_text, lr=self.learning_rate,
                                              igr_weight=self.igr_weight, mask_weight=self.mask_weight,
                                              clip_weight=1.0 if self.clip_weight is None else self.clip_weight,
-                                             device=self.device)
+                                             process_group=self.process_group, device=self.device)
             self.trainer.iter_step = self.iter_step
             if self._pending_optimizer_state is not None:      # checkpoint loaded before init_clip() (the CLI order)
                 self._load_optimizer_state_dict(self._pending_optimizer_state)
@@ -250,14 +260,15 @@ class Runner:
                                   camera_angle_x=2 * np.arctan(0.5 * self.dataset.W / self.dataset.focal))
         res_step = self.end_iter - self.iter_step
         texts = {"body": self.encoded_text, "face": self.encoded_face_text, "back": self.encoded_back_text}
-        pending = builder.submit(sampler.draw(0)) if builder is not None else None
+        draw = lambda i: sampler.draw_for_rank(i, self.rank, self.world)
+        pending = builder.submit(draw(0)) if builder is not None else None
         for iter_i in range(res_step):
             if iter_i == 30010 or (max_steps is not None and iter_i >= max_steps):      # main.py:346-347
                 break
             if builder is not None:
                 view = builder.finish(pending)
                 nxt = iter_i + 1
-                pending = builder.submit(sampler.draw(nxt)) if nxt < res_step else None    # lookahead: overlaps this step
+                pending = builder.submit(draw(nxt)) if nxt < res_step else None             # lookahead: overlaps this step
                 which = view.draw.prompt
                 if which == "back" and not self.use_back_prompt:
                     which = "body"

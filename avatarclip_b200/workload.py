@@ -258,3 +258,23 @@ def synthetic_body_mesh(n_lat: int = 24, n_lon: int = 32):
     v = np.concatenate(vs)
     v = np.stack([v[:, 0], -v[:, 2], v[:, 1]], 1)
     return v.astype(np.float32), np.asarray(fs, dtype=np.int32)
+
+
+SMPL_PARENTS = (-1, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21)
+
+
+def synthetic_smpl(V: int = 6890, seed: int = 0):
+    """SMPL-shaped random tensors for measurements (SMPL_NEUTRAL.pkl is licence-gated and absent): body-like
+    vertices, sparse skin weights (<= 4 joints per vertex, rows sum to 1), J_regressor rows summing to 1, small pose blend
+    shapes [207, 3V], the standard 24-joint parent table, a moderate pose [1, 72] (axis-angle)."""
+    g = torch.Generator().manual_seed(seed)
+    nj = len(SMPL_PARENTS)
+    v = torch.randn(V, 3, generator=g) * torch.tensor([0.25, 0.55, 0.12])
+    w = torch.zeros(V, nj)
+    w.scatter_add_(1, torch.randint(0, nj, (V, 4), generator=g), torch.rand(V, 4, generator=g) + 0.05)
+    w = w / w.sum(1, keepdim=True)
+    jr = torch.rand(nj, V, generator=g) ** 8
+    jr = jr / jr.sum(1, keepdim=True)
+    return dict(v_shaped=v[None], pose=torch.randn(1, nj * 3, generator=g) * 0.25,
+                posedirs=torch.randn((nj - 1) * 9, V * 3, generator=g) * 1e-3, J_regressor=jr,
+                parents=torch.tensor(SMPL_PARENTS, dtype=torch.long), lbs_weights=w)

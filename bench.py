@@ -552,6 +552,178 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (parity-test cases of the tier, benchable on request): --config 2 | 3 | 4
+# ------------------------------------------------------------------------------------------------------------------
+def run_other_config(args):
+    """configs[2]: full 224 x 224 views (50 176 rays each, chunked forward + recompute backward), `--batch-views B` views
+    accumulated per optimiser step and sharded over the ranks (B = world: weak scaling, one view per GPU; B = 8 fixed:
+    strong scaling of an 8-view batch).  configs[3]: configs[1] + SMPL linear-blend skinning of the 6890-vertex template
+    inside every step.  configs[4]: the real train_clip loop (Runner, shipped-size nets, per-step camera draw + template
+    raster + silhouette rays on the device, ~max_ray_num rays), throughput + final CLIP cosine."""
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    real_stdout = StdoutToStderr()
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", os.environ.get("AVC_NCCL_DEBUG", "INFO"))
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    from avatarclip_b200.trainer import AppearanceTrainer, DeviceView
+    K, Wm = args.steps, args.warmup
+    cfg = args.config
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    extra = {}
+    if cfg in (2, 3):
+        sp, cp, clip_sd, text, ren, tower = build_world(device, args.engine)
+        tr = AppearanceTrainer(ren, tower, text, lr=5e-4, process_group=pg, device=device)
+        if cfg == 2:
+            B = args.batch_views if args.batch_views > 0 else world
+            if B % world:
+                raise SystemExit("--batch-views must be a multiple of the number of ranks")
+            per_rank = B // world
+            n_rays = CANVAS * CANVAS
+            views = [DeviceView(WL.make_view(rank * per_rank + i, n_rays=n_rays, H=CANVAS, W=CANVAS, seed=0, bg_choice=3,
+                                             radius=1.5), device) for i in range(per_rank)]
+
+            def step(i):
+                acc = None
+                for v in views:                                  # gradient accumulation over this rank's views
+                    g = tr.forward_backward(v)
+                    acc = g.clone() if (acc is None and per_rank > 1) else (g if acc is None else acc.add_(g))
+                if acc is not tr.grad:
+                    tr.grad.copy_(acc)
+                tr.optimizer_step()
+            units = B
+            workload = (f"BASELINE configs[2]: {B} views x 224x224 = {n_rays} rays each x (64+64) samples per optimiser step, "
+                        f"8x256 SDF + 4x256 colour, CLIP loss per view, chunked render (4096-ray chunks, backward recompute); "
+                        f"{per_rank} view(s) per GPU, gradients accumulated then all-reduced")
+            scaling = "strong" if args.batch_views > 0 else "weak"
+            metric, unit = "appearance-optim views/sec (224x224 full views, CLIP loss)", "views/s"
+        else:
+            from avatarclip_b200.lbs import my_lbs
+            smpl = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in WL.synthetic_smpl().items()}
+            views = [DeviceView(WL.make_view(rank + world * i, n_rays=N_RAYS, H=CANVAS, W=CANVAS, seed=0, bg_choice=3), device)
+                     for i in range(8)]
+
+            def step(i):
+                verts, _ = my_lbs(smpl["v_shaped"], smpl["pose"], None, None, smpl["posedirs"], smpl["J_regressor"],
+                                  smpl["parents"], smpl["lbs_weights"], pose2rot=True)
+                extra["verts_checksum"] = verts
+                tr.step(views[i % 8])
+            units = world
+            workload = ("BASELINE configs[3]: configs[1] step + avc_lbs_fwd (my_lbs, 6890-vertex template, 24 joints, "
+                        "synthetic SMPL tensors) inside every step; 1 view per GPU per step")
+            scaling, metric, unit = "weak", METRIC + " + LBS per step", "steps/s"
+    else:
+        import tempfile
+        from avatarclip_b200.runner import Runner
+        tmp = tempfile.mkdtemp(prefix="avc_cfg4_")
+        conf = f"""
+general {{ base_exp_dir = {tmp}/exp }}
+dataset {{ data_dir = {tmp}/none }}
+train {{ learning_rate = 5e-4
+  learning_rate_alpha = 0.05
+  end_iter = 100000
+  batch_size = 512
+  warm_up_end = 500
+  anneal_end = 0
+  save_freq = 100000
+  val_freq = 100000
+  val_mesh_freq = 100000
+  report_freq = 100000
+  igr_weight = 0.1
+  mask_weight = 0.5
+  clip_weight = 1.0
+  add_no_texture = True
+  texture_cast_light = True
+  use_face_prompt = True
+  use_back_prompt = True
+  use_silhouettes = True
+  seed = 1000 }}
+clip {{ prompt = a 3D rendering of the Iron Man in unreal engine }}
+model {{
+  sdf_network {{ d_out = 257, d_in = 3, d_hidden = 256, n_layers = 4, skip_in = [4], multires = 6, bias = 0.5, scale = 1.0, geometric_init = True, weight_norm = True }}
+  variance_network {{ init_val = 0.3 }}
+  rendering_network {{ d_feature = 256, mode = no_view_dir, d_in = 6, d_out = 3, d_hidden = 256, n_layers = 2, weight_norm = True, multires_view = 0, squeeze_out = True, extra_color = True }}
+  neus_renderer {{ n_samples = 32, n_importance = 32, n_outside = 0, up_sample_steps = 4, perturb = 1.0, extra_color = True }}
+}}"""
+        cpath = os.path.join(tmp, "ironman_like.conf")
+        open(cpath, "w").write(conf)
+        r = Runner(cpath, mode="train_clip", case="smpl", device=str(device), engine=args.engine)
+        g = torch.Generator().manual_seed(5)
+        r.init_clip(WL.random_vit_state(seed=0), torch.randn(1, 512, generator=g), torch.randn(1, 512, generator=g),
+                    torch.randn(1, 512, generator=g))
+        v, f = WL.synthetic_body_mesh()
+        r.init_smpl(v, f)
+        r.set_process_group(pg)
+        state = {"done": 0}
+
+        def step(i):
+            pass
+        units = world
+        workload = ("BASELINE configs[4]-like: Runner.train_clip real loop, shipped-size nets (4x256 + 2x256, 32+32 samples), "
+                    "max_ray_num 12544 (~11-12.5 k silhouette rays / step), per-step camera draw + template raster + "
+                    "dilation + canvas + rays on the device with one-step lookahead, face/back prompts, bg augmentation; "
+                    "synthetic body mesh, seeded random CLIP weights (stand-ins for the licence-gated assets)")
+        scaling, metric, unit = "weak", "appearance-optim steps/sec (real train_clip loop, ~12 k rays x 64 samples, CLIP loss)", "steps/s"
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    if cfg == 4:
+        r.train_clip(max_steps=Wm, log=lambda m: None, validate=False)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev[0].record()
+        r.train_clip(max_steps=K, log=lambda m: None, validate=False)
+        ev[1].record()
+        barrier()
+        extra["final_clip_cosine"] = [float(x) for x in r.trainer.cos]
+        extra["rays_last_step"] = int(r.trainer._out["weights"].shape[0])
+    else:
+        for i in range(Wm):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev[0].record()
+        for i in range(K):
+            step(i)
+        ev[1].record()
+        barrier()
+    ms = ev[0].elapsed_time(ev[1])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=device)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        line = {"metric": metric, "value": units * K / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f32" if args.engine == 0 else "bf16x3(split)->f32", "data": "synthetic",
+                "config": {"workload": workload, "baseline_config": cfg, "parallelism": f"view-sharded dp{world}" if world > 1 else "single",
+                           "launch": "eager C-ABI calls", "l2": "working set >> 126 MB L2"},
+                "clocks": clocks, "last_loss": float(tr.loss_value()) if cfg in (2, 3) else float(r.trainer.loss_value())}
+        for k, v in extra.items():
+            if not torch.is_tensor(v):
+                line[k] = v
+        real_stdout.emit(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -562,6 +734,10 @@ def main():
                     help="MLP contraction engine: 1 = tcgen05 split-bf16 tiles (default), 0 = fp32 FFMA tiles")
     ap.add_argument("--graph", type=int, default=int(os.environ.get("AVC_GRAPH", "1")),
                     help="1: replay the step as one captured CUDA graph (default); 0: eager C-ABI calls")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4],
+                    help="BASELINE.json configs index (default 1 = the headline config; 2, 3, 4: see run_other_config)")
+    ap.add_argument("--batch-views", type=int, default=0,
+                    help="--config 2: views per optimiser step over ALL ranks (0: one per rank = weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true",
                     help="skip the cpu_baseline / parity / ref_gpu legs (kernel experiments)")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds the cpu_baseline leg may spend on steps")
@@ -574,7 +750,10 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
-        run_native(args)
+        if args.config != 1:
+            run_other_config(args)
+        else:
+            run_native(args)
 
 
 if __name__ == "__main__":

@@ -136,14 +136,15 @@ def test_extract_geometry_sphere_is_watertight_and_outward(tmp_path):
     shared by exactly two triangles, normals pointing out of the body; boundary evaluators against the oracle."""
     import util_neus as U
     from oracle import neus
-    sdf_kw, col_kw, ren_kw, _ = U.CASES["shipped"]
+    sdf_kw, col_kw, ren_kw, _ = U.CASES["b2"]            # untamed geometric init of the 8x256 net: |x| - 0.5, smooth
     sconf, _, _ = U.confs_from_kw(sdf_kw, col_kw, ren_kw)
     sp, cp = U.synth_state(sdf_kw, col_kw, 3, tame=False)
-    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda")
+    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda", engine=1)
     verts, tris = ren.extract_geometry([-1.01] * 3, [1.01] * 3, resolution=64, threshold=0.0)
     assert verts.shape[0] > 500 and tris.shape[0] > 1000
     s = neus.sdf_value(sp, sconf, torch.from_numpy(verts).float()).reshape(-1)
-    assert float(s.abs().max()) < 2e-3                      # linear interpolation on a 64^3 grid of a smooth field
+    assert float(s.abs().max()) < 2e-3      # linear interpolation on a 64^3 grid (measured on the CPU field: 1.1e-3)
+    assert abs(float(np.linalg.norm(verts, axis=1).mean()) - 0.5) < 0.01
     e = np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]])
     key = np.sort(e, axis=1)
     _, counts = np.unique(key[:, 0].astype(np.int64) * verts.shape[0] + key[:, 1], return_counts=True)
