@@ -252,9 +252,13 @@ k_sdf_chain(const __grid_constant__ Maps maps, const __grid_constant__ DevArgs a
           }
           fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
         } else {
-          // sdf head: partial dots of the 4 column groups meet in shared memory
-          if (64 * cw < ly.N) atomicAdd(&sdf_acc[row], dot);
-          named_bar_sync(1, 32 * kEW);
+          // sdf head: the partial dots of the 4 column groups are added in a FIXED order (group 0, 1, 2, 3), so the
+          // result does not depend on warp scheduling (sample placement is discontinuous in the sdf: bit-stable runs)
+#pragma unroll 1
+          for (int k = 0; k < 4; ++k) {
+            if (cw == k && 64 * cw < ly.N) sdf_acc[row] += dot;
+            named_bar_sync(1, 32 * kEW);
+          }
           if (cw == 0) {
             float s = sdf_acc[row];
             sdf_acc[row] = 0.f;

@@ -11,6 +11,9 @@
 // cannot fill the SMs, and every kernel issues all its global loads in one batch.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "avc_common.cuh"
 
 using namespace avc;
@@ -38,6 +41,35 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
 
 
 
+
+// ------------------------------------------------------------------------------------------------
+// Execution contexts.  Every kernel body below is a device function template over a context `c` that supplies the
+// (virtual) block index, the thread index / count of the (sub-)CTA, its barrier and its shared memory:
+//   HwCtx   one hardware CTA per virtual block (the stand-alone, programmatic-dependent-launch chained kernels);
+//   SubCtx  a slice of a persistent 512-thread CTA (avc_clip_mega: the whole pass as ONE cooperative kernel whose
+//           stages are separated by grid-wide barriers): 128-thread GEMM tiles run four to a CTA on named barriers.
+// ------------------------------------------------------------------------------------------------
+struct HwCtx {
+  int bx, by, bz, tid, nt;
+  unsigned char* smem;
+  int early;      // GEMM: release the dependent kernel at the top (tuning knob) instead of after the main loop
+  __device__ __forceinline__ HwCtx(unsigned char* sm = nullptr, int early_ = 0)
+      : bx(blockIdx.x), by(blockIdx.y), bz(blockIdx.z), tid(threadIdx.x), nt(blockDim.x), smem(sm), early(early_) {}
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ void gemm_top() const { if (early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+  __device__ __forceinline__ void gemm_wait() const { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+  __device__ __forceinline__ void gemm_tail() const { if (!early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+};
+struct SubCtx {
+  int bx, by, bz, tid, nt;
+  unsigned char* smem;
+  int bar;        // named barrier of this sub-CTA (1 ..), bar.sync over nt threads
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory"); }
+  __device__ __forceinline__ void gemm_top() const {}
+  __device__ __forceinline__ void gemm_wait() const {}
+  __device__ __forceinline__ void gemm_tail() const {}
+};
+
 // ------------------------------------------------------------------------------------------------
 // fp16 tensor-core GEMM  C[M,N] = A[M,K] . W[N,K]^T  (mma.sync m16n8k16, fp32 accumulate).
 // CTA: 128 threads, tile 64 x 32, BK = 64, 6-stage cp.async pipeline, grid (N/32, ceil(M/64), ksplit).
@@ -56,20 +88,19 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <typename Epi>
-__global__ void __launch_bounds__(128)
-k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
-         int k_per_split, Epi epi, int early_trigger) {
-  // early_trigger: let the successor kernel start launching at once.  Otherwise it is released after the main loop,
-  // so that its CTAs (which only spin in griddepcontrol.wait) do not take SM slots from this kernel's later waves.
-  if (early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  extern __shared__ __align__(16) unsigned char g_smem[];
+template <int STG, typename Epi, class C>
+__device__ __forceinline__ void d_gemm16(const C& K_, const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw,
+                                         int M, int N, int K, int k_per_split, const Epi& epi) {
+  // stand-alone kernels: the successor is released after the main loop (or at the top, knob), so that its CTAs (which
+  // only spin in griddepcontrol.wait) do not take SM slots from this kernel's later waves
+  K_.gemm_top();
+  unsigned char* g_smem = K_.smem;
   __half (*sA)[GBM][GBK + GPAD] = reinterpret_cast<__half (*)[GBM][GBK + GPAD]>(g_smem);
   __half (*sW)[GBN][GBK + GPAD] =
-      reinterpret_cast<__half (*)[GBN][GBK + GPAD]>(g_smem + (size_t)GST * GBM * (GBK + GPAD) * 2);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = blockIdx.x * GBN, m0 = blockIdx.y * GBM;
-  const int kb = blockIdx.z * k_per_split;
+      reinterpret_cast<__half (*)[GBN][GBK + GPAD]>(g_smem + (size_t)STG * GBM * (GBK + GPAD) * 2);
+  const int tid = K_.tid, lane = tid & 31, warp = tid >> 5;
+  const int n0 = K_.bx * GBN, m0 = K_.by * GBM;
+  const int kb = K_.bz * k_per_split;
   const int ke = min(K, kb + k_per_split);
   const int nk = (ke - kb + GBK - 1) / GBK;
 
@@ -104,8 +135,8 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
 
   // (Streaming the constant weight stages in before griddepcontrol.wait was measured: no gain forward, 0.1 ms slower
   // backward -- the first MMA then waits for five weight stages instead of one.)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  for (int s = 0; s < GST - 1; ++s) {
+  K_.gemm_wait();
+  for (int s = 0; s < STG - 1; ++s) {
     if (s < nk) issue(s, s);
     cp_async_commit();
   }
@@ -116,15 +147,15 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int col = n0 + t * 8 + (lane & 3) * 2;
-    epre[t][0] = (er0 < M) ? epi.prefetch(er0, col, (int)blockIdx.z) : make_float2(0.f, 0.f);
-    epre[t][1] = (er0 + 8 < M) ? epi.prefetch(er0 + 8, col, (int)blockIdx.z) : make_float2(0.f, 0.f);
+    epre[t][0] = (er0 < M) ? epi.prefetch(er0, col, (int)K_.bz) : make_float2(0.f, 0.f);
+    epre[t][1] = (er0 + 8 < M) ? epi.prefetch(er0 + 8, col, (int)K_.bz) : make_float2(0.f, 0.f);
   }
   for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<GST - 2>();
-    __syncthreads();
-    if (kt + GST - 1 < nk) issue(kt + GST - 1, (kt + GST - 1) % GST);
+    cp_async_wait<STG - 2>();
+    K_.sync();
+    if (kt + STG - 1 < nk) issue(kt + STG - 1, (kt + STG - 1) % STG);
     cp_async_commit();
-    const int st = kt % GST;
+    const int st = kt % STG;
 #pragma unroll
     for (int kk = 0; kk < GBK; kk += 16) {
       unsigned a[4];
@@ -152,14 +183,23 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
     }
   }
   cp_async_wait<0>();
-  if (!early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  K_.gemm_tail();
   const int r0 = m0 + warp * 16 + (lane >> 2);
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     int col = n0 + t * 8 + (lane & 3) * 2;
-    if (r0 < M) epi(r0, col, acc[t][0], acc[t][1], (int)blockIdx.z, epre[t][0]);
-    if (r0 + 8 < M) epi(r0 + 8, col, acc[t][2], acc[t][3], (int)blockIdx.z, epre[t][1]);
+    if (r0 < M) epi(r0, col, acc[t][0], acc[t][1], (int)K_.bz, epre[t][0]);
+    if (r0 + 8 < M) epi(r0 + 8, col, acc[t][2], acc[t][3], (int)K_.bz, epre[t][1]);
   }
+}
+
+
+template <typename Epi>
+__global__ void __launch_bounds__(128)
+k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, int ldw, int M, int N, int K,
+         int k_per_split, Epi epi, int early_trigger) {
+  extern __shared__ __align__(16) unsigned char g_smem_hw[];
+  d_gemm16<GST>(HwCtx(g_smem_hw, early_trigger), A, lda, Wt, ldw, M, N, K, k_per_split, epi);
 }
 
 template <typename Epi>
@@ -271,10 +311,10 @@ __device__ __forceinline__ ResizeTap resize_tap(int dst, float scale, int in) {
   return t;
 }
 
-__global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int B, int IS, int P,
+template <class C>
+__device__ __forceinline__ void d_preprocess(const C& K_, const float* __restrict__ canvas, int H, int W, int B, int IS, int P,
                              __half* __restrict__ a0, int mode) {
-  pdl_enter();
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = (int64_t)K_.bx * K_.nt + K_.tid;
   int64_t tot = (int64_t)B * 3 * IS * IS;
   if (i >= tot) return;
   int x = (int)(i % IS); int64_t r = i / IS;
@@ -298,12 +338,17 @@ __global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int
   int col = c * P * P + (y % P) * P + (x % P);
   a0[((size_t)b * g * g + patch) * (3 * P * P) + col] = __float2half_rn(v);
 }
+__global__ void k_preprocess(const float* __restrict__ canvas, int H, int W, int B, int IS, int P,
+                             __half* __restrict__ a0, int mode) {
+  pdl_enter();
+  d_preprocess(HwCtx(), canvas, H, W, B, IS, P, a0, mode);
+}
 
 // adjoint: d canvas += bilinear^T ( d img / std ), d img read from the im2col gradient
-__global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W, int B, int IS, int P,
+template <class C>
+__device__ __forceinline__ void d_preprocess_bwd(const C& K_, const float* __restrict__ dpatch, int H, int W, int B, int IS, int P,
                                  float* __restrict__ dcanvas, int mode) {
-  pdl_enter();
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t i = (int64_t)K_.bx * K_.nt + K_.tid;
   int64_t tot = (int64_t)B * 3 * IS * IS;
   if (i >= tot) return;
   int x = (int)(i % IS); int64_t r = i / IS;
@@ -322,15 +367,25 @@ __global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W,
   add(ty.i1, tx.i0, ty.l * (1.f - tx.l));
   add(ty.i1, tx.i1, ty.l * tx.l);
 }
+__global__ void k_preprocess_bwd(const float* __restrict__ dpatch, int H, int W, int B, int IS, int P,
+                                 float* __restrict__ dcanvas, int mode) {
+  pdl_enter();
+  d_preprocess_bwd(HwCtx(), dpatch, H, W, B, IS, P, dcanvas, mode);
+}
 
 // token buffer initialisation: row 0 = class_embedding + pos[0], rows 1.. = pos[t] (the patch GEMM adds onto them)
-__global__ void k_cls_rows(const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
+template <class C>
+__device__ __forceinline__ void d_cls_rows(const C& K_, const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
                            float* __restrict__ x) {
-  pdl_enter();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = K_.bx * K_.nt + K_.tid;
   if (i >= B * T * Wd) return;
   int c = i % Wd, t = (i / Wd) % T;
   x[i] = pos[(size_t)t * Wd + c] + (t == 0 ? cls[c] : 0.f);
+}
+__global__ void k_cls_rows(const float* __restrict__ cls, const float* __restrict__ pos, int B, int T, int Wd,
+                           float* __restrict__ x) {
+  pdl_enter();
+  d_cls_rows(HwCtx(), cls, pos, B, T, Wd, x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -339,13 +394,12 @@ __global__ void k_cls_rows(const float* __restrict__ cls, const float* __restric
 // Rows are cached in registers (Wd <= 32 * kLnMax): one round trip to memory per operand instead of one per pass.
 constexpr int kLnMax = 32;
 
-__global__ void __launch_bounds__(256)
-k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
+template <class C>
+__device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
             float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
-  pdl_enter();
-  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int row = K_.bx * (K_.nt >> 5) + (K_.tid >> 5);
   if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = K_.tid & 31;
   const float* xr = x + (size_t)row * Wd;
   float xv[kLnMax], gv[kLnMax], bv[kLnMax];      // gamma / beta are fetched with the row, not after the reductions
   float s = 0.f;
@@ -372,17 +426,22 @@ k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict_
     }
   }
 }
+__global__ void __launch_bounds__(256)
+k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
+            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
+  pdl_enter();
+  d_layernorm(HwCtx(), x, M, Wd, g, b, y32, y16, save_x);
+}
 
 // dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); optionally also the row-scaled fp16
 // copy of the updated dx row (operand of the next input-gradient GEMM)
-__global__ void __launch_bounds__(256)
-k_layernorm_bwd(const float* __restrict__ x, float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
+template <class C>
+__device__ __forceinline__ void d_layernorm_bwd(const C& K_, const float* __restrict__ x, float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
                 float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx,
                 __half* __restrict__ dx16, float* __restrict__ dx_scale, int zero_dy) {
-  pdl_enter();
-  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int row = K_.bx * (K_.nt >> 5) + (K_.tid >> 5);
   if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = K_.tid & 31;
   const float* xr = x + (size_t)row * row_stride_x;
   float* dr = dy + (size_t)row * row_stride_dy;
   float* o = dx + (size_t)row * row_stride_dx;
@@ -435,16 +494,22 @@ k_layernorm_bwd(const float* __restrict__ x, float* __restrict__ dy, int M, int 
     if (lane == 0) dx_scale[row] = sc;
   }
 }
+__global__ void __launch_bounds__(256)
+k_layernorm_bwd(const float* __restrict__ x, float* __restrict__ dy, int M, int Wd, const float* __restrict__ g,
+                float* __restrict__ dx, int accumulate, int row_stride_x, int row_stride_dy, int row_stride_dx,
+                __half* __restrict__ dx16, float* __restrict__ dx_scale, int zero_dy) {
+  pdl_enter();
+  d_layernorm_bwd(HwCtx(), x, dy, M, Wd, g, dx, accumulate, row_stride_x, row_stride_dy, row_stride_dx, dx16, dx_scale, zero_dy);
+}
 
 // fp32 -> fp16 with a per-row power-of-two scale so that max|row| lands in [1,2): keeps tiny
 // gradients out of the fp16 subnormal range.  scale[row] is undone in the consuming GEMM's epilogue.
-__global__ void __launch_bounds__(256)
-k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __half* __restrict__ dst,
+template <class C>
+__device__ __forceinline__ void d_to_half_rowscaled(const C& K_, const float* __restrict__ src, int M, int N, int ld_src, __half* __restrict__ dst,
                     float* __restrict__ scale, const int* __restrict__ row_map) {
-  pdl_enter();
-  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int row = K_.bx * (K_.nt >> 5) + (K_.tid >> 5);
   if (row >= M) return;
-  const int lane = threadIdx.x & 31;
+  const int lane = K_.tid & 31;
   const float* s = src + (size_t)(row_map ? row_map[row] : row) * ld_src;
   // Rows up to 32 * 4 * kRsMax = 2304 floats (3 x 768, the widest operand) are held in registers: ONE batch of
   // independent 16-byte loads instead of a loop of dependent round trips, and no second pass over memory.
@@ -488,6 +553,12 @@ k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __h
   }
   if (lane == 0) scale[row] = sc;
 }
+__global__ void __launch_bounds__(256)
+k_to_half_rowscaled(const float* __restrict__ src, int M, int N, int ld_src, __half* __restrict__ dst,
+                    float* __restrict__ scale, const int* __restrict__ row_map) {
+  pdl_enter();
+  d_to_half_rowscaled(HwCtx(), src, M, N, ld_src, dst, scale, row_map);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Attention, one CTA per (image, head): T <= 64 tokens, head dim 64.  fp32 throughout.
@@ -501,22 +572,21 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
-__global__ void __launch_bounds__(512)
-k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
-  pdl_enter();
-  extern __shared__ __align__(16) float sm[];
+template <class C>
+__device__ __forceinline__ void d_attention(const C& K_, const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
+  float* sm = reinterpret_cast<float*>(K_.smem);
   float* q = sm;                  // [T][AP]
   float* k = q + AT * AP;
   float* v = k + AT * AP;
   float* S = v + AT * AP;         // [T][AT+1]
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int b = K_.bx / heads, h = K_.bx % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
   {   // all global loads of the thread first (one latency, not one per loop trip), then the shared-memory stores
     constexpr int NIT = (AT * (AD / 4) + 511) / 512;
     float4 rq[NIT], rk[NIT], rv[NIT];
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
-      const int i = threadIdx.x + j * 512;
+      const int i = K_.tid + j * 512;
       if (i < T * (AD / 4)) {
         const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
         const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
@@ -527,7 +597,7 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
     }
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
-      const int i = threadIdx.x + j * 512;
+      const int i = K_.tid + j * 512;
       if (i < T * (AD / 4)) {
         const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
         *reinterpret_cast<float4*>(q + t * AP + d) = rq[j];
@@ -536,8 +606,8 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
       }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+  K_.sync();
+  for (int i = K_.tid; i < T * T; i += K_.nt) {
     int a = i / T, c = i % T;
     float s = 0.f;
 #pragma unroll
@@ -545,9 +615,9 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
       s = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), s);
     S[a * (AT + 1) + c] = s * 0.125f;          // 1/sqrt(64)
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
+  K_.sync();
+  const int lane = K_.tid & 31, warp = K_.tid >> 5;
+  for (int a = warp; a < T; a += (K_.nt >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, S[a * (AT + 1) + c]);
 #pragma unroll
@@ -558,8 +628,8 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
     float inv = 1.f / sum;
     for (int c = lane; c < T; c += 32) S[a * (AT + 1) + c] *= inv;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+  K_.sync();
+  for (int i = K_.tid; i < T * (AD / 4); i += K_.nt) {
     int a = i / (AD / 4), d = (i % (AD / 4)) * 4;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < T; ++c) {
@@ -573,27 +643,32 @@ k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __r
     *reinterpret_cast<uint2*>(o16 + ((size_t)b * T + a) * Wd + h * AD + d) = pk;
   }
 }
+__global__ void __launch_bounds__(512)
+k_attention(const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char dyn_smem_hw[];
+  d_attention(HwCtx(dyn_smem_hw), qkv, T, Wd, heads, o16);
+}
 
 // backward: recompute P; dqkv[M][3W] fp32 from dO[M][W] fp32
-__global__ void __launch_bounds__(512)
-k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
+template <class C>
+__device__ __forceinline__ void d_attention_bwd(const C& K_, const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
                 float* __restrict__ dqkv) {
-  pdl_enter();
-  extern __shared__ __align__(16) float sm[];
+  float* sm = reinterpret_cast<float*>(K_.smem);
   float* q = sm;
   float* k = q + AT * AP;
   float* v = k + AT * AP;
   float* dO_s = v + AT * AP;
   float* Pm = dO_s + AT * AP;           // [T][AT+1]
   float* dS = Pm + AT * (AT + 1);
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int b = K_.bx / heads, h = K_.bx % heads;
   const float* base = qkv + (size_t)b * T * 3 * Wd;
   {   // all global loads first, then the shared-memory stores (see k_attention)
     constexpr int NIT = (AT * (AD / 4) + 511) / 512;
     float4 rq[NIT], rk[NIT], rv[NIT], ro[NIT];
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
-      const int i = threadIdx.x + j * 512;
+      const int i = K_.tid + j * 512;
       if (i < T * (AD / 4)) {
         const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
         const float* r = base + (size_t)t * 3 * Wd + h * AD + d;
@@ -605,7 +680,7 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
     }
 #pragma unroll
     for (int j = 0; j < NIT; ++j) {
-      const int i = threadIdx.x + j * 512;
+      const int i = K_.tid + j * 512;
       if (i < T * (AD / 4)) {
         const int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
         *reinterpret_cast<float4*>(q + t * AP + d) = rq[j];
@@ -615,8 +690,8 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
       }
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+  K_.sync();
+  for (int i = K_.tid; i < T * T; i += K_.nt) {
     int a = i / T, c = i % T;
     float s = 0.f, dp = 0.f;
 #pragma unroll
@@ -627,9 +702,9 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
     Pm[a * (AT + 1) + c] = s * 0.125f;
     dS[a * (AT + 1) + c] = dp;               // dP for now
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int a = warp; a < T; a += (blockDim.x >> 5)) {
+  K_.sync();
+  const int lane = K_.tid & 31, warp = K_.tid >> 5;
+  for (int a = warp; a < T; a += (K_.nt >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, Pm[a * (AT + 1) + c]);
 #pragma unroll
@@ -642,9 +717,9 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
     dot = warp_sum(dot);
     for (int c = lane; c < T; c += 32) dS[a * (AT + 1) + c] = Pm[a * (AT + 1) + c] * (dS[a * (AT + 1) + c] - dot) * 0.125f;
   }
-  __syncthreads();
+  K_.sync();
   float* dbase = dqkv + (size_t)b * T * 3 * Wd;
-  for (int i = threadIdx.x; i < T * (AD / 4); i += blockDim.x) {
+  for (int i = K_.tid; i < T * (AD / 4); i += K_.nt) {
     int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
     float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
     for (int c = 0; c < T; ++c) {
@@ -662,47 +737,53 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
     *reinterpret_cast<float4*>(r + 2 * Wd) = dv;
   }
 }
+__global__ void __launch_bounds__(512)
+k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int T, int Wd, int heads,
+                float* __restrict__ dqkv) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char dyn_smem_hw[];
+  d_attention_bwd(HwCtx(dyn_smem_hw), qkv, dO, T, Wd, heads, dqkv);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Head: ln_post(x[b,0]) @ proj -> emb ; cosine with the text embedding.  One CTA per image.
 // ------------------------------------------------------------------------------------------------
 // ln_post(x[b,0]) @ proj: grid (B, OD/64); every CTA recomputes the (cheap) LayerNorm of the cls row and produces 64
 // outputs, each from 4 partial dots over a quarter of the 768 inputs.
-__global__ void __launch_bounds__(256)
-k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
+template <class C>
+__device__ __forceinline__ void d_head_proj(const C& K_, const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
             const float* __restrict__ proj, int OD, float* __restrict__ emb, float* __restrict__ ynorm) {
-  pdl_enter();
-  extern __shared__ float sm[];
+  float* sm = reinterpret_cast<float*>(K_.smem);
   float* y = sm;               // [Wd]
   float* part = y + Wd;        // [4][64]
   __shared__ float red[8];
-  const int b = blockIdx.x;
+  const int b = K_.bx;
   const float* xr = x + (size_t)b * T * Wd;
   float s = 0.f;
-  for (int c = threadIdx.x; c < Wd; c += blockDim.x) s += xr[c];
+  for (int c = K_.tid; c < Wd; c += K_.nt) s += xr[c];
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
+  if ((K_.tid & 31) == 0) red[K_.tid >> 5] = s;
+  K_.sync();
   float mean = 0.f;
   for (int i = 0; i < 8; ++i) mean += red[i];
   mean /= (float)Wd;
   float v = 0.f;
-  for (int c = threadIdx.x; c < Wd; c += blockDim.x) { float d = xr[c] - mean; v += d * d; }
+  for (int c = K_.tid; c < Wd; c += K_.nt) { float d = xr[c] - mean; v += d * d; }
   v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  K_.sync();
+  if ((K_.tid & 31) == 0) red[K_.tid >> 5] = v;
+  K_.sync();
   float var = 0.f;
   for (int i = 0; i < 8; ++i) var += red[i];
   float rstd = rsqrtf(var / (float)Wd + 1e-5f);
-  for (int c = threadIdx.x; c < Wd; c += blockDim.x) {
+  for (int c = K_.tid; c < Wd; c += K_.nt) {
     float yy = (xr[c] - mean) * rstd * g[c] + bta[c];
     y[c] = yy;
-    if (blockIdx.y == 0) ynorm[(size_t)b * Wd + c] = yy;
+    if (K_.by == 0) ynorm[(size_t)b * Wd + c] = yy;
   }
-  __syncthreads();
-  const int ol = threadIdx.x & 63, pt = threadIdx.x >> 6;
-  const int o = blockIdx.y * 64 + ol;
+  K_.sync();
+  const int ol = K_.tid & 63, pt = K_.tid >> 6;
+  const int o = K_.by * 64 + ol;
   const int c0 = pt * (Wd / 4), c1 = c0 + Wd / 4;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (o < OD) {
@@ -716,121 +797,148 @@ k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict_
     for (; c < c1; ++c) a0 = fmaf(y[c], proj[(size_t)c * OD + o], a0);
   }
   part[pt * 64 + ol] = (a0 + a1) + (a2 + a3);
-  __syncthreads();
+  K_.sync();
   if (pt == 0 && o < OD) emb[(size_t)b * OD + o] = (part[ol] + part[64 + ol]) + (part[128 + ol] + part[192 + ol]);
+}
+__global__ void __launch_bounds__(256)
+k_head_proj(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ bta,
+            const float* __restrict__ proj, int OD, float* __restrict__ emb, float* __restrict__ ynorm) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char dyn_smem_hw[];
+  d_head_proj(HwCtx(dyn_smem_hw), x, T, Wd, g, bta, proj, OD, emb, ynorm);
 }
 
 // cosine(emb[b], text[b]); torch.cosine_similarity: x.y / max(||x|| * ||y||, 1e-8)
-__global__ void __launch_bounds__(256)
-k_cosine(const float* __restrict__ emb, const float* __restrict__ text, int OD, float* __restrict__ cos_out) {
-  pdl_enter();
+template <class C>
+__device__ __forceinline__ void d_cosine(const C& K_, const float* __restrict__ emb, const float* __restrict__ text, int OD, float* __restrict__ cos_out) {
   __shared__ float red[3][8];
-  const int b = blockIdx.x;
+  const int b = K_.bx;
   float ee = 0.f, tt = 0.f, et = 0.f;
-  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+  for (int o = K_.tid; o < OD; o += K_.nt) {
     float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
     ee += a * a; tt += t * t; et += a * t;
   }
   ee = warp_sum(ee); tt = warp_sum(tt); et = warp_sum(et);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ee; red[1][threadIdx.x >> 5] = tt; red[2][threadIdx.x >> 5] = et; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if ((K_.tid & 31) == 0) { red[0][K_.tid >> 5] = ee; red[1][K_.tid >> 5] = tt; red[2][K_.tid >> 5] = et; }
+  K_.sync();
+  if (K_.tid == 0) {
     float a = 0.f, t = 0.f, c = 0.f;
     for (int i = 0; i < 8; ++i) { a += red[0][i]; t += red[1][i]; c += red[2][i]; }
     cos_out[b] = c / fmaxf(sqrtf(a) * sqrtf(t), 1e-8f);
   }
 }
+__global__ void __launch_bounds__(256)
+k_cosine(const float* __restrict__ emb, const float* __restrict__ text, int OD, float* __restrict__ cos_out) {
+  pdl_enter();
+  d_cosine(HwCtx(), emb, text, OD, cos_out);
+}
 
 // d cos / d emb (+ g_emb) -> dy = proj . de, spread over (B, Wd/96) CTAs (one warp per row of proj: coalesced)
-__global__ void __launch_bounds__(256)
-k_head_bwd_dy(int Wd, const float* __restrict__ proj, int OD, const float* __restrict__ text,
+template <class C>
+__device__ __forceinline__ void d_head_bwd_dy(const C& K_, int Wd, const float* __restrict__ proj, int OD, const float* __restrict__ text,
               const float* __restrict__ emb, const float* __restrict__ g_cos, const float* __restrict__ g_emb,
               float* __restrict__ dy_out, int rows_per_cta) {
-  pdl_enter();
-  extern __shared__ float sm[];
+  float* sm = reinterpret_cast<float*>(K_.smem);
   float* de = sm;            // [OD]
   __shared__ float red[3][8];
-  const int b = blockIdx.x;
+  const int b = K_.bx;
   float ee = 0.f, tt = 0.f, et = 0.f;
-  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+  for (int o = K_.tid; o < OD; o += K_.nt) {
     float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
     ee += a * a; tt += t * t; et += a * t;
   }
   ee = warp_sum(ee); tt = warp_sum(tt); et = warp_sum(et);
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ee; red[1][threadIdx.x >> 5] = tt; red[2][threadIdx.x >> 5] = et; }
-  __syncthreads();
+  if ((K_.tid & 31) == 0) { red[0][K_.tid >> 5] = ee; red[1][K_.tid >> 5] = tt; red[2][K_.tid >> 5] = et; }
+  K_.sync();
   float a2 = 0.f, t2 = 0.f, c = 0.f;
   for (int i = 0; i < 8; ++i) { a2 += red[0][i]; t2 += red[1][i]; c += red[2][i]; }
   float na = sqrtf(a2), nt = sqrtf(t2);
   float gc = g_cos ? g_cos[b] : 0.f;
-  for (int o = threadIdx.x; o < OD; o += blockDim.x) {
+  for (int o = K_.tid; o < OD; o += K_.nt) {
     float a = emb[(size_t)b * OD + o], t = text[(size_t)b * OD + o];
     // d/d a [ a.t / (|a||t|) ] = t/(|a||t|) - (a.t) a / (|a|^3 |t|)
     float d = (g_cos && na > 0.f && nt > 0.f) ? gc * (t / (na * nt) - c * a / (na * na * na * nt)) : 0.f;
     if (g_emb) d += g_emb[(size_t)b * OD + o];
     de[o] = d;
   }
-  __syncthreads();
-  const int r0 = blockIdx.y * rows_per_cta, r1 = min(Wd, r0 + rows_per_cta);
-  for (int cc = r0 + (threadIdx.x >> 5); cc < r1; cc += (blockDim.x >> 5)) {
+  K_.sync();
+  const int r0 = K_.by * rows_per_cta, r1 = min(Wd, r0 + rows_per_cta);
+  for (int cc = r0 + (K_.tid >> 5); cc < r1; cc += (K_.nt >> 5)) {
     float s = 0.f;
-    for (int o = threadIdx.x & 31; o < OD; o += 32) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
+    for (int o = K_.tid & 31; o < OD; o += 32) s = fmaf(proj[(size_t)cc * OD + o], de[o], s);
     s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) dy_out[(size_t)b * Wd + cc] = s;
+    if ((K_.tid & 31) == 0) dy_out[(size_t)b * Wd + cc] = s;
   }
+}
+__global__ void __launch_bounds__(256)
+k_head_bwd_dy(int Wd, const float* __restrict__ proj, int OD, const float* __restrict__ text,
+              const float* __restrict__ emb, const float* __restrict__ g_cos, const float* __restrict__ g_emb,
+              float* __restrict__ dy_out, int rows_per_cta) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char dyn_smem_hw[];
+  d_head_bwd_dy(HwCtx(dyn_smem_hw), Wd, proj, OD, text, emb, g_cos, g_emb, dy_out, rows_per_cta);
 }
 
 // LayerNorm (ln_post) backward on the cls row; the other token rows receive no gradient from the head
-__global__ void __launch_bounds__(256)
-k_head_bwd_ln(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ dy_in,
+template <class C>
+__device__ __forceinline__ void d_head_bwd_ln(const C& K_, const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ dy_in,
               float* __restrict__ dx) {
-  pdl_enter();
   __shared__ float red[3][8];
-  const int b = blockIdx.x;
+  const int b = K_.bx;
   const float* xr = x + (size_t)b * T * Wd;
   const float* dy = dy_in + (size_t)b * Wd;
   float s = 0.f;
-  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) s += xr[cc];
+  for (int cc = K_.tid; cc < Wd; cc += K_.nt) s += xr[cc];
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = s;
-  __syncthreads();
+  if ((K_.tid & 31) == 0) red[0][K_.tid >> 5] = s;
+  K_.sync();
   float mean = 0.f;
   for (int i = 0; i < 8; ++i) mean += red[0][i];
   mean /= (float)Wd;
   float v = 0.f;
-  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) { float d = xr[cc] - mean; v += d * d; }
+  for (int cc = K_.tid; cc < Wd; cc += K_.nt) { float d = xr[cc] - mean; v += d * d; }
   v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = v;
-  __syncthreads();
+  K_.sync();
+  if ((K_.tid & 31) == 0) red[0][K_.tid >> 5] = v;
+  K_.sync();
   float var = 0.f;
   for (int i = 0; i < 8; ++i) var += red[0][i];
   float rstd = rsqrtf(var / (float)Wd + 1e-5f);
   float pa = 0.f, pb = 0.f;
-  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+  for (int cc = K_.tid; cc < Wd; cc += K_.nt) {
     float dg = dy[cc] * g[cc];
     pa += dg; pb += dg * (xr[cc] - mean) * rstd;
   }
   pa = warp_sum(pa); pb = warp_sum(pb);
-  if ((threadIdx.x & 31) == 0) { red[1][threadIdx.x >> 5] = pa; red[2][threadIdx.x >> 5] = pb; }
-  __syncthreads();
+  if ((K_.tid & 31) == 0) { red[1][K_.tid >> 5] = pa; red[2][K_.tid >> 5] = pb; }
+  K_.sync();
   float A = 0.f, Bq = 0.f;
   for (int i = 0; i < 8; ++i) { A += red[1][i]; Bq += red[2][i]; }
   A /= (float)Wd; Bq /= (float)Wd;
-  for (int cc = threadIdx.x; cc < Wd; cc += blockDim.x) {
+  for (int cc = K_.tid; cc < Wd; cc += K_.nt) {
     float xh = (xr[cc] - mean) * rstd;
     dx[(size_t)b * T * Wd + cc] = rstd * (dy[cc] * g[cc] - A - xh * Bq);
   }
-  for (int64_t i = threadIdx.x; i < (int64_t)(T - 1) * Wd; i += blockDim.x) dx[(size_t)b * T * Wd + Wd + i] = 0.f;
+  for (int64_t i = K_.tid; i < (int64_t)(T - 1) * Wd; i += K_.nt) dx[(size_t)b * T * Wd + Wd + i] = 0.f;
+}
+__global__ void __launch_bounds__(256)
+k_head_bwd_ln(const float* __restrict__ x, int T, int Wd, const float* __restrict__ g, const float* __restrict__ dy_in,
+              float* __restrict__ dx) {
+  pdl_enter();
+  d_head_bwd_ln(HwCtx(), x, T, Wd, g, dy_in, dx);
 }
 
-__global__ void k_patch_row_map(int B, int T, int* __restrict__ map) {
-  pdl_enter();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+template <class C>
+__device__ __forceinline__ void d_patch_row_map(const C& K_, int B, int T, int* __restrict__ map) {
+  int i = K_.bx * K_.nt + K_.tid;
   int np = T - 1;
   if (i >= B * np) return;
   int b = i / np, p = i - b * np;
   map[i] = b * T + 1 + p;
+}
+__global__ void k_patch_row_map(int B, int T, int* __restrict__ map) {
+  pdl_enter();
+  d_patch_row_map(HwCtx(), B, T, map);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -857,6 +965,7 @@ struct ClipWs {
   float* scale;      // [M]
   float* dpatch;     // [B*np][3pp]
   int* rowmap;       // [B*np]
+  unsigned int* bar; // [32] grid-barrier counter of the persistent kernels (zeroed once per workspace)
   size_t bytes;
 };
 
@@ -897,6 +1006,7 @@ void carve_clip(const avc_clip_cfg& c, int B, int T, int np, int pp3, void* base
   w->scale = cv.take<float>(M);
   w->dpatch = cv.take<float>((int64_t)B * np * pp3);
   w->rowmap = cv.take<int>((int64_t)B * np);
+  w->bar = cv.take<unsigned int>(32);
   w->bytes = cv.used();
 }
 
@@ -904,6 +1014,236 @@ int set_attn_smem(int fwd_bytes, int bwd_bytes) {
   AVC_CUDA_TRY(cudaFuncSetAttribute(k_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_bytes));
   AVC_CUDA_TRY(cudaFuncSetAttribute(k_attention_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_bytes));
   return 0;
+}
+
+
+// ================================================================================================
+// The whole pass as ONE persistent cooperative kernel (`avc_clip_mega_fwd` / `avc_clip_mega_bwd`): one 512-thread
+// CTA per SM, the ~90 (forward) / ~105 (backward) dependent stages separated by grid-wide barriers instead of kernel
+// boundaries.  Each stage hands the virtual blocks of the stand-alone kernel to sub-CTAs of the persistent CTAs
+// (GEMM tiles: four 128-thread sub-CTAs per CTA with a 3-stage cp.async ring each; LayerNorm / conversions: 16 rows per
+// CTA; attention: one (image, head) per CTA).  The bodies are the same device functions the stand-alone kernels run.
+// ================================================================================================
+constexpr int kMegaThreads = 512;
+constexpr int kMegaGemmStages = 3;
+constexpr int kMegaGemmSmem = kMegaGemmStages * (GBM + GBN) * (GBK + GPAD) * 2;     // 41,472 B per sub-CTA
+constexpr int kMegaAttnFwdSmem = (3 * AT * AP + AT * (AT + 1)) * (int)sizeof(float);
+constexpr int kMegaAttnBwdSmem = (4 * AT * AP + 2 * AT * (AT + 1)) * (int)sizeof(float);
+constexpr int kMegaSmem = 4 * kMegaGemmSmem > kMegaAttnBwdSmem ? 4 * kMegaGemmSmem : kMegaAttnBwdSmem;
+
+struct MegaArgs {
+  avc_clip_cfg cfg;
+  avc_clip_weights wt;
+  ClipWs w;
+  const float* canvases; const float* text; float* emb_out; float* cos_out;      // forward
+  const float* g_cos; const float* g_emb; float* d_canvases;                      // backward
+  int H, W, B, mode, T, np, pp3;
+  unsigned int* bar;      // grid barrier counter (workspace), monotonically increasing
+};
+
+// Grid-wide barrier on one monotonically increasing counter: the last thread block of generation g bumps the counter
+// to g * gridDim.x; everybody spins (acquire) until then.  All CTAs are co-resident (cooperative launch).
+__device__ __forceinline__ void mega_grid_sync(unsigned int* bar, unsigned int& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++gen;
+    const unsigned int target = gen * gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <class F>
+__device__ __forceinline__ void mega_stage(unsigned char* smem, int nx, int ny, int nz, int sub_threads, int nsub,
+                                           int smem_per_sub, F&& f) {
+  const int sub = threadIdx.x / sub_threads;
+  if (sub < nsub) {
+    SubCtx c;
+    c.tid = threadIdx.x - sub * sub_threads; c.nt = sub_threads; c.smem = smem + (size_t)sub * smem_per_sub; c.bar = 1 + sub;
+    const int total = nx * ny * nz;
+    for (int v = blockIdx.x + sub * gridDim.x; v < total; v += gridDim.x * nsub) {
+      c.bx = v % nx; c.by = (v / nx) % ny; c.bz = v / (nx * ny);
+      f(c);
+      c.sync();          // the next virtual block of this sub-CTA reuses its shared memory
+    }
+  }
+}
+
+template <typename Epi>
+__device__ __forceinline__ void mega_gemm(unsigned char* smem, const __half* A, int lda, const __half* Wt, int ldw, int M,
+                                          int N, int K, int ksplit, const Epi& epi) {
+  const int kper = (int)(((K + ksplit - 1) / ksplit + GBK - 1) / GBK * GBK);
+  const int ks = (K + kper - 1) / kper;
+  mega_stage(smem, N / GBN, (M + GBM - 1) / GBM, ks, 128, 4, kMegaGemmSmem, [&](const SubCtx& c) {
+    d_gemm16<kMegaGemmStages>(c, A, lda, Wt, ldw, M, N, K, kper, epi);
+  });
+}
+
+__global__ void __launch_bounds__(kMegaThreads, 1) k_clip_mega_fwd(const __grid_constant__ MegaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned int gen = 0;          // the launcher clears the counter before every launch
+  const avc_clip_cfg& cf = a.cfg;
+  const ClipWs& w = a.w;
+  const int Wd = cf.width, B = a.B, T = a.T, M = B * T, IS = cf.image_size, np = a.np, pp3 = a.pp3, mlp = cf.mlp;
+#define MEGA_SYNC() mega_grid_sync(a.bar, gen)
+  // every CTA must leave the kernel only after the LAST barrier's counter is complete; that is the final MEGA_SYNC
+  {
+    const int64_t npx = (int64_t)B * 3 * IS * IS;
+    mega_stage(smem, (int)((npx + 511) / 512), 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_preprocess(c, a.canvases, a.H, a.W, B, IS, cf.patch, w.a0, a.mode); });
+    mega_stage(smem, (B * T * Wd + 511) / 512, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_cls_rows(c, a.wt.cls, a.wt.pos, B, T, Wd, w.tok_pre); });
+  }
+  MEGA_SYNC();
+  { EpiPatch e{w.tok_pre, T, Wd, np};
+    mega_gemm(smem, w.a0, pp3, (const __half*)a.wt.w_patch, pp3, B * np, Wd, pp3, 4, e); }
+  MEGA_SYNC();
+  mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+    d_layernorm(c, w.tok_pre, M, Wd, a.wt.ln_pre_g, a.wt.ln_pre_b, w.x, (__half*)nullptr, (float*)nullptr); });
+  MEGA_SYNC();
+  for (int l = 0; l < cf.layers; ++l) {
+    const avc_clip_layer_weights& lw = a.wt.layer[l];
+    float* xs1 = w.xs + (size_t)(2 * l) * M * Wd;
+    float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
+    float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
+    float* fcp = w.fc_pre + (size_t)l * M * mlp;
+    mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_layernorm(c, w.x, M, Wd, lw.ln1_g, lw.ln1_b, (float*)nullptr, w.h16, xs1); });
+    MEGA_SYNC();
+    { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
+      mega_gemm(smem, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e); }
+    MEGA_SYNC();
+    mega_stage(smem, B * cf.heads, 1, 1, 512, 1, 0, [&](const SubCtx& c) { d_attention(c, qkv, T, Wd, cf.heads, w.o16); });
+    MEGA_SYNC();
+    { EpiResidual e{w.x, Wd, lw.b_out};
+      mega_gemm(smem, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 4, e); }
+    MEGA_SYNC();
+    mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_layernorm(c, w.x, M, Wd, lw.ln2_g, lw.ln2_b, (float*)nullptr, w.h16, xs2); });
+    MEGA_SYNC();
+    { EpiFc e{fcp, w.g16, mlp, lw.b_fc};
+      mega_gemm(smem, w.h16, Wd, (const __half*)lw.w_fc, Wd, M, mlp, Wd, 1, e); }
+    MEGA_SYNC();
+    { EpiResidual e{w.x, Wd, lw.b_proj};
+      mega_gemm(smem, w.g16, mlp, (const __half*)lw.w_proj, mlp, M, Wd, mlp, 8, e); }
+    MEGA_SYNC();
+  }
+  // head: x_final keeps the residual stream for the backward; ln_post(cls) @ proj; cosine
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * Wd; i += (int64_t)gridDim.x * blockDim.x)
+    w.x_final[i] = w.x[i];
+  mega_stage(smem, B, (cf.out_dim + 63) / 64, 1, 256, 1, 0, [&](const SubCtx& c) {
+    d_head_proj(c, w.x, T, Wd, a.wt.ln_post_g, a.wt.ln_post_b, a.wt.proj, cf.out_dim, w.emb, w.ynorm); });
+  MEGA_SYNC();
+  mega_stage(smem, B, 1, 1, 256, 1, 0, [&](const SubCtx& c) { d_cosine(c, w.emb, a.text, cf.out_dim, a.cos_out); });
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * cf.out_dim; i += gridDim.x * blockDim.x) a.emb_out[i] = w.emb[i];
+  MEGA_SYNC();
+#undef MEGA_SYNC
+}
+
+__global__ void __launch_bounds__(kMegaThreads, 1) k_clip_mega_bwd(const __grid_constant__ MegaArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned int gen = 0;
+  const avc_clip_cfg& cf = a.cfg;
+  const ClipWs& w = a.w;
+  const int Wd = cf.width, B = a.B, T = a.T, M = B * T, IS = cf.image_size, np = a.np, pp3 = a.pp3, mlp = cf.mlp;
+#define MEGA_SYNC() mega_grid_sync(a.bar, gen)
+  {
+    const int rows = 96;
+    mega_stage(smem, B, (Wd + rows - 1) / rows, 1, 256, 1, 0, [&](const SubCtx& c) {
+      d_head_bwd_dy(c, Wd, a.wt.proj, cf.out_dim, a.text, w.emb, a.g_cos, a.g_emb, w.dO, rows); });
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)M * Wd; i += (int64_t)gridDim.x * blockDim.x)
+      w.dtmp[i] = 0.f;                     // split-K accumulator of the Wd-wide input-gradient GEMMs
+  }
+  MEGA_SYNC();
+  mega_stage(smem, B, 1, 1, 256, 1, 0, [&](const SubCtx& c) {
+    d_head_bwd_ln(c, w.x_final, T, Wd, a.wt.ln_post_g, w.dO, w.dx); });
+  MEGA_SYNC();
+  mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+    d_to_half_rowscaled(c, w.dx, M, Wd, Wd, w.d16a, w.scale, (const int*)nullptr); });
+  MEGA_SYNC();
+  for (int l = cf.layers - 1; l >= 0; --l) {
+    const avc_clip_layer_weights& lw = a.wt.layer[l];
+    const float* xs1 = w.xs + (size_t)(2 * l) * M * Wd;
+    const float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
+    const float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
+    const float* fcp = w.fc_pre + (size_t)l * M * mlp;
+    { EpiDfc e{fcp, w.d16b, mlp};
+      mega_gemm(smem, w.d16a, Wd, (const __half*)lw.w_proj_t, Wd, M, mlp, Wd, 1, e); }
+    MEGA_SYNC();
+    { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
+      mega_gemm(smem, w.d16b, mlp, (const __half*)lw.w_fc_t, mlp, M, Wd, mlp, 8, e); }
+    MEGA_SYNC();
+    mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_layernorm_bwd(c, xs2, w.dtmp, M, Wd, lw.ln2_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, 1); });
+    MEGA_SYNC();
+    { EpiStoreUnscale e{w.dO, Wd, w.scale};
+      mega_gemm(smem, w.d16a, Wd, (const __half*)lw.w_out_t, Wd, M, Wd, Wd, 1, e); }
+    MEGA_SYNC();
+    mega_stage(smem, B * cf.heads, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_attention_bwd(c, qkv, w.dO, T, Wd, cf.heads, w.dqkv); });
+    MEGA_SYNC();
+    mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_to_half_rowscaled(c, w.dqkv, M, 3 * Wd, 3 * Wd, w.d16a, w.scale, (const int*)nullptr); });
+    MEGA_SYNC();
+    { EpiAccumUnscale e{w.dtmp, Wd, w.scale};
+      mega_gemm(smem, w.d16a, 3 * Wd, (const __half*)lw.w_qkv_t, 3 * Wd, M, Wd, 3 * Wd, 6, e); }
+    MEGA_SYNC();
+    mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_layernorm_bwd(c, xs1, w.dtmp, M, Wd, lw.ln1_g, w.dx, 1, Wd, Wd, Wd, w.d16a, w.scale, 1); });
+    MEGA_SYNC();
+  }
+  // ln_pre, patch embedding, pre-processing
+  mega_stage(smem, (M + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+    d_layernorm_bwd(c, w.tok_pre, w.dx, M, Wd, a.wt.ln_pre_g, w.dtmp, 0, Wd, Wd, Wd, (__half*)nullptr, (float*)nullptr, 0); });
+  mega_stage(smem, (B * np + 511) / 512, 1, 1, 512, 1, 0, [&](const SubCtx& c) { d_patch_row_map(c, B, T, w.rowmap); });
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (int64_t)B * a.H * a.W * 3; i += (int64_t)gridDim.x * blockDim.x)
+    a.d_canvases[i] = 0.f;
+  MEGA_SYNC();
+  mega_stage(smem, (B * np + 15) / 16, 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+    d_to_half_rowscaled(c, w.dtmp, B * np, Wd, Wd, w.d16a, w.scale, w.rowmap); });
+  MEGA_SYNC();
+  { EpiStoreUnscale e{w.dpatch, pp3, w.scale};
+    mega_gemm(smem, w.d16a, Wd, (const __half*)a.wt.w_patch_t, Wd, B * np, pp3, Wd, 1, e); }
+  MEGA_SYNC();
+  {
+    const int64_t npx = (int64_t)B * 3 * IS * IS;
+    mega_stage(smem, (int)((npx + 511) / 512), 1, 1, 512, 1, 0, [&](const SubCtx& c) {
+      d_preprocess_bwd(c, w.dpatch, a.H, a.W, B, IS, cf.patch, a.d_canvases, a.mode); });
+  }
+  MEGA_SYNC();
+#undef MEGA_SYNC
+}
+
+// one cooperative launch (all CTAs co-resident: the grid barrier needs it); returns 1 when the device cannot host it
+int launch_mega(bool fwd, const MegaArgs& args, cudaStream_t st) {
+  static int grid = 0;
+  if (!grid) {
+    int dev = 0, sms = 0, coop = 0, per = 0;
+    AVC_CUDA_TRY(cudaGetDevice(&dev));
+    AVC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    AVC_CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    AVC_CUDA_TRY(cudaFuncSetAttribute(k_clip_mega_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem));
+    AVC_CUDA_TRY(cudaFuncSetAttribute(k_clip_mega_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmem));
+    AVC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_clip_mega_bwd, kMegaThreads, kMegaSmem));
+    if (!coop || per < 1) { grid = -1; } else grid = sms;
+  }
+  if (grid < 0) return 1;
+  AVC_CUDA_TRY(cudaMemsetAsync(args.bar, 0, sizeof(unsigned int), st));
+  void* params[1] = {(void*)&args};
+  AVC_CUDA_TRY(cudaLaunchCooperativeKernel(fwd ? (const void*)k_clip_mega_fwd : (const void*)k_clip_mega_bwd, dim3(grid),
+                                           dim3(kMegaThreads), params, (size_t)kMegaSmem, st));
+  return 0;
+}
+
+int mega_enabled() {      // AVC_CLIP_MEGA=0: the chain of stand-alone kernels (A-B knob; read on every call)
+  const char* e = getenv("AVC_CLIP_MEGA");
+  return (e && atoi(e) == 0) ? 0 : 1;
 }
 
 }  // namespace
@@ -940,6 +1280,15 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
   const int attn_bwd_smem = (4 * AT * AP + 2 * AT * (AT + 1)) * (int)sizeof(float);
   AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
 
+  if (mega_enabled()) {
+    MegaArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.cfg = *cfg; ma.wt = *wt; ma.w = w; ma.canvases = canvases; ma.text = text_emb; ma.emb_out = emb_out; ma.cos_out = cos_out;
+    ma.H = H; ma.W = W; ma.B = B; ma.mode = input_mode; ma.T = T; ma.np = np; ma.pp3 = pp3; ma.bar = w.bar;
+    if (Wd % 4) return AVC_E_BADCFG;
+    int r = launch_mega(true, ma, st);
+    if (r != 1) return r;
+  }
   int64_t npx = (int64_t)B * 3 * IS * IS;
   AVC_CUDA_TRY(launch_pdl(k_preprocess, dim3((int)((npx + 255) / 256)), dim3(256), 0, st, canvases, H, W, B, IS, cfg->patch, w.a0, input_mode));
   AVC_CUDA_TRY(launch_pdl(k_cls_rows, dim3((B * T * Wd + 255) / 256), dim3(256), 0, st, wt->cls, wt->pos, B, T, Wd, w.tok_pre));
@@ -999,6 +1348,14 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, int32
   const int attn_bwd_smem = (4 * AT * AP + 2 * AT * (AT + 1)) * (int)sizeof(float);
   AVC_TRY(set_attn_smem(attn_fwd_smem, attn_bwd_smem));
 
+  if (mega_enabled()) {
+    MegaArgs ma;
+    memset(&ma, 0, sizeof(ma));
+    ma.cfg = *cfg; ma.wt = *wt; ma.w = w; ma.text = text_emb; ma.g_cos = g_cos; ma.g_emb = g_emb; ma.d_canvases = d_canvases;
+    ma.H = H; ma.W = W; ma.B = B; ma.mode = input_mode; ma.T = T; ma.np = np; ma.pp3 = pp3; ma.bar = w.bar;
+    int r = launch_mega(false, ma, st);
+    if (r != 1) return r;
+  }
   {
     const int rows = 96;
     AVC_CUDA_TRY(launch_pdl(k_head_bwd_dy, dim3(dim3(B, ceil_div(Wd, rows))), dim3(256), cfg->out_dim * sizeof(float), st, 

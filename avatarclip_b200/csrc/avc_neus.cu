@@ -165,9 +165,8 @@ EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
 // network shape (the caller then runs the layer-by-layer launches), 0 on success.
 int value_chain_fused(const NeusPlan& pl, const NeusWs& w, int64_t Pn, float* sdf_out, cudaStream_t st, int sdf_nz,
                       int sdf_pitch) {
-  static int enabled = -1;      // AVC_FUSED_CHAIN=0: layer-by-layer launches (tuning / A-B knob)
-  if (enabled < 0) { const char* e = getenv("AVC_FUSED_CHAIN"); enabled = (e && atoi(e) == 0) ? 0 : 1; }
-  if (!enabled || pl.L > chain::kMaxHidden) return 1;
+  const char* env = getenv("AVC_FUSED_CHAIN");      // 0: layer-by-layer launches (A-B knob, read on every call)
+  if ((env && atoi(env) == 0) || pl.L > chain::kMaxHidden) return 1;
   chain::Args a;
   memset(&a, 0, sizeof(a));
   a.L = pl.L;

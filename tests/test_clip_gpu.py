@@ -1,6 +1,8 @@
 """GPU parity of the CLIP ViT-B/32 image tower + cosine loss against the CPU oracle (oracle/clip_vit.py:
 the published architecture restated and cross-checked against HF transformers; PARITY UNPINNED w.r.t.
 openai/CLIP itself -- see oracle/__init__.py)."""
+import os
+
 import pytest
 import torch
 
@@ -16,8 +18,21 @@ def _tower(seed=0):
     return sd, ClipImageTower(sd, device="cuda")
 
 
+@pytest.fixture(params=["persistent", "chained"])
+def clip_mode(request):
+    """Both launch structures of the tower: one persistent cooperative kernel per pass (default) and the chain of
+    stand-alone kernels (AVC_CLIP_MEGA=0); same device functions, same results up to fp32 atomic order."""
+    old = os.environ.get("AVC_CLIP_MEGA")
+    os.environ["AVC_CLIP_MEGA"] = "1" if request.param == "persistent" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("AVC_CLIP_MEGA", None)
+    else:
+        os.environ["AVC_CLIP_MEGA"] = old
+
+
 @pytest.mark.parametrize("H", [160, 224, 256])
-def test_clip_cosine_and_canvas_gradient(H):
+def test_clip_cosine_and_canvas_gradient(H, clip_mode):
     sd, tower = _tower()
     g = torch.Generator().manual_seed(H)
     # smooth-ish image content (renders are smooth) + noise background
@@ -39,12 +54,13 @@ def test_clip_cosine_and_canvas_gradient(H):
     loss_o, loss_p = 1.0 - cos_o.detach(), 1.0 - cos_p.detach().cpu()
     rel = ((loss_o - loss_p).abs() / loss_o.abs()).max().item()
     gerr = U.rel_to_max(cp.grad, go)
+    U.log_parity("clip_tower", {"mode": clip_mode, "H": H, "clip_loss_rel": rel, "canvas_grad_rel_to_max": gerr})
     print(f"H={H}: cos oracle {cos_o.tolist()} product {cos_p.tolist()} loss rel err {rel:.2e} canvas-grad err {gerr:.2e}")
     assert rel < 1e-3
     assert gerr < 2e-2      # fp16 GEMM operands (as in the reference's CUDA path); fp32 accumulate
 
 
-def test_encode_image_matches_oracle():
+def test_encode_image_matches_oracle(clip_mode):
     sd, tower = _tower(seed=3)
     g = torch.Generator().manual_seed(9)
     img = torch.randn(1, 3, 224, 224, generator=g)

@@ -106,6 +106,24 @@ def test_sdf_query_matches_oracle():
     assert U.rel_to_max(got, want) < 1e-5
 
 
+@pytest.mark.parametrize("name,P", [("tiny", 77), ("tiny", 5000), ("skiplast", 1000), ("shipped", 4099), ("b2", 20000)])
+def test_fused_chain_sdf_query_matches_oracle(name, P):
+    """engine 1 without a stash (sample placement, SDFNetwork.sdf) runs the whole value chain of a 128-point tile in ONE
+    kernel (csrc/avc_chain.cu: activations resident in shared memory, sdf head folded into the last epilogue).  Covered:
+    widths 48 / 64 / 256, the skip concat inside the chain and at the head, ragged last tile, P < one tile."""
+    sdf_kw, col_kw, ren_kw, _ = U.CASES[name]
+    sconf, cconf, rconf = U.confs_from_kw(sdf_kw, col_kw, ren_kw)
+    sp, cp = U.synth_state(sdf_kw, col_kw, 5)
+    sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda", engine=1)
+    pts = (torch.rand(P, 3, generator=torch.Generator().manual_seed(P)) - 0.5) * 2
+    got = sdf.sdf(pts.cuda()).cpu()
+    from oracle import neus
+    want = neus.sdf_value(sp, sconf, pts)
+    err = U.rel_to_max(got, want)
+    U.log_parity("fused_chain_sdf_query", {"case": name, "P": P, "rel_to_max": err})
+    assert err < 5e-5, err                     # two-term bf16 split operands (~16 mantissa bits); measured ~1e-5
+
+
 @pytest.mark.parametrize("name,bg,anneal", [("tiny", "ray", 1.0), ("skiplast", "none", 0.3), ("shipped", "ray", 1.0),
                                              ("b2", "white", 1.0)])
 def test_tcgen05_engine_matches_oracle(name, bg, anneal):
