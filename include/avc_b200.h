@@ -340,6 +340,11 @@ int avc_uniform_fill(uint32_t seed, int32_t n, float lo, float hi, float* out, a
  * coordinates (the caller rescales like renderer.py:33-35) and, per vertex, a 64-bit key of the grid edge it lies
  * on (for welding).  Triangles are oriented with normals towards decreasing u.
  * ------------------------------------------------------------------------------------------ */
+/* Profiling aid of the fused value-chain kernel: with AVC_CHAIN_DEBUG=1 in the environment block 0 records cycle
+ * counters ([0] MMA warp waiting for its A operand, [1] for weight slabs, [2] MMA warp total, [3] tile-layers,
+ * [4] epilogue waiting for the accumulator, [5] epilogue work); this call synchronises the device and copies them. */
+int avc_chain_debug_read(long long* out8);
+
 int avc_march_count(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, int32_t* counts,
                     avc_stream_t stream);
 int avc_march_emit(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, const int32_t* offsets,

@@ -20,8 +20,8 @@ def _tower(seed=0):
 
 @pytest.fixture(params=["persistent", "chained"])
 def clip_mode(request):
-    """Both launch structures of the tower: one persistent cooperative kernel per pass (default) and the chain of
-    stand-alone kernels (AVC_CLIP_MEGA=0); same device functions, same results up to fp32 atomic order."""
+    """Both launch structures of the tower: the chain of stand-alone kernels (default) and one persistent cooperative
+    kernel per pass (AVC_CLIP_MEGA=1); same device functions, same results up to fp32 atomic order."""
     old = os.environ.get("AVC_CLIP_MEGA")
     os.environ["AVC_CLIP_MEGA"] = "1" if request.param == "persistent" else "0"
     yield request.param
