@@ -143,12 +143,13 @@ int prepare_weights(const NeusPlan& pl, const NeusWs& w, const float* params, cu
 EncodeTargets make_targets(const NeusPlan& pl, const NeusWs& w) {
   EncodeTargets t;
   memset(&t, 0, sizeof(t));
-  t.in0 = w.in[0]; t.ld0 = pl.sdf[0].Kp;
+  const bool tc1 = pl.cfg.engine == 1;      // tcgen05 engine: every consumer of the encoding reads the bf16 pairs ...
+  t.in0 = tc1 ? nullptr : w.in[0]; t.ld0 = pl.sdf[0].Kp;
   t.in0_16 = w.in16[0];
   for (int l = 1; l <= pl.L; ++l) {
     if (!pl.sdf[l].skip) continue;
     if (t.n_skip >= 4) break;
-    t.skip_ptr[t.n_skip] = w.in[l];
+    t.skip_ptr[t.n_skip] = (tc1 && l != pl.L) ? nullptr : w.in[l];      // ... except the thin sdf head (fp32 in[L])
     t.skip_ld[t.n_skip] = pl.sdf[l].Kp;
     t.skip_col[t.n_skip] = pl.sdf[l].K - pl.E;
     t.skip16[t.n_skip] = w.in16[l];

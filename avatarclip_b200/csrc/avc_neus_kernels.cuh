@@ -151,18 +151,20 @@ struct EncodeTargets {
 __device__ __forceinline__ void encode_group(float x0, float x1, float x2, float scale, int multires, int E, int EP,
                                              int64_t p, int g, const EncodeTargets& t) {
   const float y[3] = {x0 * scale, x1 * scale, x2 * scale};
-  float* r0 = t.in0 + (size_t)p * t.ld0;
+  // fp32 destinations may be NULL: the tcgen05 engine reads the encoding only through the bf16 pairs (except the fp32
+  // input of the thin sdf head when the LAST linear takes the skip concat)
+  float* r0 = t.in0 ? t.in0 + (size_t)p * t.ld0 : nullptr;
   auto put = [&](int c, float v) {
-    r0[c] = v;
+    if (r0) r0[c] = v;
     split16_put(t.in0_16, (size_t)p, c, v);
     for (int s = 0; s < t.n_skip; ++s) {
-      t.skip_ptr[s][(size_t)p * t.skip_ld[s] + t.skip_col[s] + c] = v * kSqrtHalf;
+      if (t.skip_ptr[s]) t.skip_ptr[s][(size_t)p * t.skip_ld[s] + t.skip_col[s] + c] = v * kSqrtHalf;
       split16_put(t.skip16[s], (size_t)p, t.skip_col[s] + c, v * kSqrtHalf);
     }
   };
   if (g == 0) {
     put(0, y[0]); put(1, y[1]); put(2, y[2]);
-    for (int c = E; c < EP; ++c) { r0[c] = 0.f; split16_put(t.in0_16, (size_t)p, c, 0.f); }
+    for (int c = E; c < EP; ++c) { if (r0) r0[c] = 0.f; split16_put(t.in0_16, (size_t)p, c, 0.f); }
   }
   for (int k = g - 1; k >= 0 && k < multires; k += 7) {
     const float f = (float)(1 << k);

@@ -83,6 +83,7 @@ class AppearanceTrainer:
         self._graph_key = None
         self._graph_loss = None
         self._adam_state = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._graph_has_adam = True
         self._lr_on_device = None
         self._dev_step = -1
 
@@ -168,10 +169,12 @@ class AppearanceTrainer:
     def _graph_body(self, dv: DeviceView, cos_anneal: float, with_adam: bool):
         self.forward_backward(dv, cos_anneal)
         if with_adam:
+            if self.world > 1:        # the step's only collective, captured into the graph (NCCL supports stream capture)
+                avc_dist.allreduce_sum_(self.grad, self.pg)
             b1, b2 = self.betas
             _lib.check(_lib.lib().avc_adam_step_dev(_lib.ptr(self.fp.flat), _lib.ptr(self.grad),
                                                     _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq), self.fp.n,
-                                                    _lib.ptr(self._adam_state), b1, b2, self.eps, 1.0,
+                                                    _lib.ptr(self._adam_state), b1, b2, self.eps, 1.0 / self.world,
                                                     _lib.stream_ptr()), "avc_adam_step_dev")
         return self.loss_value()
 
@@ -188,9 +191,27 @@ class AppearanceTrainer:
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
         self._set_device_adam(self.lr)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._graph_loss = self._graph_body(dv, cos_anneal, with_adam=(self.world == 1))
+        # Single GPU: the whole step including Adam is one graph.  View-sharded ranks: the all-reduce and Adam are captured
+        # too (AVC_GRAPH_ALLREDUCE=0, or a failing capture, falls back to launching them after the graph).
+        import os
+        self._graph_has_adam = True
+        want_inside = self.world == 1 or os.environ.get("AVC_GRAPH_ALLREDUCE", "1") != "0"
+        g = None
+        if want_inside:
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._graph_loss = self._graph_body(dv, cos_anneal, with_adam=True)
+            except Exception:
+                if self.world == 1:
+                    raise
+                g = None
+                torch.cuda.synchronize(self.device)
+        if g is None:
+            self._graph_has_adam = False
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_loss = self._graph_body(dv, cos_anneal, with_adam=False)
         self._graph, self._graph_key = g, (id(dv), dv.bg_choice, float(cos_anneal))
         return g
 
@@ -205,7 +226,7 @@ class AppearanceTrainer:
         if self._graph is None or self._graph_key != (id(dv), dv.bg_choice, float(cos_anneal)):
             self.capture(dv, cos_anneal)
         lr = self.lr if lr is None else lr
-        if self.world == 1:
+        if self._graph_has_adam:
             if self._dev_step != self.iter_step:      # eager steps ran in between: resynchronise the device counter
                 self._set_device_adam(lr)
             elif lr != self._lr_on_device:

@@ -70,6 +70,13 @@ def algorithmic_flops_per_step():
     return mlp, nt, tn, clip
 
 
+def placement_flops_per_step():
+    """The 0.875 F_sdf of the sample-placement passes (coarse + 3 up-sampling rounds): executed by the fused value-chain
+    kernel (avc::chain::k_sdf_chain) when it is on, by the NT tiles otherwise."""
+    mac_sdf = 39 * 256 + 6 * 256 * 256 + 256 * 217 + 256 * 257
+    return 0.875 * 2 * mac_sdf * N_RAYS * (REN_KW["n_samples"] + REN_KW["n_importance"])
+
+
 def host_cores() -> int:
     """Usable host cores: the cgroup CPU quota when there is one (the GPU boxes expose 128 logical CPUs but
     grant a 16-CPU quota; 128 threads then run ~50x slower than 16), else the affinity mask."""
@@ -356,7 +363,10 @@ def run_native(args):
         # dominant kernel: algorithmic FLOP its launches execute per step / the sum of their device durations in the
         # profiled step (CUPTI kernel records taken live in this process, not under ncu)
         kern_us = {k: v for k, v in table.items() if isinstance(v, list)}
-        dom_flops = {"avc::tc::gemm_tc_nt_kernel": nt_flops, "avc::tc::gemm_tc_tn_kernel": tn_flops,
+        chain_on = "avc::chain::k_sdf_chain" in kern_us
+        if chain_on:
+            nt_flops -= placement_flops_per_step()
+        dom_flops = {"avc::tc::gemm_tc_nt_kernel": nt_flops, "avc::chain::k_sdf_chain": placement_flops_per_step(), "avc::tc::gemm_tc_tn_kernel": tn_flops,
                      "avc::gemm_nt_kernel": nt_flops, "avc::gemm_tn_kernel": tn_flops}.get(dom)
         if dom_flops is not None and dom in kern_us and kern_us[dom][1] > 0:
             n_launch, dom_us = kern_us[dom]
@@ -374,7 +384,8 @@ def run_native(args):
                        "views_per_step": world, "engine": "fp32 FFMA tiles" if args.engine == 0 else "tcgen05 split",
                        "l2": "per-step working set (activation stash ~2.4 GB) >> 126 MB L2; no flush needed",
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single",
-                       "launch": ("one CUDA graph per step" + (" + all-reduce + Adam" if world > 1 else ""))
+                       "launch": ("one CUDA graph per step" + ((" (NCCL all-reduce + Adam captured inside)" if tr._graph_has_adam
+                                                                 else " + all-reduce + Adam after it") if world > 1 else ""))
                                  if use_graph else "eager C-ABI calls"},
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "steps/s",
                     "h2d_bytes_per_step": views[0].h2d_bytes(), "d2h_bytes_per_step": 4},
@@ -386,7 +397,8 @@ def run_native(args):
                          "traffic": TRAFFIC_PER_LAUNCH.get(dom),
                          "per_launch": per_launch,
                          "scope": "algorithmic FLOP executed by the dominant kernel's launches in one step (SURVEY 8d "
-                                  "split: NT tiles 4.875 F_sdf + 2 F_col per point, TN tiles 2 F_sdf + F_col) / sum of "
+                                  "split: NT tiles 4.875 F_sdf + 2 F_col per point -- 4.0 F_sdf when the fused value-chain "
+                                  "kernel runs the 0.875 F_sdf of the placement passes --, TN tiles 2 F_sdf + F_col) / sum of "
                                   "their device durations (CUPTI, live); peak = " + peak_src + "; the kernel runs 3 "
                                   "bf16 MMAs per product (two-term split), so its ceiling is peak/3",
                          "hbm_view": (lambda b, us: {"designed_bytes_per_step": b, "kernel_us_per_step": us,
@@ -397,6 +409,11 @@ def run_native(args):
                                                              "the activation traffic they move by design (operands in, "
                                                              "stash + split out), not by the tensor pipe"})(
                              nt_designed_bytes_per_step(), kern_us.get("avc::tc::gemm_tc_nt_kernel", [0, 0.0])[1]),
+                         "fused_chain": ({"kernel": "avc::chain::k_sdf_chain", "launches_per_step": kern_us["avc::chain::k_sdf_chain"][0],
+                                          "us_per_step": kern_us["avc::chain::k_sdf_chain"][1],
+                                          "achieved": placement_flops_per_step() / (kern_us["avc::chain::k_sdf_chain"][1] * 1e-6) / 1e12,
+                                          "frac": placement_flops_per_step() / (kern_us["avc::chain::k_sdf_chain"][1] * 1e-6) / 1e12 / peak_tf,
+                                          "hbm_bytes_per_point": 164} if chain_on else None),
                          "step_level": {"achieved": achieved_step, "frac": achieved_step / peak_tf,
                                         "ms_render_fwd_bwd": ms_render,
                                         "note": "all MLP FLOP/step (0.577 T) / CUDA-event time of render fwd+bwd"},
