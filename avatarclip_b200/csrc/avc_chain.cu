@@ -354,12 +354,12 @@ int launch(const Args& a, cudaStream_t st) {
   d.w_sdf = a.w_sdf; d.b_sdf = a.b_sdf; d.head_skip_cols = a.head_skip_cols; d.head_hidden = a.lay[a.L - 1].N;
   d.inv_scale = a.inv_scale; d.sdf_out = a.sdf_out; d.nz = a.nz; d.pitch = a.pitch; d.P = a.P;
   d.tiles = (int)((a.P + kCM - 1) / kCM);
-  static bool attr_set = false;
+  static thread_local bool attr_set = false;
   if (!attr_set) {
     AVC_CUDA_TRY(cudaFuncSetAttribute(k_sdf_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
-  static int num_sms = 0;
+  static thread_local int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     AVC_CUDA_TRY(cudaGetDevice(&dev));

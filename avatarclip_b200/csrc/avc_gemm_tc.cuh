@@ -44,7 +44,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spins > (1u << 22)) __trap();
+    if (spins > (1u << 26)) __trap();      // ~seconds: far beyond any legitimate wait, short of the box's watchdog
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -158,7 +158,7 @@ static inline int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows,
                                 uint32_t box_cols, uint32_t box_rows);
 static inline int make_map_bf16_cached(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                                        uint32_t box_cols, uint32_t box_rows) {
-  static MapCacheEntry cache[256];
+  static thread_local MapCacheEntry cache[256];      // one host thread per device: every thread has its own cache
   uint64_t h = ((uintptr_t)base >> 8) * 0x9E3779B97F4A7C15ull ^ (rows * 31 + cols * 131 + ld * 7 + box_cols + 3 * box_rows);
   MapCacheEntry& e = cache[(h >> 32) & 255];
   if (e.base == base && e.rows == rows && e.cols == cols && e.ld == ld && e.bc == box_cols && e.br == box_rows) {
@@ -473,12 +473,12 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
     mAl = mAh; mBl = mBh;
   }
   auto kern = gemm_tc_nt_kernel<BN, NPROD, EW, PFB, RESB, Epi>;
-  static bool attr_set = false;    // per template instantiation
+  static thread_local bool attr_set = false;    // per template instantiation and host thread (= device)
   if (!attr_set) {
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  static int num_sms = 0;
+  static thread_local int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
     AVC_CUDA_TRY(cudaGetDevice(&dev));
@@ -683,7 +683,9 @@ static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, 
   auto go = [&](auto kern, int BN, int smem) -> int {
     AVC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int t2 = ceil_div(N2, BN);
-    int splits = (148 + t1 * t2 - 1) / (t1 * t2);
+    static thread_local int sms = 0;
+    if (!sms) { int dev = 0; AVC_CUDA_TRY(cudaGetDevice(&dev)); AVC_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    int splits = (sms + t1 * t2 - 1) / (t1 * t2);
     int rows = (int)round_up(ceil_div(P, splits), kBK);
     splits = ceil_div(P, rows);
     dim3 grid(t1, t2, splits);

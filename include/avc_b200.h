@@ -13,7 +13,10 @@
  *   - every function enqueues work on `stream` and returns immediately (no host sync);
  *   - nothing allocates: scratch is sized by the *_workspace_bytes queries and passed in;
  *   - return value: 0 ok, <0 AVC_E_* (invalid argument), >0 a cudaError_t;
- *   - no global mutable state; safe to call from one host thread per device.
+ *   - no results or device state are kept between calls outside the caller's buffers.  Host-side conveniences are
+ *     thread-local (a cache of encoded TMA tensor maps, the SM count, "attribute already set" flags): safe to call
+ *     from one host thread per device (the supported deployment is one process per GPU, torchrun style).  Tuning
+ *     knobs are environment variables (AVC_*) read on the host.
  */
 #ifndef AVC_B200_H
 #define AVC_B200_H
