@@ -396,7 +396,10 @@ constexpr int kLnMax = 32;
 
 template <class C>
 __device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
-            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
+            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x, float* __restrict__ add = nullptr,
+            float* __restrict__ x_out = nullptr) {
+  // add != NULL: the row is x + add (the attention block's out-projection, accumulated by its head CTAs); the sum is
+  // written back to x_out (the residual stream) and `add` is handed back cleared for the next layer
   int row = K_.bx * (K_.nt >> 5) + (K_.tid >> 5);
   if (row >= M) return;
   const int lane = K_.tid & 31;
@@ -408,6 +411,11 @@ __device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict
     int c = lane + 32 * i;
     bool ok = c < Wd;
     xv[i] = ok ? xr[c] : 0.f; gv[i] = ok ? g[c] : 0.f; bv[i] = ok ? b[c] : 0.f;
+    if (add && ok) {
+      xv[i] += add[(size_t)row * Wd + c];
+      add[(size_t)row * Wd + c] = 0.f;
+      x_out[(size_t)row * Wd + c] = xv[i];
+    }
     s += xv[i];
   }
   float mean = warp_sum(s) / (float)Wd;
@@ -428,9 +436,10 @@ __device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict
 }
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
-            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
+            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x, float* __restrict__ add,
+            float* __restrict__ x_out) {
   pdl_enter();
-  d_layernorm(HwCtx(), x, M, Wd, g, b, y32, y16, save_x);
+  d_layernorm(HwCtx(), x, M, Wd, g, b, y32, y16, save_x, add, x_out);
 }
 
 // dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); optionally also the row-scaled fp16
@@ -745,6 +754,246 @@ k_attention_bwd(const float* __restrict__ qkv, const float* __restrict__ dO, int
   d_attention_bwd(HwCtx(dyn_smem_hw), qkv, dO, T, Wd, heads, dqkv);
 }
 
+
+// ================================================================================================
+// The attention half of a residual block as ONE kernel per (image, head):
+//     ln_1 -> in_proj (this head's q, k, v) -> softmax(q k^T / 8) v -> this head's slice of out_proj
+// (openai/CLIP ResidualAttentionBlock: x = x + attn(ln_1(x))).  24 CTAs (B = 2 images x 12 heads) of 256 threads replace
+// four dependent kernels of the chain (LayerNorm, in_proj GEMM, attention, out_proj GEMM).  Per CTA: the normalised
+// 50 x 768 tile is built in shared memory (fp16, 64 padded rows), this head's 192 in_proj rows stream through a 4-stage
+// cp.async ring in 12 chunks of 64 k (mma.sync m16n8k16, fp32 accumulate), q / k / v stay in shared memory for the softmax
+// (fp32), and the head's [50 x 64] output multiplies its 64 columns of out_proj in four 192-row chunks of the same ring;
+// the partial out-projections of the 12 heads meet in fp32 atomics in `attn_sum`, which the following LayerNorm (ln_2)
+// adds to the residual stream and clears.  q / k / v are also written to the stash the backward reads.
+// ================================================================================================
+constexpr int FA_ROWS = 64;                       // padded token rows
+constexpr int FA_WN = 192;                        // weight rows per chunk (q|k|v of one head; a quarter of out_proj)
+constexpr int FA_LDA = 768 + 8;                   // shared-memory pitch of the normalised tile (halfs)
+constexpr int FA_LDW = GBK + GPAD;                // 72
+constexpr int FA_ST = 4;
+constexpr int FA_SA_BYTES = FA_ROWS * FA_LDA * 2;                 // 99,328
+constexpr int FA_SW_BYTES = FA_ST * FA_WN * FA_LDW * 2;           // 110,592
+constexpr int FA_SMEM = FA_SA_BYTES + FA_SW_BYTES;                // 209,920
+
+__device__ __forceinline__ void fa_issue_chunk(__half* sW, int stage, const __half* __restrict__ src, int ld_src, int tid) {
+  // 192 rows x 64 halfs (8 chunks of 16 B per row) -> sW[stage][row][..]; 256 threads x 6
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = tid + i * 256;
+    const int r = c >> 3, ch = c & 7;
+    cp_async16(sW + ((size_t)stage * FA_WN + r) * FA_LDW + ch * 8, src + (size_t)r * ld_src + ch * 8, true);
+  }
+}
+
+// acc[mt? no: one m16 tile per warp][12 n8 tiles][4] += A[16 rows x 64 k] . W[96 rows x 64 k]^T for this warp's (wm, wn)
+__device__ __forceinline__ void fa_mma_chunk(float (&acc)[12][4], const __half* sA_rows /* &sA[wm*16][k0] */, int lda,
+                                             const __half* sWst /* &sW[stage][wn*96][0] */, int lane) {
+#pragma unroll
+  for (int kk = 0; kk < GBK; kk += 16) {
+    unsigned a[4];
+    {
+      unsigned addr = (unsigned)__cvta_generic_to_shared(sA_rows + (size_t)(lane & 15) * lda + kk + (lane >> 4) * 8);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+    }
+#pragma unroll
+    for (int np = 0; np < 6; ++np) {     // six pairs of n8 tiles
+      unsigned b[4];
+      unsigned addr = (unsigned)__cvta_generic_to_shared(
+          sWst + (size_t)(np * 16 + (lane & 7) + (lane >> 4) * 8) * FA_LDW + kk + ((lane >> 3) & 1) * 8);
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                   : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float* c = acc[np * 2 + h];
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[h * 2]), "r"(b[h * 2 + 1]));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_attn_block_fwd(const float* __restrict__ x, int T, int Wd, int heads, const float* __restrict__ ln_g,
+                 const float* __restrict__ ln_b, const __half* __restrict__ w_qkv, const float* __restrict__ b_qkv,
+                 const __half* __restrict__ w_out, const float* __restrict__ b_out, float* __restrict__ save_x,
+                 float* __restrict__ qkv_stash, float* __restrict__ attn_sum) {
+  extern __shared__ __align__(16) unsigned char fa_smem[];
+  __half* sA = reinterpret_cast<__half*>(fa_smem);
+  __half* sW = reinterpret_cast<__half*>(fa_smem + FA_SA_BYTES);
+  // after the in_proj GEMM the tile region is reused: q, k, v fp32 [T][AP] | S [T][AT+1] | o16 [64][72]
+  float* q = reinterpret_cast<float*>(fa_smem);
+  float* k = q + AT * AP;
+  float* v = k + AT * AP;
+  float* S = v + AT * AP;
+  __half* o16 = reinterpret_cast<__half*>(S + AT * (AT + 1));
+  static_assert((3 * AT * AP + AT * (AT + 1)) * 4 + FA_ROWS * FA_LDW * 2 <= FA_SA_BYTES, "attention scratch must fit the tile region");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int wm = warp & 3, wn = warp >> 2;        // 4 row tiles of 16 x 2 column halves of 96
+
+  // the weight stream does not depend on the predecessor kernel: start it before waiting for it
+  // chunks 0..11: in_proj rows {q,k,v} x [h*64, h*64+64), k-chunk kc -> src = w_qkv + row * Wd + kc * 64 (three row blocks)
+  auto issue = [&](int ci) {
+    const int stage = ci % FA_ST;
+    if (ci < 12) {
+      // rows 0..63 -> q rows, 64..127 -> k rows, 128..191 -> v rows of this head
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int c = tid + i * 256;
+        const int r = c >> 3, ch = c & 7;
+        const int grow = (r >> 6) * Wd + h * AD + (r & 63);
+        cp_async16(sW + ((size_t)stage * FA_WN + r) * FA_LDW + ch * 8, w_qkv + (size_t)grow * Wd + ci * GBK + ch * 8, true);
+      }
+    } else {
+      // out_proj rows [(ci - 12) * 192, +192), columns [h*64, h*64+64)
+      fa_issue_chunk(sW, stage, w_out + (size_t)(ci - 12) * FA_WN * Wd + h * AD, Wd, tid);
+    }
+  };
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  for (int ci = 0; ci < FA_ST - 1; ++ci) { issue(ci); cp_async_commit(); }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- ln_1 of this image's T rows -> sA (fp16); rows T..63 zero; this CTA saves its 64 columns of x for the backward
+  for (int r = warp; r < FA_ROWS; r += 8) {
+    __half* dst = sA + (size_t)r * FA_LDA;
+    if (r >= T) {
+      for (int c = lane; c < Wd; c += 32) dst[c] = __float2half_rn(0.f);
+      continue;
+    }
+    const float* xr = x + ((size_t)b * T + r) * Wd;
+    float xv[kLnMax], gv[kLnMax], bv[kLnMax];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+      const int c = lane + 32 * i;
+      const bool ok = c < Wd;
+      xv[i] = ok ? xr[c] : 0.f; gv[i] = ok ? ln_g[c] : 0.f; bv[i] = ok ? ln_b[c] : 0.f;
+      s += xv[i];
+    }
+    const float mean = warp_sum(s) / (float)Wd;
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) { const int c = lane + 32 * i; const float d = (c < Wd) ? xv[i] - mean : 0.f; var += d * d; }
+    const float rstd = rsqrtf(warp_sum(var) / (float)Wd + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < kLnMax; ++i) {
+      const int c = lane + 32 * i;
+      if (c < Wd) {
+        dst[c] = __float2half_rn((xv[i] - mean) * rstd * gv[i] + bv[i]);
+        if (save_x && (c >> 6) == h) save_x[((size_t)b * T + r) * Wd + c] = xv[i];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- in_proj: [64 x 192] = sA[64 x 768] . Wh[192 x 768]^T, 12 k-chunks
+  float acc[12][4];
+#pragma unroll
+  for (int i = 0; i < 12; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  int ci = 0;
+  for (; ci < 12; ++ci) {
+    cp_async_wait<FA_ST - 2>();
+    __syncthreads();
+    if (ci + FA_ST - 1 < 16) issue(ci + FA_ST - 1);
+    cp_async_commit();
+    fa_mma_chunk(acc, sA + (size_t)(wm * 16) * FA_LDA + ci * GBK, FA_LDA, sW + ((size_t)(ci % FA_ST) * FA_WN + wn * 96) * FA_LDW, lane);
+  }
+  __syncthreads();      // every warp is done reading the tile: its region becomes q / k / v
+  {
+    const int r0 = wm * 16 + (lane >> 2);
+#pragma unroll
+    for (int nt = 0; nt < 12; ++nt) {
+      const int col = wn * 96 + nt * 8 + (lane & 3) * 2;           // 0..191: q | k | v
+      const int which = col >> 6, d = col & 63;
+      float* dstm = which == 0 ? q : (which == 1 ? k : v);
+      const float b0 = b_qkv[which * Wd + h * AD + d], b1 = b_qkv[which * Wd + h * AD + d + 1];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = r0 + 8 * hh;
+        const float v0 = acc[nt][2 * hh] + b0, v1 = acc[nt][2 * hh + 1] + b1;
+        if (r < AT) { dstm[r * AP + d] = v0; dstm[r * AP + d + 1] = v1; }
+        if (r < T) {
+          float* g = qkv_stash + ((size_t)b * T + r) * 3 * Wd + which * Wd + h * AD + d;
+          g[0] = v0; g[1] = v1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- softmax(q k^T / 8) v  (fp32, as k_attention)
+  for (int i = tid; i < T * T; i += 256) {
+    const int a = i / T, c = i % T;
+    float sc = 0.f;
+#pragma unroll
+    for (int d = 0; d < AD; d += 4)
+      sc = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), sc);
+    S[a * (AT + 1) + c] = sc * 0.125f;
+  }
+  __syncthreads();
+  for (int a = warp; a < T; a += 8) {
+    float mx = -1e30f;
+    for (int c = lane; c < T; c += 32) mx = fmaxf(mx, S[a * (AT + 1) + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < T; c += 32) { const float e = expf(S[a * (AT + 1) + c] - mx); S[a * (AT + 1) + c] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int c = lane; c < T; c += 32) S[a * (AT + 1) + c] *= inv;
+  }
+  __syncthreads();
+  for (int i = tid; i < FA_ROWS * (AD / 4); i += 256) {
+    const int a = i / (AD / 4), d = (i % (AD / 4)) * 4;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < T)
+      for (int c = 0; c < T; ++c) {
+        const float p = S[a * (AT + 1) + c];
+        const float4 vv = *reinterpret_cast<const float4*>(v + c * AP + d);
+        o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
+      }
+    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
+    *reinterpret_cast<uint2*>(o16 + (size_t)a * FA_LDW + d) = pk;
+  }
+  __syncthreads();
+
+  // ---- this head's slice of out_proj: part[64 x 768] = o16[64 x 64] . W_out[:, h*64 : h*64+64]^T in four 192-row chunks
+  for (; ci < 16; ++ci) {
+    cp_async_wait<FA_ST - 2>();
+    __syncthreads();
+    if (ci + FA_ST - 1 < 16) issue(ci + FA_ST - 1);
+    cp_async_commit();
+#pragma unroll
+    for (int i = 0; i < 12; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    fa_mma_chunk(acc, o16 + (size_t)(wm * 16) * FA_LDW, FA_LDW, sW + ((size_t)(ci % FA_ST) * FA_WN + wn * 96) * FA_LDW, lane);
+    const int r0 = wm * 16 + (lane >> 2);
+#pragma unroll
+    for (int nt = 0; nt < 12; ++nt) {
+      const int col = (ci - 12) * FA_WN + wn * 96 + nt * 8 + (lane & 3) * 2;
+      const float b0 = h == 0 ? b_out[col] : 0.f, b1 = h == 0 ? b_out[col + 1] : 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = r0 + 8 * hh;
+        if (r < T) {
+          float* g = attn_sum + ((size_t)b * T + r) * Wd + col;
+          atomicAdd(g, acc[nt][2 * hh] + b0);
+          atomicAdd(g + 1, acc[nt][2 * hh + 1] + b1);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Head: ln_post(x[b,0]) @ proj -> emb ; cosine with the text embedding.  One CTA per image.
 // ------------------------------------------------------------------------------------------------
@@ -966,6 +1215,7 @@ struct ClipWs {
   float* dpatch;     // [B*np][3pp]
   int* rowmap;       // [B*np]
   unsigned int* bar; // [32] grid-barrier counter of the persistent kernels (zeroed once per workspace)
+  float* attn_sum;   // [M][W] out-projection of the fused attention block, summed over heads (cleared by ln_2)
   size_t bytes;
 };
 
@@ -1007,6 +1257,7 @@ void carve_clip(const avc_clip_cfg& c, int B, int T, int np, int pp3, void* base
   w->dpatch = cv.take<float>((int64_t)B * np * pp3);
   w->rowmap = cv.take<int>((int64_t)B * np);
   w->bar = cv.take<unsigned int>(32);
+  w->attn_sum = cv.take<float>(M * Wd);
   w->bytes = cv.used();
 }
 
@@ -1298,15 +1549,38 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     EpiPatch e{w.tok_pre, T, Wd, np};
     AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 4, e));
   }
-  AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr));
+  AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr, nullptr, nullptr));
   AVC_LAUNCH_TRY();
+  // AVC_CLIP_FUSED_ATTN=1 (opt-in): ln_1 / in_proj / attention / out_proj as ONE kernel per (image, head) instead of four
+  // kernels.  Measured on B200 (r2): forward 1.05 ms against 0.60 ms -- 24 fat CTAs serialise what the chain spreads over
+  // 100-190 CTAs per kernel (7 LayerNorm rows per warp, 256-thread softmax, 38 k atomics per CTA) -- so it is off by default.
+  const char* fa_env = getenv("AVC_CLIP_FUSED_ATTN");
+  const bool fused_attn = (fa_env && atoi(fa_env) == 1) && T <= AT && Wd == 768 && Wd / cfg->heads == AD;
+  if (fused_attn) {
+    AVC_CUDA_TRY(cudaMemsetAsync(w.attn_sum, 0, sizeof(float) * (size_t)B * T * cfg->width, st));
+    static thread_local bool fa_attr = false;
+    if (!fa_attr) {
+      AVC_CUDA_TRY(cudaFuncSetAttribute(k_attn_block_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+      fa_attr = true;
+    }
+  }
   for (int l = 0; l < cfg->layers; ++l) {
     const avc_clip_layer_weights& lw = wt->layer[l];
     float* xs1 = w.xs + (size_t)(2 * l) * M * Wd;
     float* xs2 = w.xs + (size_t)(2 * l + 1) * M * Wd;
     float* qkv = w.qkv + (size_t)l * M * 3 * Wd;
     float* fcp = w.fc_pre + (size_t)l * M * cfg->mlp;
-    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1));
+    if (fused_attn) {
+      // ln_1 + in_proj + attention + out_proj of one (image, head) per CTA; the 12 partial out-projections meet in
+      // attn_sum, which ln_2 adds to the residual stream (and clears)
+      AVC_CUDA_TRY(launch_pdl(k_attn_block_fwd, dim3(B * cfg->heads), dim3(256), (size_t)FA_SMEM, st, (const float*)w.x, T, Wd,
+                              cfg->heads, lw.ln1_g, lw.ln1_b, (const __half*)lw.w_qkv, lw.b_qkv, (const __half*)lw.w_out,
+                              lw.b_out, xs1, qkv, w.attn_sum));
+      AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2,
+                              w.attn_sum, w.x));
+      AVC_LAUNCH_TRY();
+    } else {
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1, nullptr, nullptr));
     AVC_LAUNCH_TRY();
     { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e)); }
@@ -1314,8 +1588,9 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     AVC_LAUNCH_TRY();
     { EpiResidual e{w.x, Wd, lw.b_out};
       AVC_TRY(gemm16(st, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 2, e)); }
-    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2));
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2, nullptr, nullptr));
     AVC_LAUNCH_TRY();
+    }
     { EpiFc e{fcp, w.g16, cfg->mlp, lw.b_fc};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_fc, Wd, M, cfg->mlp, Wd, 1, e)); }
     { EpiResidual e{w.x, Wd, lw.b_proj};

@@ -195,7 +195,17 @@ class AppearanceTrainer:
         # too (AVC_GRAPH_ALLREDUCE=0, or a failing capture, falls back to launching them after the graph).
         import os
         self._graph_has_adam = True
-        want_inside = self.world == 1 or os.environ.get("AVC_GRAPH_ALLREDUCE", "1") != "0"
+        # (opt-in at N > 1: AVC_GRAPH_ALLREDUCE=1; the default keeps NCCL outside the capture, the structure measured at
+        # 2 / 4 / 8 GPUs in round 1)
+        want_inside = self.world == 1 or os.environ.get("AVC_GRAPH_ALLREDUCE", "0") == "1"
+        if want_inside and self.world > 1:
+            # NCCL sets its channels up lazily on the first collective: that must not happen inside a capture
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                avc_dist.allreduce_sum_(torch.zeros(1024, device=self.device), self.pg)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.device)
         g = None
         if want_inside:
             try:

@@ -18,17 +18,20 @@ def _tower(seed=0):
     return sd, ClipImageTower(sd, device="cuda")
 
 
-@pytest.fixture(params=["persistent", "chained"])
+@pytest.fixture(params=["chained", "persistent", "fused_attention"])
 def clip_mode(request):
-    """Both launch structures of the tower: the chain of stand-alone kernels (default) and one persistent cooperative
-    kernel per pass (AVC_CLIP_MEGA=1); same device functions, same results up to fp32 atomic order."""
-    old = os.environ.get("AVC_CLIP_MEGA")
+    """The launch structures of the tower: the chain of stand-alone kernels (default), one persistent cooperative kernel
+    per pass (AVC_CLIP_MEGA=1) and the chain with the attention half of every block as one kernel per (image, head)
+    (AVC_CLIP_FUSED_ATTN=1); same arithmetic, same results up to fp32 atomic order."""
+    old = {k: os.environ.get(k) for k in ("AVC_CLIP_MEGA", "AVC_CLIP_FUSED_ATTN")}
     os.environ["AVC_CLIP_MEGA"] = "1" if request.param == "persistent" else "0"
+    os.environ["AVC_CLIP_FUSED_ATTN"] = "1" if request.param == "fused_attention" else "0"
     yield request.param
-    if old is None:
-        os.environ.pop("AVC_CLIP_MEGA", None)
-    else:
-        os.environ["AVC_CLIP_MEGA"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.mark.parametrize("H", [160, 224, 256])
