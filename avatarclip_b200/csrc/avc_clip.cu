@@ -394,10 +394,10 @@ __global__ void k_cls_rows(const float* __restrict__ cls, const float* __restric
 // Rows are cached in registers (Wd <= 32 * kLnMax): one round trip to memory per operand instead of one per pass.
 constexpr int kLnMax = 32;
 
-template <class C>
-__device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
+template <bool ADD = false, class C>
+__device__ __forceinline__ void d_layernorm(const C& K_, const float* x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
             float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x, float* __restrict__ add = nullptr,
-            float* __restrict__ x_out = nullptr) {
+            float* x_out = nullptr) {
   // add != NULL: the row is x + add (the attention block's out-projection, accumulated by its head CTAs); the sum is
   // written back to x_out (the residual stream) and `add` is handed back cleared for the next layer
   int row = K_.bx * (K_.nt >> 5) + (K_.tid >> 5);
@@ -411,7 +411,7 @@ __device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict
     int c = lane + 32 * i;
     bool ok = c < Wd;
     xv[i] = ok ? xr[c] : 0.f; gv[i] = ok ? g[c] : 0.f; bv[i] = ok ? b[c] : 0.f;
-    if (add && ok) {
+    if (ADD && ok) {
       xv[i] += add[(size_t)row * Wd + c];
       add[(size_t)row * Wd + c] = 0.f;
       x_out[(size_t)row * Wd + c] = xv[i];
@@ -436,10 +436,17 @@ __device__ __forceinline__ void d_layernorm(const C& K_, const float* __restrict
 }
 __global__ void __launch_bounds__(256)
 k_layernorm(const float* __restrict__ x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
-            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x, float* __restrict__ add,
-            float* __restrict__ x_out) {
+            float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x) {
   pdl_enter();
-  d_layernorm(HwCtx(), x, M, Wd, g, b, y32, y16, save_x, add, x_out);
+  d_layernorm<false>(HwCtx(), x, M, Wd, g, b, y32, y16, save_x);
+}
+// x_mid = x + add (the fused attention block's summed out-projection), written back to x_out; add handed back cleared
+__global__ void __launch_bounds__(256)
+k_layernorm_add(const float* x, int M, int Wd, const float* __restrict__ g, const float* __restrict__ b,
+                float* __restrict__ y32, __half* __restrict__ y16, float* __restrict__ save_x, float* __restrict__ add,
+                float* x_out) {
+  pdl_enter();
+  d_layernorm<true>(HwCtx(), x, M, Wd, g, b, y32, y16, save_x, add, x_out);
 }
 
 // dx (+)= LN'(x)^T dy :  dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)); optionally also the row-scaled fp16
@@ -1549,7 +1556,7 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     EpiPatch e{w.tok_pre, T, Wd, np};
     AVC_TRY(gemm16(st, w.a0, pp3, (const __half*)wt->w_patch, pp3, B * np, Wd, pp3, 4, e));
   }
-  AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr, nullptr, nullptr));
+  AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.tok_pre, M, Wd, wt->ln_pre_g, wt->ln_pre_b, w.x, nullptr, nullptr));
   AVC_LAUNCH_TRY();
   // AVC_CLIP_FUSED_ATTN=1 (opt-in): ln_1 / in_proj / attention / out_proj as ONE kernel per (image, head) instead of four
   // kernels.  Measured on B200 (r2): forward 1.05 ms against 0.60 ms -- 24 fat CTAs serialise what the chain spreads over
@@ -1576,11 +1583,11 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
       AVC_CUDA_TRY(launch_pdl(k_attn_block_fwd, dim3(B * cfg->heads), dim3(256), (size_t)FA_SMEM, st, (const float*)w.x, T, Wd,
                               cfg->heads, lw.ln1_g, lw.ln1_b, (const __half*)lw.w_qkv, lw.b_qkv, (const __half*)lw.w_out,
                               lw.b_out, xs1, qkv, w.attn_sum));
-      AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2,
-                              w.attn_sum, w.x));
+      AVC_CUDA_TRY(launch_pdl(k_layernorm_add, dim3(ceil_div(M, 8)), dim3(256), 0, st, (const float*)w.x, M, Wd, lw.ln2_g, lw.ln2_b,
+                              (float*)nullptr, w.h16, xs2, w.attn_sum, w.x));
       AVC_LAUNCH_TRY();
     } else {
-    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1, nullptr, nullptr));
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln1_g, lw.ln1_b, nullptr, w.h16, xs1));
     AVC_LAUNCH_TRY();
     { EpiBiasStore e{qkv, 3 * Wd, lw.b_qkv};
       AVC_TRY(gemm16(st, w.h16, Wd, (const __half*)lw.w_qkv, Wd, M, 3 * Wd, Wd, 1, e)); }
@@ -1588,7 +1595,7 @@ int avc_clip_loss_fwd(const avc_clip_cfg* cfg, const avc_clip_weights* wt, const
     AVC_LAUNCH_TRY();
     { EpiResidual e{w.x, Wd, lw.b_out};
       AVC_TRY(gemm16(st, w.o16, Wd, (const __half*)lw.w_out, Wd, M, Wd, Wd, 2, e)); }
-    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2, nullptr, nullptr));
+    AVC_CUDA_TRY(launch_pdl(k_layernorm, dim3(ceil_div(M, 8)), dim3(256), 0, st, w.x, M, Wd, lw.ln2_g, lw.ln2_b, nullptr, w.h16, xs2));
     AVC_LAUNCH_TRY();
     }
     { EpiFc e{fcp, w.g16, cfg->mlp, lw.b_fc};

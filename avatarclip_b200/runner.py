@@ -281,13 +281,11 @@ class Runner:
             loss = tr.step(view, lr=self.current_lr(), cos_anneal=self.get_cos_anneal_ratio())
             self.iter_step += 1
             if not isinstance(self.writer, _NullWriter):
-                sc = tr.scalars                                                           # main.py:542-547
-                self.writer.add_scalar("Loss/loss", loss, self.iter_step)
-                self.writer.add_scalar("Loss/color_loss", sc[0], self.iter_step)
-                self.writer.add_scalar("Loss/eikonal_loss", sc[1], self.iter_step)
-                self.writer.add_scalar("Loss/cosine", tr.cos[0], self.iter_step)
-                self.writer.add_scalar("Statistics/s_val", tr._out["s_val"].mean(), self.iter_step)
-                self.writer.add_scalar("Statistics/psnr", sc[3], self.iter_step)
+                sc = tr.scalars                                                           # main.py:542-547 (one read-back)
+                vals = torch.stack([loss.reshape(()), sc[0], sc[1], tr.cos[0], tr._out["s_val"].mean(), sc[3]]).tolist()
+                for name, v in zip(("Loss/loss", "Loss/color_loss", "Loss/eikonal_loss", "Loss/cosine", "Statistics/s_val",
+                                    "Statistics/psnr"), vals):
+                    self.writer.add_scalar(name, v, self.iter_step)
             if self.iter_step % self.report_freq == 0:
                 log(self.base_exp_dir)
                 log("iter:{:8>d} loss = {} lr={}".format(self.iter_step, float(loss), self.current_lr()))

@@ -103,8 +103,11 @@ class AppearanceTrainer:
         bg = dv.ray_background if dv.bg_choice in (1, 2) else (torch.ones(3, device=self.device) if dv.bg_choice == 0 else None)
         bg_kind = 2 if dv.bg_choice in (1, 2) else (1 if dv.bg_choice == 0 else 0)
         jit = dv.jitter if r.perturb > 0 else None
+        # the output buffers are reused from step to step only while the ray count stays the same (the real loop's
+        # silhouettes give a different R every step)
+        reuse = self._out if (self._out is not None and self._out["color_fine"].shape[0] == dv.rays_o.shape[0]) else None
         out, ws, chunk = render_forward_raw(r, dv.rays_o, dv.rays_d, dv.near, dv.far, jit, bg, bg_kind, cos_anneal,
-                                            None, keep_ws=False, out=self._out)
+                                            None, keep_ws=False, out=reuse)
         self._out = out
         mark("render_fwd")
         si = losses.StepInputs(dv.pix, dv.in_mask, dv.true_rgb, dv.mask, dv.H, dv.W, dv.light_dir, dv.ambience,

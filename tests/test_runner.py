@@ -81,16 +81,27 @@ def test_runner_train_clip_real_loop_and_cli_order_resume(tmp_path):
     assert any("loss" in str(l) for l in logs)
     assert used[0] == r.encoded_face_text.data_ptr() and used[4] == r.encoded_face_text.data_ptr()   # iter_i % 4 == 0
     assert all(u in (r.encoded_text.data_ptr(), r.encoded_back_text.data_ptr()) for i, u in enumerate(used) if i % 4)
+    # a ray count above the renderer's chunk (4096) and different every step: chunked forward + recompute backward, output
+    # buffers re-sized per step
+    r.max_ray_num = 5000
+    r.report_freq = 1
+    logs2, rays = [], []
+    for _ in range(2):
+        assert r.train_clip(max_steps=2, log=logs2.append, validate=False) == r.iter_step      # a face step + a body step
+        rays.append(int(r.trainer._out["weights"].shape[0]))
+    vals = [float(str(m).split("loss = ")[1].split(" ")[0]) for m in logs2 if "loss = " in str(m)]
+    assert len(vals) == 4 and all(np.isfinite(vals)) and max(rays) > 4096 and max(rays) < 5200, (vals, rays)
+    r.max_ray_num = 600
     path = r.save_checkpoint()
     ck = torch.load(path, weights_only=False)
     assert len(ck["optimizer"]["state"]) == len(r._all_params())
     torch.optim.Adam(r._all_params(), lr=5e-4).load_state_dict(ck["optimizer"])       # reference-format Adam state
     # CLI order: constructor (loads the checkpoint) first, init_clip afterwards
     r2 = _runner(tmp_path, "cuda", is_continue=True)
-    assert r2.iter_step == 6 and r2.trainer is None and r2._pending_optimizer_state is not None
+    assert r2.iter_step == 10 and r2.trainer is None and r2._pending_optimizer_state is not None
     r2.init_clip(sd, text, face, back)
     tr2 = r2._ensure_trainer()
-    assert tr2.iter_step == 6 and torch.equal(tr2.exp_avg, r.trainer.exp_avg) and torch.equal(tr2.exp_avg_sq, r.trainer.exp_avg_sq)
+    assert tr2.iter_step == 10 and torch.equal(tr2.exp_avg, r.trainer.exp_avg) and torch.equal(tr2.exp_avg_sq, r.trainer.exp_avg_sq)
     assert float(tr2.exp_avg.abs().max()) > 0
     img = r2.render_image(ol.lookat([0.0, 0.0, 1.6], [0.0, 0.0, 0.0]), resolution_level=8)
     assert img.shape == (32, 32, 3) and torch.isfinite(img).all()

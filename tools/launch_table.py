@@ -47,6 +47,12 @@ def main():
     for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:50]:
         print(f"{v[1]:9.1f} us {100 * v[1] / T:5.1f}% n={v[0]:3d} avg {v[1] / v[0]:7.1f}  {k}")
     print()
+    print("fused value-chain launches of the step (k_sdf_chain): grid, us, DRAM MB (read+write)")
+    for d in W:
+        if "k_sdf_chain" in d["name"]:
+            mb = (d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)) / 1e6
+            print(f"  k_sdf_chain    grid {int(d.get('launch__grid_size', 0)):4d} {d['gpu__time_duration.sum']:7.1f} us {mb:7.1f} MB")
+    print()
     print("tcgen05 NT launches of the step, in launch order: epilogue, grid, us, DRAM MB (read+write), GB/s")
     for d in W:
         if "gemm_tc_nt" in d["name"]:
