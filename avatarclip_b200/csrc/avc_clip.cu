@@ -588,6 +588,39 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
 }
 
+
+// 64 x 64 x 64 tile product on the tensor cores for the attention kernels (16 warps): C(m, n) = sum_k A(m, k) B(k, n) with
+// TF32 operands (mma.sync.m16n8k8, fp32 accumulate: the same 10-bit mantissa as the fp16 matmuls of the reference's CUDA
+// path, fp32 range).  fa(m, k) / fb(k, n) fetch (guarded) elements from shared memory; warp w owns the 16-row tile w / 4 and
+// the two 8-column tiles 2 (w % 4), 2 (w % 4) + 1:  c[j][0..3] = C(m0+g, n0+8j+2t), (.., +1), (m0+g+8, ..), (.., +1).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm volatile("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+template <class FA, class FB>
+__device__ __forceinline__ void mma_tf32_64(float (&c)[2][4], int warp, int lane, FA&& fa, FB&& fb) {
+  const int g = lane >> 2, t = lane & 3, m0 = (warp >> 2) * 16, n0 = (warp & 3) * 16;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[j][i] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const int k0 = ks * 8;
+    const uint32_t a0 = to_tf32(fa(m0 + g, k0 + t)), a1 = to_tf32(fa(m0 + g + 8, k0 + t));
+    const uint32_t a2 = to_tf32(fa(m0 + g, k0 + t + 4)), a3 = to_tf32(fa(m0 + g + 8, k0 + t + 4));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t b0 = to_tf32(fb(k0 + t, n0 + 8 * j + g)), b1 = to_tf32(fb(k0 + t + 4, n0 + 8 * j + g));
+      asm volatile(
+          "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+          : "+f"(c[j][0]), "+f"(c[j][1]), "+f"(c[j][2]), "+f"(c[j][3])
+          : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+  }
+}
+
 template <class C>
 __device__ __forceinline__ void d_attention(const C& K_, const float* __restrict__ qkv, int T, int Wd, int heads, __half* __restrict__ o16) {
   float* sm = reinterpret_cast<float*>(K_.smem);
@@ -623,16 +656,21 @@ __device__ __forceinline__ void d_attention(const C& K_, const float* __restrict
     }
   }
   K_.sync();
-  for (int i = K_.tid; i < T * T; i += K_.nt) {
-    int a = i / T, c = i % T;
-    float s = 0.f;
+  const int lane = K_.tid & 31, warp = K_.tid >> 5;
+  {   // S = q k^T / sqrt(64) on the tensor cores
+    float c[2][4];
+    mma_tf32_64(c, warp, lane, [&](int m, int kk) { return m < T ? q[m * AP + kk] : 0.f; },
+                [&](int kk, int n) { return n < T ? k[n * AP + kk] : 0.f; });
+    const int g = lane >> 2, t = lane & 3, m0 = (warp >> 2) * 16, n0 = (warp & 3) * 16;
 #pragma unroll
-    for (int d = 0; d < AD; d += 4)
-      s = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), s);
-    S[a * (AT + 1) + c] = s * 0.125f;          // 1/sqrt(64)
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + g + 8 * (i >> 1), n = n0 + 8 * j + 2 * t + (i & 1);
+        if (m < T && n < T) S[m * (AT + 1) + n] = c[j][i] * 0.125f;
+      }
   }
   K_.sync();
-  const int lane = K_.tid & 31, warp = K_.tid >> 5;
   for (int a = warp; a < T; a += (K_.nt >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, S[a * (AT + 1) + c]);
@@ -645,18 +683,19 @@ __device__ __forceinline__ void d_attention(const C& K_, const float* __restrict
     for (int c = lane; c < T; c += 32) S[a * (AT + 1) + c] *= inv;
   }
   K_.sync();
-  for (int i = K_.tid; i < T * (AD / 4); i += K_.nt) {
-    int a = i / (AD / 4), d = (i % (AD / 4)) * 4;
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < T; ++c) {
-      const float p = S[a * (AT + 1) + c];
-      const float4 vv = *reinterpret_cast<const float4*>(v + c * AP + d);
-      o.x = fmaf(p, vv.x, o.x); o.y = fmaf(p, vv.y, o.y); o.z = fmaf(p, vv.z, o.z); o.w = fmaf(p, vv.w, o.w);
-    }
-    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<unsigned*>(&h0); pk.y = *reinterpret_cast<unsigned*>(&h1);
-    *reinterpret_cast<uint2*>(o16 + ((size_t)b * T + a) * Wd + h * AD + d) = pk;
+  {   // o = P v on the tensor cores -> fp16 operand of out_proj
+    float c[2][4];
+    mma_tf32_64(c, warp, lane, [&](int m, int kk) { return (m < T && kk < T) ? S[m * (AT + 1) + kk] : 0.f; },
+                [&](int kk, int n) { return kk < T ? v[kk * AP + n] : 0.f; });
+    const int g = lane >> 2, t = lane & 3, m0 = (warp >> 2) * 16, n0 = (warp & 3) * 16;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = m0 + g + 8 * hh, n = n0 + 8 * j + 2 * t;
+        if (m < T)
+          *reinterpret_cast<__half2*>(o16 + ((size_t)b * T + m) * Wd + h * AD + n) = __floats2half2_rn(c[j][2 * hh], c[j][2 * hh + 1]);
+      }
   }
 }
 __global__ void __launch_bounds__(512)
@@ -707,19 +746,23 @@ __device__ __forceinline__ void d_attention_bwd(const C& K_, const float* __rest
     }
   }
   K_.sync();
-  for (int i = K_.tid; i < T * T; i += K_.nt) {
-    int a = i / T, c = i % T;
-    float s = 0.f, dp = 0.f;
+  const int lane = K_.tid & 31, warp = K_.tid >> 5;
+  const int fg = lane >> 2, ft = lane & 3, fm0 = (warp >> 2) * 16, fn0 = (warp & 3) * 16;      // C-fragment coordinates
+  {   // S = q k^T / 8 and dP = dO v^T on the tensor cores
+    float c[2][4], e[2][4];
+    mma_tf32_64(c, warp, lane, [&](int m, int kk) { return m < T ? q[m * AP + kk] : 0.f; },
+                [&](int kk, int n) { return n < T ? k[n * AP + kk] : 0.f; });
+    mma_tf32_64(e, warp, lane, [&](int m, int kk) { return m < T ? dO_s[m * AP + kk] : 0.f; },
+                [&](int kk, int n) { return n < T ? v[n * AP + kk] : 0.f; });
 #pragma unroll
-    for (int d = 0; d < AD; d += 4) {
-      s = dot4(*reinterpret_cast<const float4*>(q + a * AP + d), *reinterpret_cast<const float4*>(k + c * AP + d), s);
-      dp = dot4(*reinterpret_cast<const float4*>(dO_s + a * AP + d), *reinterpret_cast<const float4*>(v + c * AP + d), dp);
-    }
-    Pm[a * (AT + 1) + c] = s * 0.125f;
-    dS[a * (AT + 1) + c] = dp;               // dP for now
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = fm0 + fg + 8 * (i >> 1), n = fn0 + 8 * j + 2 * ft + (i & 1);
+        if (m < T && n < T) { Pm[m * (AT + 1) + n] = c[j][i] * 0.125f; dS[m * (AT + 1) + n] = e[j][i]; }      // dP for now
+      }
   }
   K_.sync();
-  const int lane = K_.tid & 31, warp = K_.tid >> 5;
   for (int a = warp; a < T; a += (K_.nt >> 5)) {
     float mx = -1e30f;
     for (int c = lane; c < T; c += 32) mx = fmaxf(mx, Pm[a * (AT + 1) + c]);
@@ -735,22 +778,25 @@ __device__ __forceinline__ void d_attention_bwd(const C& K_, const float* __rest
   }
   K_.sync();
   float* dbase = dqkv + (size_t)b * T * 3 * Wd;
-  for (int i = K_.tid; i < T * (AD / 4); i += K_.nt) {
-    int t = i / (AD / 4), d = (i % (AD / 4)) * 4;
-    float4 dq = make_float4(0.f, 0.f, 0.f, 0.f), dk = dq, dv = dq;
-    for (int c = 0; c < T; ++c) {
-      const float s_tc = dS[t * (AT + 1) + c], s_ct = dS[c * (AT + 1) + t], p_ct = Pm[c * (AT + 1) + t];
-      const float4 kc = *reinterpret_cast<const float4*>(k + c * AP + d);
-      const float4 qc = *reinterpret_cast<const float4*>(q + c * AP + d);
-      const float4 oc = *reinterpret_cast<const float4*>(dO_s + c * AP + d);
-      dq.x = fmaf(s_tc, kc.x, dq.x); dq.y = fmaf(s_tc, kc.y, dq.y); dq.z = fmaf(s_tc, kc.z, dq.z); dq.w = fmaf(s_tc, kc.w, dq.w);
-      dk.x = fmaf(s_ct, qc.x, dk.x); dk.y = fmaf(s_ct, qc.y, dk.y); dk.z = fmaf(s_ct, qc.z, dk.z); dk.w = fmaf(s_ct, qc.w, dk.w);
-      dv.x = fmaf(p_ct, oc.x, dv.x); dv.y = fmaf(p_ct, oc.y, dv.y); dv.z = fmaf(p_ct, oc.z, dv.z); dv.w = fmaf(p_ct, oc.w, dv.w);
-    }
-    float* r = dbase + (size_t)t * 3 * Wd + h * AD + d;
-    *reinterpret_cast<float4*>(r) = dq;
-    *reinterpret_cast<float4*>(r + Wd) = dk;
-    *reinterpret_cast<float4*>(r + 2 * Wd) = dv;
+  {   // dq = dS k, dk = dS^T q, dv = P^T dO on the tensor cores
+    float cq[2][4], ck[2][4], cv[2][4];
+    auto dS_at = [&](int a, int c) { return (a < T && c < T) ? dS[a * (AT + 1) + c] : 0.f; };
+    auto P_at = [&](int a, int c) { return (a < T && c < T) ? Pm[a * (AT + 1) + c] : 0.f; };
+    mma_tf32_64(cq, warp, lane, [&](int m, int kk) { return dS_at(m, kk); }, [&](int kk, int n) { return kk < T ? k[kk * AP + n] : 0.f; });
+    mma_tf32_64(ck, warp, lane, [&](int m, int kk) { return dS_at(kk, m); }, [&](int kk, int n) { return kk < T ? q[kk * AP + n] : 0.f; });
+    mma_tf32_64(cv, warp, lane, [&](int m, int kk) { return P_at(kk, m); }, [&](int kk, int n) { return kk < T ? dO_s[kk * AP + n] : 0.f; });
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = fm0 + fg + 8 * hh, n = fn0 + 8 * j + 2 * ft;
+        if (m < T) {
+          float* r = dbase + (size_t)m * 3 * Wd + h * AD + n;
+          *reinterpret_cast<float2*>(r) = make_float2(cq[j][2 * hh], cq[j][2 * hh + 1]);
+          *reinterpret_cast<float2*>(r + Wd) = make_float2(ck[j][2 * hh], ck[j][2 * hh + 1]);
+          *reinterpret_cast<float2*>(r + 2 * Wd) = make_float2(cv[j][2 * hh], cv[j][2 * hh + 1]);
+        }
+      }
   }
 }
 __global__ void __launch_bounds__(512)
