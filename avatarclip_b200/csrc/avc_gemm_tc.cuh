@@ -261,6 +261,40 @@ struct EpiTraits<E, std::void_t<typename E::Aux>> {
   static __device__ __forceinline__ Aux prefetch(const E& e, int r, int c) { return e.prefetch(r, c); }
   static __device__ __forceinline__ void apply(const E& e, int r, int c, float4 a, const Aux& x) { e(r, c, a, x); }
 };
+// A full 32-row sub-block hands every thread FOUR groups of the same 4 columns, rows r, r + 8, r + 16, r + 24.  Functors
+// with a member `quad(row, col, acc[4], aux[4])` take them together: the column-range test and the null checks of the
+// optional outputs (uniform per launch, but each one a branch that ends a scheduling region) are then made once per four
+// groups and the four groups' loads / math / stores sit in one straight-line region the scheduler can interleave.
+// Operands of the four groups of a sub-block (rows row + 8 p, clamped to row_last).  Functors whose operands depend on
+// the column only (biases) provide `prefetch4(col, aux[4])` and load them once instead of four times.
+template <typename E, typename = void>
+struct EpiPrefetch4 {
+  template <typename Aux>
+  static __device__ __forceinline__ void run(const E& e, int row, int row_last, int col, Aux (&dst)[4]) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) dst[p] = EpiTraits<E>::prefetch(e, min(row + 8 * p, row_last), col);
+  }
+};
+template <typename E>
+struct EpiPrefetch4<E, std::void_t<decltype(&E::prefetch4)>> {
+  template <typename Aux>
+  static __device__ __forceinline__ void run(const E& e, int, int, int col, Aux (&dst)[4]) { e.prefetch4(col, dst); }
+};
+template <typename E, typename = void>
+struct EpiQuad {
+  template <typename Aux>
+  static __device__ __forceinline__ void run(const E& e, int r, int c, const float4 (&a)[4], const Aux (&x)[4]) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) EpiTraits<E>::apply(e, r + 8 * p, c, a[p], x[p]);
+  }
+};
+template <typename E>
+struct EpiQuad<E, std::void_t<decltype(&E::quad)>> {
+  template <typename Aux>
+  static __device__ __forceinline__ void run(const E& e, int r, int c, const float4 (&a)[4], const Aux (&x)[4]) {
+    e.quad(r, c, a, x);
+  }
+};
 
 // Persistent: gridDim.x CTAs (<= one per SM, a multiple of the number of column tiles); a CTA keeps one column tile
 // and walks the row tiles m_first, +m_stride, ...  The accumulator is multi-buffered in TMEM (NBUF x BN columns) so
@@ -410,8 +444,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     auto issue = [&](Aux (&dst)[4], int mt, int sb) {
       const int row = min(mt, tiles_m - 1) * kBM + q * 32 + ri;
       const int col = min(n0 + (cw + sb * (EW / 4)) * 16 + cg, col_last);
-#pragma unroll
-      for (int p = 0; p < 4; ++p) dst[p] = Tr::prefetch(epi, min(row + 8 * p, row_last), col);
+      EpiPrefetch4<Epi>::run(epi, row, row_last, col, dst);
     };
 #pragma unroll
     for (int s = 0; s < NPF; ++s) issue(aux[s], m_first, s);
@@ -435,10 +468,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
             st_shared_v4(st_row + (((uint32_t)c4 ^ st_sw) << 4), r[4 * c4], r[4 * c4 + 1], r[4 * c4 + 2], r[4 * c4 + 3]);
           __syncwarp();
           if (col0 + cg < N) {
+            if (nrows == 32) {      // full sub-block: no row guards, the four groups go to the functor together
+              float4 acc[4];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              const int i = ri + 8 * p;
-              if (i < nrows) Tr::apply(epi, row0 + i, col0 + cg, ld_shared_v4(ld_addr + (uint32_t)p * 512u), aux[sb % NPF][p]);
+              for (int p = 0; p < 4; ++p) acc[p] = ld_shared_v4(ld_addr + (uint32_t)p * 512u);
+              EpiQuad<Epi>::run(epi, row0 + ri, col0 + cg, acc, aux[sb % NPF]);
+            } else {
+#pragma unroll
+              for (int p = 0; p < 4; ++p) {
+                const int i = ri + 8 * p;
+                if (i < nrows) Tr::apply(epi, row0 + i, col0 + cg, ld_shared_v4(ld_addr + (uint32_t)p * 512u), aux[sb % NPF][p]);
+              }
             }
           }
           __syncwarp();

@@ -30,14 +30,23 @@ inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) /
 // B operands are addressed by their offset in the packed-weight buffer (same offset in the bf16 split).
 inline Split16 with_ld(Split16 s, int ld) { s.ld = ld; return s; }
 
-template <typename Epi>
+// NP: MMAs per product on the tcgen05 engine: 3 = two-term split operands, 1 = the hi halves only (single-pass bf16).
+template <int NP = 3, typename Epi>
 int gemm_nt(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int N, int K, const float* A, int lda,
             const Split16& A16, int64_t pk_off, int ldb, const Epi& epi) {
   if (pl.cfg.engine == 1) {
     tc::SplitPtr a{A16.hi, A16.lo, lda}, b{w.pk_hi + pk_off, w.pk_lo + pk_off, ldb};
-    return tc::launch_gemm_tc_nt<3, Epi>(st, M, N, K, a, b, epi);
+    return tc::launch_gemm_tc_nt<NP, Epi>(st, M, N, K, a, b, epi);
   }
   return launch_gemm_nt(st, M, N, (int)round_up(K, 4), A, lda, w.pack + pk_off, ldb, epi);
+}
+// The colour net (it tolerates single-pass bf16) runs with cfg.color_products MMAs per product.
+inline bool color_single(const NeusPlan& pl) { return pl.cfg.engine == 1 && pl.cfg.color_products == 1; }
+template <typename Epi>
+int gemm_nt_color(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int N, int K, const float* A, int lda,
+                  const Split16& A16, int64_t pk_off, int ldb, const Epi& epi) {
+  return color_single(pl) ? gemm_nt<1>(pl, w, st, M, N, K, A, lda, A16, pk_off, ldb, epi)
+                          : gemm_nt<3>(pl, w, st, M, N, K, A, lda, A16, pk_off, ldb, epi);
 }
 
 int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float scale, float* out);
@@ -46,10 +55,11 @@ int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float sca
 // tcgen05 kernel as one extra 16-wide MMA against a tile of ones, a separate column-sum kernel for the fp32 engine.
 inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t P, int N1, int N2, const float* A,
                    int lda, const Split16& A16, const float* B, int ldb, const Split16& B16, float* C, int ldc,
-                   float* bias_out = nullptr) {
+                   float* bias_out = nullptr, bool single = false) {
   (void)w;
   if (pl.cfg.engine == 1) {
     tc::SplitPtr a{A16.hi, A16.lo, lda}, b{B16.hi, B16.lo, ldb};
+    if (single) return tc::launch_gemm_tc_tn<1>(st, P, N1, N2, a, b, C, ldc, bias_out);
     return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, ldc, bias_out);
   }
   AVC_TRY(launch_gemm_tn(st, P, N1, N2, A, lda, B, ldb, C, ldc));
@@ -341,11 +351,11 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
     // tcgen05 engine: the fp32 copy of a hidden colour activation is only read by the heads (layer Lc)
     const bool tc1 = pl.cfg.engine == 1;
     EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0xT, pl.Hc, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc, w.ch16[1]};
-    AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
+    AVC_TRY(gemm_nt_color(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
     for (int l = 1; l < pl.Lc; ++l) {
       const LinDim& c = pl.col[l];
       EpiRelu e{pack + c.pk_b, (tc1 && l + 1 < pl.Lc) ? nullptr : w.ch[l + 1], pl.Hc, w.ch16[l + 1]};
-      AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, w.ch16[l], c.pk_W, pl.Hc, e));
+      AVC_TRY(gemm_nt_color(pl, w, st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, w.ch16[l], c.pk_W, pl.Hc, e));
     }
     OutHeads oh{w.rgb6};
     k_thin_nt<6, OutHeads><<<blocks_for(P, 8), 256, 0, st>>>(w.ch[pl.Lc], pl.Hc, pl.Hc, pack + pl.pk_W6, pl.Hc,
@@ -420,21 +430,21 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     float* cb = w.cbar[cur];
     if (l > 0) {
       AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], w.ch[l], pl.Hc, w.ch16[l], wbar + c.off_v, c.K,
-                      wbar + c.off_b));
+                      wbar + c.off_b, color_single(pl)));
       // tcgen05 engine: ReLU mask from the split of ch[l]; the fp32 copy of cbar is only read at layer 0 (thin ops)
       const bool tc1 = pl.cfg.engine == 1;
       EpiDgradRelu e{tc1 ? nullptr : w.ch[l], w.ch16[l].hi, (tc1 && l > 1) ? nullptr : w.cbar[cur ^ 1], pl.Hc,
                      w.cbar16[cur ^ 1]};
-      AVC_TRY(gemm_nt(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, e));
+      AVC_TRY(gemm_nt_color(pl, w, st, P, pl.Hc, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, e));
       cur ^= 1;
     } else {
       // lin0 input = [x(3), n(3), feat(F)]: dW[:, 6:] += cbar^T feat ; dW[:, :6] += cbar^T cin6
       AVC_TRY(gemm_tn(pl, w, st, P, pl.Hc, pl.F, cb, pl.Hc, w.cbar16[cur], w.feat, pl.Fp, w.feat16, wbar + c.off_v + 6, c.K,
-                      wbar + c.off_b));
+                      wbar + c.off_b, color_single(pl)));
       AVC_TRY(thin_tn<6>(st, w.cin, 8, 1.f, cb, pl.Hc, pl.Hc, P, wbar + c.off_v, 1, c.K, nullptr));
       // featbar = cbar . W0[:, 6:]
       EpiStore es{pl.cfg.engine == 1 ? nullptr : w.featbar, pl.Fp, pl.F, w.featbar16};
-      AVC_TRY(gemm_nt(pl, w, st, P, pl.F, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, es));
+      AVC_TRY(gemm_nt_color(pl, w, st, P, pl.F, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, es));
       // nbar += cbar . W0[:, 3:6]   (d/d points is discarded: pts is a leaf, models/fields.py:97)
       OutNbarAdd on{w.nbar};
       k_thin_nt<6, OutNbarAdd><<<blocks_for(P, 8), 256, 0, st>>>(cb, pl.Hc, pl.Hc, pack + pl.pk_c0xT, pl.Hc, nullptr,

@@ -10,6 +10,7 @@ fused Adam and the multi-GPU gradient all-reduce operate on.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -174,7 +175,8 @@ class NeuSRenderer:
     shipped conf -- main.py:136; the reference's ``render_core_outside`` is dead code there)."""
 
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
-                 up_sample_steps, perturb, extra_color=False, engine: int = 0, max_rays_per_chunk: int = 4096):
+                 up_sample_steps, perturb, extra_color=False, engine: int = 0, max_rays_per_chunk: int = 4096,
+                 color_products: Optional[int] = None):
         if n_outside != 0:
             raise NotImplementedError("n_outside > 0 (NeRF background) is not part of the AvatarCLIP hot path")
         if not extra_color:
@@ -193,7 +195,9 @@ class NeuSRenderer:
             col_d_feature=color_network.d_feature, col_d_hidden=color_network.d_hidden,
             col_n_layers=color_network.n_layers,
             n_samples=self.n_samples, n_importance=self.n_importance, up_sample_steps=self.up_sample_steps,
-            engine=int(engine))
+            engine=int(engine),
+            # tcgen05 engine: MMAs per product in the colour net; None -> AVC_COLOR_PRODUCTS (default 3 = split operands)
+            color_products=int(os.environ.get("AVC_COLOR_PRODUCTS", "3") if color_products is None else color_products))
         self._flat: Optional[FlatParams] = None
         self._hook = torch.zeros((), requires_grad=True)
         self._ws_cache: Dict[int, torch.Tensor] = {}

@@ -37,7 +37,7 @@ typedef void* avc_stream_t; /* cudaStream_t */
 #define AVC_E_ALIGN (-4)    /* pointer not 16-byte aligned                              */
 #define AVC_E_NOSTASH (-5)  /* backward called on a workspace with no matching forward  */
 
-#define AVC_ABI_VERSION 1
+#define AVC_ABI_VERSION 2
 int avc_abi_version(void);
 /* Compiled-for architecture string, e.g. "sm_100a". */
 const char* avc_build_arch(void);
@@ -68,6 +68,9 @@ typedef struct avc_neus_cfg {
   /* arithmetic engine for the MLP contractions: 0 = fp32 CUDA-core (FFMA) tiles,
    * 1 = tcgen05 tensor-core tiles with two-term split operands (3 MMAs per product) */
   int32_t engine;
+  /* tcgen05 engine only: MMAs per product in the COLOUR net (forward, dgrad, wgrad).  3 (or 0) = the same two-term split
+   * as the SDF trunk; 1 = single-pass bf16 on the hi halves (the colour net tolerates it). */
+  int32_t color_products;
 } avc_neus_cfg;
 
 /* Flat parameter vector layout (fp32), identical for the gradient vector:
