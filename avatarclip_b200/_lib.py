@@ -10,6 +10,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libavc_b200.so")
+# diagnostic builds (e.g. the NT stall probe of tools/nt_probe.py) live next to the product library
+if os.environ.get("AVC_B200_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["AVC_B200_LIB"])
 
 _ERR = {
     -1: "AVC_E_BADCFG (unsupported configuration)",

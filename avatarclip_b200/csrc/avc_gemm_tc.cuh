@@ -47,6 +47,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spins > (1u << 26)) __trap();      // ~seconds: far beyond any legitimate wait, short of the box's watchdog
   }
 }
+// Optional stall probe of the NT kernel (compile with -DAVC_NT_PROBE=1, see tools/nt_probe.py): cycles the TMA warp waits
+// for a free stage, the MMA warp for operands / for a drained accumulator, one epilogue warp for a finished accumulator,
+// and each role's total loop time, summed over the CTAs of every launch, per epilogue functor (Epi::kProbeId).
+#ifdef AVC_NT_PROBE
+static __device__ unsigned long long g_nt_probe[16][8];
+#define AVC_PROBE_WAIT(acc, bar, par) do { long long t__ = clock64(); mbar_wait(bar, par); (acc) += clock64() - t__; } while (0)
+#define AVC_PROBE_DECL(name) long long name = 0
+#define AVC_PROBE_NOW() clock64()
+#define AVC_PROBE_ADD(id, slot, v) atomicAdd(&g_nt_probe[id][slot], (unsigned long long)(v))
+#else
+#define AVC_PROBE_WAIT(acc, bar, par) mbar_wait(bar, par)
+#define AVC_PROBE_DECL(name)
+#define AVC_PROBE_NOW() 0
+#define AVC_PROBE_ADD(id, slot, v)
+#endif
+template <typename E, typename = void>
+struct EpiNoAPf { static constexpr bool value = false; };
+template <typename E>
+struct EpiNoAPf<E, std::void_t<decltype(E::kNoATilePrefetch)>> { static constexpr bool value = E::kNoATilePrefetch; };
+template <typename E, typename = void>
+struct EpiProbeId { static constexpr int value = 0; };
+template <typename E>
+struct EpiProbeId<E, std::void_t<decltype(E::kProbeId)>> { static constexpr int value = E::kProbeId; };
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -265,6 +289,31 @@ struct EpiTraits<E, std::void_t<typename E::Aux>> {
 // with a member `quad(row, col, acc[4], aux[4])` take them together: the column-range test and the null checks of the
 // optional outputs (uniform per launch, but each one a branch that ends a scheduling region) are then made once per four
 // groups and the four groups' loads / math / stores sit in one straight-line region the scheduler can interleave.
+// The epilogue's own global operands (stashes written passes ago: always DRAM misses) are register-prefetched only one
+// sub-block ahead -- far less than a loaded DRAM latency.  Functors with `l2_prefetch(m0, n0, bn, M, et, nth)` get the
+// chance to pull the NEXT row tile's operand lines into L2 a whole tile ahead (thread et of nth epilogue threads).
+template <int ES>   // element size in bytes; [rows][ld] row-major array, tile rows [m0, m0 + 128) x columns [n0, n0 + bn)
+__device__ __forceinline__ void l2_prefetch_tile(const void* base, int ld, int ncols, int m0, int n0, int bn, int M,
+                                                 int et, int nth) {
+  constexpr int kPerLine = 128 / ES;
+  const int lpr = (bn + kPerLine - 1) / kPerLine;
+  for (int i = et; i < kBM * lpr; i += nth) {
+    const int row = m0 + i / lpr, col = n0 + (i % lpr) * kPerLine;
+    if (row < M && col < ncols)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(base) + ((size_t)row * ld + col) * ES));
+  }
+}
+template <typename E, typename = void>
+struct EpiL2 {
+  static __device__ __forceinline__ void run(const E&, int, int, int, int, int, int) {}
+};
+template <typename E>
+struct EpiL2<E, std::void_t<decltype(&E::l2_prefetch)>> {
+  static __device__ __forceinline__ void run(const E& e, int m0, int n0, int bn, int M, int et, int nth) {
+    if (m0 < M) e.l2_prefetch(m0, n0, bn, M, et, nth);
+  }
+};
+
 // Operands of the four groups of a sub-block (rows row + 8 p, clamped to row_last).  Functors whose operands depend on
 // the column only (biases) provide `prefetch4(col, aux[4])` and load them once instead of four times.
 template <typename E, typename = void>
@@ -346,15 +395,16 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      // Optional (AVC_NT_L2PF=1, kernel argument l2pf): pull the A boxes of the NEXT row tile into L2 while this one is
-      // loaded, so that the ring's loads see L2 latency.  Measured on B200: no change (2.77 vs 2.76 ms per step), i.e.
-      // the depth of the A ring is not what bounds these launches; off by default.
+      // l2pf (see the launcher): pull the A boxes of the NEXT row tile into L2 while this one is loaded, so that the
+      // ring's loads see L2 latency.
       if (l2pf && m_first < tiles_m)
         for (int kb = 0; kb < nk; ++kb) {
           tma_prefetch_2d(&mapAhi, kb * kBK, m_first * kBM);
           if (NPROD == 3) tma_prefetch_2d(&mapAlo, kb * kBK, m_first * kBM);
         }
       int it = 0;
+      AVC_PROBE_DECL(w_empty);
+      const long long t_tma0 = AVC_PROBE_NOW();
       for (int mt = m_first; mt < tiles_m; mt += m_stride) {
         const int m0 = mt * kBM;
         const bool pf = l2pf && (mt + m_stride < tiles_m);
@@ -370,7 +420,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
             if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull + 8 * kb);
           }
           const int s = it % Cfg::STAGES;
-          mbar_wait(empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
+          AVC_PROBE_WAIT(w_empty, empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
           const uint32_t st = smem_base + s * Cfg::STAGE_BYTES;
           mbar_expect_tx(full0 + 8 * s, Cfg::STAGE_BYTES);
           tma_load_2d(st, &mapAhi, kb * kBK, m0, full0 + 8 * s);
@@ -381,6 +431,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           }
         }
       }
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 0, w_empty);
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 1, AVC_PROBE_NOW() - t_tma0);
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 7, 1);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -389,15 +442,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     // so the descriptors are derived by adding constants to one base per operand and k-block.
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
     int it = 0, lt = 0;
+    AVC_PROBE_DECL(w_tempty); AVC_PROBE_DECL(w_full);
+    const long long t_mma0 = AVC_PROBE_NOW();
     for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
       const uint32_t buf = lt % NBUF;
-      mbar_wait(tempty0 + 8 * buf, ((lt / NBUF) & 1) ^ 1);   // epilogue has drained this accumulator
+      AVC_PROBE_WAIT(w_tempty, tempty0 + 8 * buf, ((lt / NBUF) & 1) ^ 1);   // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
       for (int kb = 0; kb < nk; ++kb, ++it) {
         const int s = it % Cfg::STAGES;
         if (RESB && lt == 0) mbar_wait(bfull + 8 * kb, 0);      // this k-block of the B panel has landed (first tile only)
-        mbar_wait(full0 + 8 * s, (it / Cfg::STAGES) & 1);
+        AVC_PROBE_WAIT(w_full, full0 + 8 * s, (it / Cfg::STAGES) & 1);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
@@ -419,6 +474,11 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
         }
         __syncwarp();
       }
+    }
+    if (lane == 0) {
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 2, w_tempty);
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 3, w_full);
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 4, AVC_PROBE_NOW() - t_mma0);
     }
   } else {
     using Tr = EpiTraits<Epi>;
@@ -449,10 +509,15 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 #pragma unroll
     for (int s = 0; s < NPF; ++s) issue(aux[s], m_first, s);
     int lt = 0;
+    AVC_PROBE_DECL(w_tfull);
+    const long long t_epi0 = AVC_PROBE_NOW();
+    const int et = (int)threadIdx.x - 64;
+    EpiL2<Epi>::run(epi, m_first * kBM, n0, BN, M, et, 32 * EW);
     for (int mt = m_first; mt < tiles_m; mt += m_stride, ++lt) {
       const int m0 = mt * kBM;
       const uint32_t buf = lt % NBUF;
-      mbar_wait(tfull0 + 8 * buf, (lt / NBUF) & 1);
+      EpiL2<Epi>::run(epi, (mt + m_stride) * kBM, n0, BN, M, et, 32 * EW);     // a whole tile ahead of its use
+      AVC_PROBE_WAIT(w_tfull, tfull0 + 8 * buf, (lt / NBUF) & 1);
       tc_fence_after();
       const int row0 = m0 + q * 32;
       const int nrows = min(32, M - row0);
@@ -489,6 +554,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * buf);    // this warp no longer reads accumulator `buf`
+    }
+    if (warp == 2 && lane == 0) {
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 5, w_tfull);
+      AVC_PROBE_ADD(EpiProbeId<Epi>::value, 6, AVC_PROBE_NOW() - t_epi0);
     }
   }
   tc_fence_before();
@@ -530,8 +599,14 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   g = (g / tiles_n) * tiles_n;                         // ... and a whole number of CTAs per column tile
   if (g < tiles_n) return AVC_E_BADCFG;
   dim3 grid(g);
-  static int l2pf = -1;       // AVC_NT_L2PF=1: TMA-prefetch the next row tile's A boxes into L2 (measured: no gain)
-  if (l2pf < 0) { const char* e = getenv("AVC_NT_L2PF"); l2pf = (e && atoi(e) == 1) ? 1 : 0; }
+  // TMA-prefetch of the next row tile's A boxes into L2.  The stall probe (profiles/r2_nt_probe_*.json) shows the MMA warp
+  // of the launches with a LIGHT epilogue waiting for operands ~50 % of its loop (two 32 KB stages do not cover a loaded
+  // DRAM latency); with the prefetch 40 % (EpiValue: loop 63.0 k -> 56.8 k cycles per CTA).  Launches whose epilogue is
+  // the bound and pulls its own operands into L2 (Epi::kNoATilePrefetch) got slower with it and keep it off.
+  // AVC_NT_L2PF=0 / 1 forces it off / on everywhere.
+  static int l2pf_env = -2;
+  if (l2pf_env == -2) { const char* e = getenv("AVC_NT_L2PF"); l2pf_env = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+  const int l2pf = l2pf_env >= 0 ? l2pf_env : (EpiNoAPf<Epi>::value ? 0 : 1);
   kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi, l2pf);
   AVC_LAUNCH_TRY();
   return 0;

@@ -41,6 +41,8 @@ int gemm_nt(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int
   return launch_gemm_nt(st, M, N, (int)round_up(K, 4), A, lda, w.pack + pk_off, ldb, epi);
 }
 // The colour net (it tolerates single-pass bf16) runs with cfg.color_products MMAs per product.
+// (Single-pass forward / dgrad with split weight gradients was measured too: same gradient error as all-single -- the
+// error enters through the rounded activations -- at half the gain; not kept.)
 inline bool color_single(const NeusPlan& pl) { return pl.cfg.engine == 1 && pl.cfg.color_products == 1; }
 template <typename Epi>
 int gemm_nt_color(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int N, int K, const float* A, int lda,
@@ -232,7 +234,7 @@ int value_chain(const NeusPlan& pl, const NeusWs& w, int64_t Pn, bool stash, boo
   }
   const LinDim& dl = pl.sdf[pl.L];
   OutSdf os{sdf_out, 1.0f / pl.cfg.sdf_scale, sdf_nz, sdf_pitch};
-  k_thin_nt<1, OutSdf><<<blocks_for(Pn, 8), 256, 0, st>>>(w.in[pl.L], dl.Kp, dl.Kp, pack + pl.pk_wsdf, dl.Kp,
+  k_thin_nt<1, OutSdf><<<blocks_for(Pn, 8 * kThinPPW), 256, 0, st>>>(w.in[pl.L], dl.Kp, dl.Kp, pack + pl.pk_wsdf, dl.Kp,
                                                            pack + pl.pk_bsdf, Pn, os);
   AVC_LAUNCH_TRY();
   if (want_feat) {
@@ -350,15 +352,19 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
     const LinDim& c0 = pl.col[0];
     // tcgen05 engine: the fp32 copy of a hidden colour activation is only read by the heads (layer Lc)
     const bool tc1 = pl.cfg.engine == 1;
-    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0xT, pl.Hc, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc, w.ch16[1]};
+    // ... and the split of the LAST hidden activation has no reader at all (the heads and their backward are thin fp32 ops)
+    const Split16 none16{nullptr, nullptr, 0};
+    EpiColor0 e0{pack + c0.pk_b, w.cin, pack + pl.pk_c0xT, pl.Hc, (tc1 && 1 < pl.Lc) ? nullptr : w.ch[1], pl.Hc,
+                 (tc1 && 1 == pl.Lc) ? none16 : w.ch16[1]};
     AVC_TRY(gemm_nt_color(pl, w, st, P, pl.Hc, pl.F, w.feat, pl.Fp, w.feat16, c0.pk_W, pl.Fp, e0));
     for (int l = 1; l < pl.Lc; ++l) {
       const LinDim& c = pl.col[l];
-      EpiRelu e{pack + c.pk_b, (tc1 && l + 1 < pl.Lc) ? nullptr : w.ch[l + 1], pl.Hc, w.ch16[l + 1]};
+      EpiRelu e{pack + c.pk_b, (tc1 && l + 1 < pl.Lc) ? nullptr : w.ch[l + 1], pl.Hc,
+                (tc1 && l + 1 == pl.Lc) ? none16 : w.ch16[l + 1]};
       AVC_TRY(gemm_nt_color(pl, w, st, P, pl.Hc, pl.Hc, w.ch[l], pl.Hc, w.ch16[l], c.pk_W, pl.Hc, e));
     }
     OutHeads oh{w.rgb6};
-    k_thin_nt<6, OutHeads><<<blocks_for(P, 8), 256, 0, st>>>(w.ch[pl.Lc], pl.Hc, pl.Hc, pack + pl.pk_W6, pl.Hc,
+    k_thin_nt<6, OutHeads><<<blocks_for(P, 8 * kThinPPW), 256, 0, st>>>(w.ch[pl.Lc], pl.Hc, pl.Hc, pack + pl.pk_W6, pl.Hc,
                                                              pack + pl.pk_b6, P, oh);
     AVC_LAUNCH_TRY();
   }
@@ -419,7 +425,9 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     // both heads read the same activation: one pass, rows 0..2 -> lin{Lc}, rows 3..5 -> extra_lin
     AVC_TRY(thin_tn<6>(st, w.y6bar, 8, 1.f, w.ch[pl.Lc], pl.Hc, pl.Hc, P, wbar + dh.off_v, pl.Hc, 1, wbar + dh.off_b, 3,
                        wbar + dx.off_v, wbar + dx.off_b));
-    k_heads_dgrad<<<blocks_for(P * pl.Hc / 4, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P, w.cbar[0],
+    // tcgen05 engine: the hidden linears consume cbar as a split operand; its fp32 copy is only read at layer 0
+    k_heads_dgrad<<<blocks_for(P * pl.Hc / 4, 256), 256, 0, st>>>(w.y6bar, pack + pl.pk_W6, pl.Hc, w.ch[pl.Lc], P,
+                                                              (pl.cfg.engine == 1 && pl.Lc > 1) ? nullptr : w.cbar[0],
                                                               w.cbar16[0]);
     AVC_LAUNCH_TRY();
   }
@@ -447,7 +455,7 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
       AVC_TRY(gemm_nt_color(pl, w, st, P, pl.F, pl.Hc, cb, pl.Hc, w.cbar16[cur], c.pk_WT, pl.Hc, es));
       // nbar += cbar . W0[:, 3:6]   (d/d points is discarded: pts is a leaf, models/fields.py:97)
       OutNbarAdd on{w.nbar};
-      k_thin_nt<6, OutNbarAdd><<<blocks_for(P, 8), 256, 0, st>>>(cb, pl.Hc, pl.Hc, pack + pl.pk_c0xT, pl.Hc, nullptr,
+      k_thin_nt<6, OutNbarAdd><<<blocks_for(P, 8 * kThinPPW), 256, 0, st>>>(cb, pl.Hc, pl.Hc, pack + pl.pk_c0xT, pl.Hc, nullptr,
                                                                  P, on);
       AVC_LAUNCH_TRY();
     }
@@ -571,6 +579,25 @@ avc_neus_cotangents offset_cot(const avc_neus_cotangents& c, int64_t r0, int S) 
 extern "C" {
 
 int avc_abi_version(void) { return AVC_ABI_VERSION; }
+
+// Stall probe of the tcgen05 NT tiles (diagnostic builds only: -DAVC_NT_PROBE=1).  out[16][8]: per functor slot the summed
+// cycles {TMA waits empty, TMA loop, MMA waits tempty, MMA waits full, MMA loop, epilogue warp waits tfull, epilogue loop,
+// CTAs}.  Returns AVC_E_BADCFG in a regular build.
+int avc_nt_probe_read(unsigned long long* host_out, int reset) {
+#ifdef AVC_NT_PROBE
+  if (!host_out) return AVC_E_NULL;
+  AVC_CUDA_TRY(cudaDeviceSynchronize());
+  AVC_CUDA_TRY(cudaMemcpyFromSymbol(host_out, tc::g_nt_probe, sizeof(unsigned long long) * 16 * 8));
+  if (reset) {
+    static unsigned long long zeros[16 * 8];
+    AVC_CUDA_TRY(cudaMemcpyToSymbol(tc::g_nt_probe, zeros, sizeof(zeros)));
+  }
+  return 0;
+#else
+  (void)host_out; (void)reset;
+  return AVC_E_BADCFG;
+#endif
+}
 const char* avc_build_arch(void) { return "sm_100a"; }
 
 int avc_neus_param_count(const avc_neus_cfg* cfg, int64_t* n_params) {

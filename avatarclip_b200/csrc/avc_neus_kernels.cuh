@@ -409,28 +409,42 @@ k_merge(const float* __restrict__ z, const float* __restrict__ sdf, int n, int p
 // Thin contractions (<= 8 outputs): one warp per row, lanes stride the reduction with float4 loads.
 //   v[i] = sum_k A[p,k] * W[i*ldw + k]  (+ b[i]);  Out functor consumes the NI values.
 // =============================================================================================
+// A warp takes kThinPPW consecutive rows: their loads are issued together (the pass is DRAM-latency bound: one row per
+// warp left 1 KB in flight per warp) and every W chunk is read once for the four rows.  Per row the arithmetic and its
+// order are those of the one-row form (lane-strided partial sums, then the xor butterfly).
+constexpr int kThinPPW = 4;
 template <int NI, typename Out>
 __global__ void __launch_bounds__(256)
 k_thin_nt(const float* __restrict__ A, int lda, int K, const float* __restrict__ W, int ldw,
           const float* __restrict__ b, int64_t P, Out out) {
-  int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (p >= P) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kThinPPW;
+  if (p0 >= P) return;
   const int lane = threadIdx.x & 31;
-  float acc[NI];
+  float acc[kThinPPW][NI];
 #pragma unroll
-  for (int i = 0; i < NI; ++i) acc[i] = 0.f;
-  const float* ar = A + (size_t)p * lda;
+  for (int j = 0; j < kThinPPW; ++j)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[j][i] = 0.f;
   for (int k = lane * 4; k < K; k += 128) {
-    float4 a = *reinterpret_cast<const float4*>(ar + k);
+    float4 a[kThinPPW];
+#pragma unroll
+    for (int j = 0; j < kThinPPW; ++j)       // rows past P re-read row p0 (valid memory); their result is dropped
+      a[j] = *reinterpret_cast<const float4*>(A + (size_t)(p0 + j < P ? p0 + j : p0) * lda + k);
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      float4 w = *reinterpret_cast<const float4*>(W + (size_t)i * ldw + k);
-      acc[i] = fmaf(a.x, w.x, fmaf(a.y, w.y, fmaf(a.z, w.z, fmaf(a.w, w.w, acc[i]))));
+      const float4 w = *reinterpret_cast<const float4*>(W + (size_t)i * ldw + k);
+#pragma unroll
+      for (int j = 0; j < kThinPPW; ++j)
+        acc[j][i] = fmaf(a[j].x, w.x, fmaf(a[j].y, w.y, fmaf(a[j].z, w.z, fmaf(a[j].w, w.w, acc[j][i]))));
     }
   }
 #pragma unroll
-  for (int i = 0; i < NI; ++i) acc[i] = warp_sum(acc[i]) + (b ? b[i] : 0.f);
-  if (lane == 0) out(p, acc);
+  for (int j = 0; j < kThinPPW; ++j)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc[j][i] = warp_sum(acc[j][i]) + (b ? b[i] : 0.f);
+#pragma unroll
+  for (int j = 0; j < kThinPPW; ++j)
+    if (lane == j && p0 + j < P) out(p0 + j, acc[j]);
 }
 
 struct OutSdf {     // sdf = z_L[0] / scale   (models/fields.py:88); point p = r * nz + j is stored at [r][j] (row pitch)
@@ -456,6 +470,8 @@ struct OutNbarAdd { // nbar[p][0..2] += d loss / d normal coming through colour 
   }
 };
 
+// (A variant with 16-byte loads, four row lanes per block meeting in shared memory and 64-row blocks was measured:
+// 45 us per launch against 27 us for this one -- twice the atomics and three resident blocks per SM; not kept.)
 // out[i*si + c*sc] += sum_p S[p*lds + i] * Hm[p*ldh + c]   (i < NI, c < NC);  optional s_scale on S;
 // optional bout[i] += sum_p S[p,i].  Rows i >= split go to (out2, bout2) with index i - split (two linears that share
 // the activation Hm, e.g. the two colour heads, in one pass over it).  Blocks split the rows; threads own columns.
@@ -657,7 +673,7 @@ __global__ void k_heads_dgrad(const float* __restrict__ y6bar, const float* __re
   }
   const float4 hv = *reinterpret_cast<const float4*>(h + i4);
   float v[4] = {hv.x > 0.f ? acc[0] : 0.f, hv.y > 0.f ? acc[1] : 0.f, hv.z > 0.f ? acc[2] : 0.f, hv.w > 0.f ? acc[3] : 0.f};
-  *reinterpret_cast<float4*>(cbar + i4) = make_float4(v[0], v[1], v[2], v[3]);
+  if (cbar) *reinterpret_cast<float4*>(cbar + i4) = make_float4(v[0], v[1], v[2], v[3]);
   split16_put4(c16, (size_t)p, c, v);
 }
 
@@ -689,6 +705,7 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int col, int N) 
 // ever use softplus' (softplus'' = beta * sp' * (1 - sp')), so the pre-activation itself is not kept.
 template <bool FAST>
 struct EpiValue {
+  static constexpr int kProbeId = 1;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   const float* bias; float* D1; int ldz; float* OUT; int ldo; float oscale; int N; Split16 o16;
   struct Aux { float4 b; };
   __device__ __forceinline__ Aux prefetch(int, int col) const { return {load4_guarded(bias, col, N)}; }
@@ -752,6 +769,7 @@ struct EpiValue {
 
 // out = acc + b (feature rows of the last SDF linear)
 struct EpiBias {
+  static constexpr int kProbeId = 9;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   const float* bias; float* OUT; int ldo; int N; Split16 o16;
   struct Aux { float4 b; };
   __device__ __forceinline__ Aux prefetch(int, int col) const { return {load4_guarded(bias, col, N)}; }
@@ -791,11 +809,15 @@ struct EpiBias {
 // columns >= Nprev (only when l is a skip layer): ge[col - Nprev] += u / sqrt(2).  Padding of qt_prev zeroed.
 // D1prev = the softplus' stash of layer l-1.  QTprev (fp32 copy) may be NULL: the tcgen05 engine keeps only the split.
 struct EpiChain {
+  static constexpr int kProbeId = 2;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   int Nprev, Npp; float s; const float* D1prev; float* QTprev; float* GE; int EP; int E; Split16 q16;
   struct Aux { float4 d; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
     const int c = clamp_group(col, Nprev);    // always a valid address; the value is only used when col + 3 < Nprev
     return {*reinterpret_cast<const float4*>(D1prev + (size_t)row * Npp + c)};
+  }
+  __device__ __forceinline__ void l2_prefetch(int m0, int n0, int bn, int M, int et, int nth) const {
+    tc::l2_prefetch_tile<4>(D1prev, Npp, Npp, m0, n0, bn, M, et, nth);
   }
   __device__ __forceinline__ void quad(int row, int col, const float4 (&a)[4], const Aux (&x)[4]) const {
     if (col + 3 >= Nprev) {
@@ -848,6 +870,8 @@ struct EpiChain {
 
 // gradient chain, layer 0: ge += acc  (width E)
 struct EpiGe {
+  static constexpr bool kNoATilePrefetch = true;     // measured slower with the A-tile L2 prefetch (avc_gemm_tc.cuh launcher)
+  static constexpr int kProbeId = 10;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   float* GE; int EP; int E;
   struct Aux { float4 g; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {     // EP % 4 == 0: the padding is addressable
@@ -866,6 +890,7 @@ struct EpiGe {
 // colour lin0: z = acc + b + cin6 . Wx[col] ; out = relu(z)        (models/fields.py:162-171)
 // WxT = the 6 point / normal columns of W0, transposed: [6][ldt] (one float4 per input for 4 output columns)
 struct EpiColor0 {
+  static constexpr int kProbeId = 7;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   const float* bias; const float* cin; const float* WxT; int ldt; float* OUT; int ldo; Split16 o16;
   struct Aux { float4 c0, c1; };
   __device__ __forceinline__ Aux prefetch(int row, int) const {
@@ -920,6 +945,7 @@ struct EpiColor0 {
 };
 
 struct EpiRelu {
+  static constexpr int kProbeId = 5;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   const float* bias; float* OUT; int ldo; Split16 o16;
   struct Aux { float4 b; };
   __device__ __forceinline__ Aux prefetch(int, int col) const {
@@ -959,12 +985,17 @@ struct EpiRelu {
 // colour dgrad: out = acc * [h > 0].  The mask comes from the fp32 activation Hm or, when Hm is NULL, from the hi
 // half of its split (h >= 0 after the ReLU, so h > 0 <=> the bf16 is not +-0).  OUT (fp32 copy) may be NULL.
 struct EpiDgradRelu {
+  static constexpr int kProbeId = 6;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   const float* Hm; const __nv_bfloat16* Hhi; float* OUT; int ld; Split16 o16;
   struct Aux { uint4 raw; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
     if (Hm) return {*reinterpret_cast<const uint4*>(Hm + (size_t)row * ld + col)};
     const uint2 h = *reinterpret_cast<const uint2*>(Hhi + (size_t)row * o16.ld + col);
     return {make_uint4(h.x, h.y, 0u, 0u)};
+  }
+  __device__ __forceinline__ void l2_prefetch(int m0, int n0, int bn, int M, int et, int nth) const {
+    if (Hm) tc::l2_prefetch_tile<4>(Hm, ld, ld, m0, n0, bn, M, et, nth);
+    else tc::l2_prefetch_tile<2>(Hhi, o16.ld, o16.ld, m0, n0, bn, M, et, nth);
   }
   __device__ __forceinline__ void quad(int row, int col, const float4 (&a)[4], const Aux (&x)[4]) const {
     float v[4][4];
@@ -1010,6 +1041,7 @@ struct EpiDgradRelu {
 };
 
 struct EpiStore {
+  static constexpr int kProbeId = 8;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   float* OUT; int ldo; int N; Split16 o16;
   __device__ __forceinline__ void operator()(int row, int col, float4 a) const {
     AVC_EPI_UNPACK;
@@ -1024,6 +1056,8 @@ struct EpiStore {
 //   ubar_next[row][col] = sp'(z_l) * qbar * s_next            (col < N_l)
 //   zbar_l[row][col]    = beta (1 - sp'(z_l)) * qt_l * qbar    (= softplus'' * ua_{l+1} * qbar), padding zeroed
 struct EpiChainBwd {
+  static constexpr bool kNoATilePrefetch = true;     // measured slower with the A-tile L2 prefetch (avc_gemm_tc.cuh launcher)
+  static constexpr int kProbeId = 3;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   int N, Np; const float* D1; const float* QT; Split16 qt16; float* ZBAR; float* UNEXT; int ldu; float s_next; Split16 u16;
   // qt_l comes from its fp32 copy QT or, when QT is NULL (tcgen05 engine), from the split hi + lo
   struct Aux { float4 d; uint4 q; };
@@ -1039,6 +1073,15 @@ struct EpiChainBwd {
       x.q = make_uint4(h.x, h.y, l.x, l.y);
     }
     return x;
+  }
+  __device__ __forceinline__ void l2_prefetch(int m0, int n0, int bn, int M, int et, int nth) const {
+    tc::l2_prefetch_tile<4>(D1, Np, Np, m0, n0, bn, M, et, nth);
+    if (QT) {
+      tc::l2_prefetch_tile<4>(QT, Np, Np, m0, n0, bn, M, et, nth);
+    } else {
+      tc::l2_prefetch_tile<2>(qt16.hi, qt16.ld, Np, m0, n0, bn, M, et, nth);
+      tc::l2_prefetch_tile<2>(qt16.lo, qt16.ld, Np, m0, n0, bn, M, et, nth);
+    }
   }
   __device__ __forceinline__ float qt_at(int row, int c) const {
     return QT ? QT[(size_t)row * Np + c] : split16_get(qt16, (size_t)row, c);
@@ -1126,12 +1169,18 @@ struct EpiChainBwd {
 // value backward dgrad into layer l-1: abar = (acc [+ sdfbar[row] * wsdf[col]]) * s ;
 //   zbar_prev[row][col] = sp'(z_prev) * abar + zbar_prev[row][col]   (col < Nprev);  D1prev = softplus'(z_prev) stash
 struct EpiDgrad {
+  static constexpr bool kNoATilePrefetch = true;     // measured slower with the A-tile L2 prefetch (avc_gemm_tc.cuh launcher)
+  static constexpr int kProbeId = 4;      // slot of the optional NT stall probe (avc_gemm_tc.cuh)
   int Nprev, Npp; float s; const float* D1prev; float* ZBARprev; const float* sdfbar; const float* wsdf;
   float sdf_inv_scale; Split16 z16; int store_f32;     // store_f32 = 0: only the split of the new zbar_prev is kept
   struct Aux { float4 d, zb; };
   __device__ __forceinline__ Aux prefetch(int row, int col) const {
     const size_t o = (size_t)row * Npp + clamp_group(col, Npp);
     return {*reinterpret_cast<const float4*>(D1prev + o), *reinterpret_cast<const float4*>(ZBARprev + o)};
+  }
+  __device__ __forceinline__ void l2_prefetch(int m0, int n0, int bn, int M, int et, int nth) const {
+    tc::l2_prefetch_tile<4>(D1prev, Npp, Npp, m0, n0, bn, M, et, nth);
+    tc::l2_prefetch_tile<4>(ZBARprev, Npp, Npp, m0, n0, bn, M, et, nth);
   }
   __device__ __forceinline__ void quad(int row, int col, const float4 (&a)[4], const Aux (&x)[4]) const {
     if (col + 3 >= Npp) {

@@ -69,7 +69,8 @@ typedef struct avc_neus_cfg {
    * 1 = tcgen05 tensor-core tiles with two-term split operands (3 MMAs per product) */
   int32_t engine;
   /* tcgen05 engine only: MMAs per product in the COLOUR net (forward, dgrad, wgrad).  3 (or 0) = the same two-term split
-   * as the SDF trunk; 1 = single-pass bf16 on the hi halves (the colour net tolerates it). */
+   * as the SDF trunk; 1 = single-pass bf16 on the hi halves (the colour net tolerates it in the
+   * rendered RGB; the flat parameter gradient moves from ~4e-5 to 3e-4 .. 1e-3 rel-L2). */
   int32_t color_products;
 } avc_neus_cfg;
 
@@ -350,6 +351,11 @@ int avc_uniform_fill(uint32_t seed, int32_t n, float lo, float hi, float* out, a
  * counters ([0] MMA warp waiting for its A operand, [1] for weight slabs, [2] MMA warp total, [3] tile-layers,
  * [4] epilogue waiting for the accumulator, [5] epilogue work); this call synchronises the device and copies them. */
 int avc_chain_debug_read(long long* out8);
+/* Stall probe of the tcgen05 NT tiles: only in a diagnostic build (-DAVC_NT_PROBE=1, tools/nt_probe.py); a regular
+ * build returns AVC_E_BADCFG.  host_out[16][8]: per epilogue functor the summed cycles {TMA warp waiting for a free
+ * stage, TMA loop, MMA warp waiting for a drained accumulator, MMA warp waiting for operands, MMA loop, one epilogue
+ * warp waiting for the accumulator, its loop, CTAs}; reset != 0 clears the counters. */
+int avc_nt_probe_read(unsigned long long* host_out, int reset);
 
 int avc_march_count(const float* field, int32_t nx, int32_t ny, int32_t nz, float iso, int32_t* counts,
                     avc_stream_t stream);
