@@ -15,6 +15,7 @@
 #include <cstring>
 
 #include "avc_common.cuh"
+#include "avc_gemm_tc.cuh"
 
 using namespace avc;
 
@@ -202,10 +203,16 @@ k_gemm16(const __half* __restrict__ A, int lda, const __half* __restrict__ Wt, i
   d_gemm16<GST>(HwCtx(g_smem_hw, early_trigger), A, lda, Wt, ldw, M, N, K, k_per_split, epi);
 }
 
+int clip_tc_enabled();
+template <typename Epi>
+int gemm16_tc(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw, int M, int N, int K, int ksplit,
+              const Epi& epi);
+
 template <typename Epi>
 int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw, int M, int N, int K, int ksplit,
            const Epi& epi) {
   if (N % GBN || K % GBK) return AVC_E_BADCFG;
+  if (M <= 128 && clip_tc_enabled()) return gemm16_tc(st, A, lda, Wt, ldw, M, N, K, ksplit, epi);
   int kper = (int)round_up(ceil_div(K, ksplit), GBK);
   ksplit = ceil_div(K, kper);
   dim3 grid(N / GBN, ceil_div(M, GBM), ksplit);
@@ -217,6 +224,148 @@ int gemm16(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw,
   static int early = -1;      // AVC_CLIP_EARLY_TRIGGER=1: release the dependent kernel at the top (tuning knob)
   if (early < 0) { const char* e = getenv("AVC_CLIP_EARLY_TRIGGER"); early = (e && atoi(e) == 1) ? 1 : 0; }
   AVC_CUDA_TRY(launch_pdl(k_gemm16<Epi>, dim3(grid), dim3(128), G_SMEM, st, A, lda, Wt, ldw, M, N, K, kper, epi, early));
+  AVC_LAUNCH_TRY();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same GEMM on tcgen05 (AVC_CLIP_TC, the chained structure's default when M <= 128): all token rows of the batch
+// (M = 100 at B = 2) are ONE 128-row MMA tile, so a CTA owns a 128 x 32 output tile for its K range.
+//   warp 0   TMA producer: W tiles (constants) go out BEFORE griddepcontrol.wait, the A tiles right after it;
+//            8-stage ring of (A 16 KB + W 4 KB), K-major SWIZZLE_128B;
+//   warp 1   TMEM (32 columns) + tcgen05.mma.kind::f16 (fp16 operands, fp32 accumulate), M = 128, N = 32;
+//   warps 2-5  epilogue: tcgen05.ld 32x32b.x32 (thread <-> row), transposed through shared memory so that lanes <->
+//            column pairs (two rows x 128 B per warp instruction), same functors as the mma.sync kernel.
+// grid (N / 32, ksplit); rows >= M of the A box are zero-filled by TMA and never stored.
+// ------------------------------------------------------------------------------------------------
+constexpr int TBN = 32, TBK = 64, TST = 8;
+constexpr int T_A_BYTES = 128 * TBK * 2, T_W_BYTES = TBN * TBK * 2, T_STAGE = T_A_BYTES + T_W_BYTES;
+constexpr int T_EPI_BYTES = 4 * 32 * 33 * 4;
+constexpr int T_SMEM = 1024 + TST * T_STAGE + 256 + T_EPI_BYTES;
+// instruction descriptor, kind::f16 with F16 operands (format 0), F32 accumulator, both operands K-major
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+template <typename Epi>
+__global__ void __launch_bounds__(192, 1)
+k_gemm16_tc(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int M, int N, int K,
+            int k_per_split, Epi epi) {
+  using namespace avc::tc;
+  extern __shared__ uint8_t t_smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)t_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TST * T_STAGE);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TST + 1);
+  float* stage_t = (float*)(smem + TST * T_STAGE + 256);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * TST, tfull = empty0 + 8 * TST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TBN, ks = blockIdx.y;
+  const int kb0 = ks * k_per_split, ke = min(K, kb0 + k_per_split);
+  const int nk = (ke - kb0 + TBK - 1) / TBK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW);
+    for (int s = 0; s < TST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 32);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int npre = nk < TST ? nk : TST;
+      for (int s = 0; s < npre; ++s) {      // weights do not depend on the predecessor kernel
+        mbar_expect_tx(full0 + 8 * s, T_STAGE);
+        tma_load_2d(smem_base + s * T_STAGE + T_A_BYTES, &mapW, kb0 + s * TBK, n0, full0 + 8 * s);
+      }
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int s = 0; s < npre; ++s) tma_load_2d(smem_base + s * T_STAGE, &mapA, kb0 + s * TBK, 0, full0 + 8 * s);
+      for (int kb = npre; kb < nk; ++kb) {
+        const int s = kb % TST;
+        mbar_wait(empty0 + 8 * s, ((kb / TST) & 1) ^ 1);
+        mbar_expect_tx(full0 + 8 * s, T_STAGE);
+        tma_load_2d(smem_base + s * T_STAGE + T_A_BYTES, &mapW, kb0 + kb * TBK, n0, full0 + 8 * s);
+        tma_load_2d(smem_base + s * T_STAGE, &mapA, kb0 + kb * TBK, 0, full0 + 8 * s);
+      }
+      // the dependent kernel is released after the main loop, like in the mma.sync kernel (the first
+      // launch_dependents of a CTA is the one that counts: no early call from the producer)
+      mbar_wait(tfull, 0);
+    }
+    __syncwarp();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else if (warp == 1) {
+    for (int kb = 0; kb < nk; ++kb) {
+      const int s = kb % TST;
+      mbar_wait(full0 + 8 * s, (kb / TST) & 1);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t da = make_smem_desc(smem_base + s * T_STAGE, 0, 1024);
+        const uint64_t db = make_smem_desc(smem_base + s * T_STAGE + T_A_BYTES, 0, 1024);
+#pragma unroll
+        for (int k4 = 0; k4 < TBK / 16; ++k4) umma_f16(tmem_base, da + 2 * k4, db + 2 * k4, kIdescF16, (kb | k4) ? 1u : 0u);
+        umma_commit(empty0 + 8 * s);
+        if (kb == nk - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+    }
+    mbar_wait(tfull, 0);
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  } else {
+    const int q = warp & 3;                       // TMEM lane quarter of this warp (warps 2..5 -> 2, 3, 0, 1)
+    const int rsub = lane >> 4, cp = lane & 15;   // after the transpose: lanes 0-15 one row, 16-31 the next; 2 columns each
+    const int col = n0 + 2 * cp;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    float2 pre[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int row = q * 32 + 2 * i + rsub;
+      pre[i] = row < M ? epi.prefetch(row, col, ks) : make_float2(0.f, 0.f);
+    }
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16), r);
+    float* st = stage_t + (warp - 2) * (32 * 33);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int rl = 2 * i + rsub, row = q * 32 + rl;
+      if (row < M) epi(row, col, st[rl * 33 + 2 * cp], st[rl * 33 + 2 * cp + 1], ks, pre[i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 32);
+  }
+}
+
+int clip_tc_enabled() {      // AVC_CLIP_TC=0: the mma.sync GEMM for every launch (A-B knob; read on every call)
+  const char* e = getenv("AVC_CLIP_TC");
+  return (e && atoi(e) == 0) ? 0 : 1;
+}
+
+template <typename Epi>
+int gemm16_tc(cudaStream_t st, const __half* A, int lda, const __half* Wt, int ldw, int M, int N, int K, int ksplit,
+              const Epi& epi) {
+  int kper = (int)round_up(ceil_div(K, ksplit), TBK);
+  ksplit = ceil_div(K, kper);
+  CUtensorMap mA, mW;     // fp16 data through bf16-typed maps: TMA only moves bytes (and zero-fills out-of-range rows)
+  AVC_TRY(tc::make_map_bf16_cached(&mA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, TBK, 128));
+  AVC_TRY(tc::make_map_bf16_cached(&mW, Wt, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, TBK, TBN));
+  static bool attr_set = false;      // per epilogue instantiation
+  if (!attr_set) {
+    AVC_CUDA_TRY(cudaFuncSetAttribute(k_gemm16_tc<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM));
+    attr_set = true;
+  }
+  AVC_CUDA_TRY(launch_pdl(k_gemm16_tc<Epi>, dim3(N / TBN, ksplit), dim3(192), T_SMEM, st, mA, mW, M, N, K, kper, epi));
   AVC_LAUNCH_TRY();
   return 0;
 }

@@ -18,14 +18,16 @@ def _tower(seed=0):
     return sd, ClipImageTower(sd, device="cuda")
 
 
-@pytest.fixture(params=["chained", "persistent", "fused_attention"])
+@pytest.fixture(params=["chained", "chained_mma_sync", "persistent", "fused_attention"])
 def clip_mode(request):
-    """The launch structures of the tower: the chain of stand-alone kernels (default), one persistent cooperative kernel
-    per pass (AVC_CLIP_MEGA=1) and the chain with the attention half of every block as one kernel per (image, head)
-    (AVC_CLIP_FUSED_ATTN=1); same arithmetic, same results up to fp32 atomic order."""
-    old = {k: os.environ.get(k) for k in ("AVC_CLIP_MEGA", "AVC_CLIP_FUSED_ATTN")}
+    """The launch structures of the tower: the chain of stand-alone kernels (default; its GEMMs on tcgen05, or on
+    mma.sync with AVC_CLIP_TC=0), one persistent cooperative kernel per pass (AVC_CLIP_MEGA=1) and the chain with the
+    attention half of every block as one kernel per (image, head) (AVC_CLIP_FUSED_ATTN=1); same arithmetic, same results
+    up to fp32 atomic order."""
+    old = {k: os.environ.get(k) for k in ("AVC_CLIP_MEGA", "AVC_CLIP_FUSED_ATTN", "AVC_CLIP_TC")}
     os.environ["AVC_CLIP_MEGA"] = "1" if request.param == "persistent" else "0"
     os.environ["AVC_CLIP_FUSED_ATTN"] = "1" if request.param == "fused_attention" else "0"
+    os.environ["AVC_CLIP_TC"] = "0" if request.param == "chained_mma_sync" else "1"
     yield request.param
     for k, v in old.items():
         if v is None:
