@@ -111,6 +111,8 @@ k_sdf_chain(const __grid_constant__ Maps maps, const __grid_constant__ DevArgs a
     // ------------------------------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int it = 0, lt = 0;
+      pdl_wait();            // the encoded points are the predecessor kernel's output (launched with launch_pdl: this
+      pdl_trigger();         // CTA's set-up ran while that kernel was still draining)
       for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++lt) {
         // the A buffer is free for the next tile's input once the last layer's MMAs of the previous tile completed
         if (lt > 0) mbar_wait(accfull, (uint32_t)((lt * L - 1) & 1));
@@ -175,6 +177,7 @@ k_sdf_chain(const __grid_constant__ Maps maps, const __grid_constant__ DevArgs a
     if (prof) { a.dbg[0] = t_wa; a.dbg[1] = t_ww; a.dbg[2] = clock64() - t_all0; a.dbg[3] = (long long)lt * L; }
   } else {
     // ------------------------------------------------------------------------------------------ epilogue
+    pdl_wait();                             // skip-concat columns in, sdf out: predecessor kernels' buffers
     const int q = warp & 3;                 // TMEM lane quarter
     const int cw = (warp - 2) >> 2;         // column group: columns [64 cw, 64 cw + 64) = k-block cw of the next A
     const int row = q * 32 + lane;          // row of the tile this thread owns
@@ -375,7 +378,7 @@ int launch(const Args& a, cudaStream_t st) {
     d.dbg = dbg_buf;
     g_dbg = dbg_buf;
   }
-  k_sdf_chain<<<grid, kThreads, kSmemBytes, st>>>(m, d);
+  AVC_CUDA_TRY(launch_pdl(k_sdf_chain, dim3(grid), dim3(kThreads), (size_t)kSmemBytes, st, m, d));
   AVC_LAUNCH_TRY();
   return 0;
 }

@@ -71,6 +71,26 @@ struct EpiProbeId { static constexpr int value = 0; };
 template <typename E>
 struct EpiProbeId<E, std::void_t<decltype(E::kProbeId)>> { static constexpr int value = E::kProbeId; };
 
+// Programmatic dependent launch (the tcgen05 kernels of a step run back to back in one stream / graph): a kernel launched
+// with launch_pdl may start while its predecessor is still running -- as SMs free up its CTAs do their set-up (barriers,
+// TMEM, tensor-map prefetch) and load what does NOT depend on the predecessor (the packed weights) -- and calls
+// pdl_wait() before it touches anything the predecessor may have written.  pdl_trigger() lets the NEXT kernel do the same;
+// it is only issued after this kernel's own pdl_wait(), so everything older than the predecessor is complete by induction.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static int on = -1;      // AVC_TC_PDL=0: plain stream-ordered launches (A-B knob)
+  if (on < 0) { const char* e = getenv("AVC_TC_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -353,7 +373,7 @@ template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                  int M, int N, int K, Epi epi, int l2pf) {
+                  int M, int N, int K, Epi epi, int l2pf, int b_const) {
   using Cfg = TcCfg<BN, NPROD, EW, RESB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B wants 1024-B tiles
@@ -395,6 +415,19 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      // b_const: B holds constants of the step (the packed weights, written many kernels ago): its resident panel is
+      // loaded while the predecessor kernel may still be running
+      if (!b_const) pdl_wait();
+      if (RESB && m_first < tiles_m) {
+        for (int kb = 0; kb < nk; ++kb) {
+          const uint32_t dst = bres_base + kb * (Cfg::NOP * Cfg::B_BYTES);
+          mbar_expect_tx(bfull + 8 * kb, (uint32_t)(Cfg::NOP * Cfg::B_BYTES));
+          tma_load_2d(dst, &mapBhi, kb * kBK, n0, bfull + 8 * kb);
+          if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull + 8 * kb);
+        }
+      }
+      if (b_const) pdl_wait();
+      pdl_trigger();
       // l2pf (see the launcher): pull the A boxes of the NEXT row tile into L2 while this one is loaded, so that the
       // ring's loads see L2 latency.
       if (l2pf && m_first < tiles_m)
@@ -412,12 +445,6 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
           if (pf) {
             tma_prefetch_2d(&mapAhi, kb * kBK, m0 + m_stride * kBM);
             if (NPROD == 3) tma_prefetch_2d(&mapAlo, kb * kBK, m0 + m_stride * kBM);
-          }
-          if (RESB && mt == m_first) {     // first row tile: k-block kb of the resident B panel goes out just before A's
-            const uint32_t dst = bres_base + kb * (Cfg::NOP * Cfg::B_BYTES);
-            mbar_expect_tx(bfull + 8 * kb, (uint32_t)(Cfg::NOP * Cfg::B_BYTES));
-            tma_load_2d(dst, &mapBhi, kb * kBK, n0, bfull + 8 * kb);
-            if (NPROD == 3) tma_load_2d(dst + Cfg::B_BYTES, &mapBlo, kb * kBK, n0, bfull + 8 * kb);
           }
           const int s = it % Cfg::STAGES;
           AVC_PROBE_WAIT(w_empty, empty0 + 8 * s, ((it / Cfg::STAGES) & 1) ^ 1);
@@ -500,6 +527,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     const uint32_t st_row = stage + (uint32_t)lane * 64u, st_sw = (uint32_t)((lane >> 1) & 3);
     const uint32_t ld_addr = stage + (uint32_t)ri * 64u + (uint32_t)(((lane & 3) ^ ((ri >> 1) & 3)) * 16);
     const int col_last = (N - 1) & ~3, row_last = M - 1;
+    pdl_wait();      // the functor's operands and outputs belong to predecessor kernels
     Aux aux[NPF][4];
     auto issue = [&](Aux (&dst)[4], int mt, int sb) {
       const int row = min(mt, tiles_m - 1) * kBM + q * 32 + ri;
@@ -570,7 +598,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
 template <int BN, int NPROD, int EW, int PFB, bool RESB, typename Epi>
 static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
-                                       const Epi& epi) {
+                                       const Epi& epi, bool b_const) {
   using Cfg = TcCfg<BN, NPROD, EW, RESB>;
   CUtensorMap mAh, mAl, mBh, mBl;
   AVC_TRY(make_map_bf16_cached(&mAh, A.hi, (uint64_t)M, (uint64_t)K, (uint64_t)A.ld, kBK, kBM));
@@ -607,7 +635,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
   static int l2pf_env = -2;
   if (l2pf_env == -2) { const char* e = getenv("AVC_NT_L2PF"); l2pf_env = e ? (atoi(e) != 0 ? 1 : 0) : -1; }
   const int l2pf = l2pf_env >= 0 ? l2pf_env : (EpiNoAPf<Epi>::value ? 0 : 1);
-  kern<<<grid, 64 + 32 * EW, Cfg::SMEM_BYTES, st>>>(mAh, mAl, mBh, mBl, (int)M, N, K, epi, l2pf);
+  AVC_CUDA_TRY(launch_pdl(kern, dim3(grid), dim3(64 + 32 * EW), (size_t)Cfg::SMEM_BYTES, st, mAh, mAl, mBh, mBl, (int)M, N, K, epi, l2pf, b_const ? 1 : 0));
   AVC_LAUNCH_TRY();
   return 0;
 }
@@ -616,7 +644,7 @@ static inline int launch_gemm_tc_nt_bn(cudaStream_t st, int64_t M, int N, int K,
 // 512 tiles = 3.46 waves over 148 persistent CTAs (13 % tail); 1024 tiles = 6.9 waves (1.4 % tail).
 template <int NPROD, typename Epi>
 static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, const SplitPtr& A, const SplitPtr& B,
-                                    const Epi& epi) {
+                                    const Epi& epi, bool b_const = false) {
   if (M <= 0 || N <= 0) return 0;
   // 16 epilogue warps, one (32-byte operands) or two (16-byte operands) sub-blocks of prefetch.  Measured per step
   // (73 launches, B200): 16 warps / 32 regs 3.01 ms, 16 / 16 3.02 ms, 8 warps / 64 regs 3.32 ms, 8 / 32 3.34 ms.
@@ -624,11 +652,11 @@ static inline int launch_gemm_tc_nt(cudaStream_t st, int64_t M, int N, int K, co
   static int resb = -1;       // AVC_NT_RESB=0 forces the streaming variant (tuning knob)
   if (resb < 0) { const char* e = getenv("AVC_NT_RESB"); resb = (e && atoi(e) == 0) ? 0 : 1; }
   if (resb && K <= kResK * kBK) {
-    if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi);
-    return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi);
+    if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi, b_const);
+    return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, true, Epi>(st, M, N, K, A, B, epi, b_const);
   }
-  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi);
-  return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi);
+  if (N <= 64) return launch_gemm_tc_nt_bn<64, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi, b_const);
+  return launch_gemm_tc_nt_bn<128, NPROD, 16, 32, false, Epi>(st, M, N, K, A, B, epi, b_const);
 }
 
 // ------------------------------------------------------------------------------------------------ TN kernel
@@ -694,6 +722,8 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();         // both operands are activations of predecessor kernels
+      pdl_trigger();
       for (int kb = 0; kb < nk; ++kb) {
         const int s = kb % Cfg::STAGES;
         mbar_wait(empty0 + 8 * s, ((kb / Cfg::STAGES) & 1) ^ 1);
@@ -751,6 +781,7 @@ gemm_tc_tn_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    pdl_wait();           // C is accumulated with atomics: not before the predecessors have drained
     mbar_wait(tfull, 0);
     tc_fence_after();
     const int row0 = i0 + q * 32;
@@ -804,7 +835,7 @@ static inline int launch_gemm_tc_tn(cudaStream_t st, int64_t P, int N1, int N2, 
     int rows = (int)round_up(ceil_div(P, splits), kBK);
     splits = ceil_div(P, rows);
     dim3 grid(t1, t2, splits);
-    kern<<<grid, kTcThreads, smem, st>>>(mAh, mAl, mBh, mBl, (int)P, N1, N2, rows, C, ldc, colsum);
+    AVC_CUDA_TRY(launch_pdl(kern, grid, dim3(kTcThreads), (size_t)smem, st, mAh, mAl, mBh, mBl, (int)P, N1, N2, rows, C, ldc, colsum));
     AVC_LAUNCH_TRY();
     return 0;
   };

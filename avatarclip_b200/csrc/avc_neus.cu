@@ -36,7 +36,7 @@ int gemm_nt(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t M, int
             const Split16& A16, int64_t pk_off, int ldb, const Epi& epi) {
   if (pl.cfg.engine == 1) {
     tc::SplitPtr a{A16.hi, A16.lo, lda}, b{w.pk_hi + pk_off, w.pk_lo + pk_off, ldb};
-    return tc::launch_gemm_tc_nt<NP, Epi>(st, M, N, K, a, b, epi);
+    return tc::launch_gemm_tc_nt<NP, Epi>(st, M, N, K, a, b, epi, /*b_const: the packed weights*/ true);
   }
   return launch_gemm_nt(st, M, N, (int)round_up(K, 4), A, lda, w.pack + pk_off, ldb, epi);
 }
