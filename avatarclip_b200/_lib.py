@@ -34,7 +34,7 @@ class NeusCfg(C.Structure):
         ("sdf_scale", C.c_float),
         ("col_d_feature", C.c_int32), ("col_d_hidden", C.c_int32), ("col_n_layers", C.c_int32),
         ("n_samples", C.c_int32), ("n_importance", C.c_int32), ("up_sample_steps", C.c_int32),
-        ("engine", C.c_int32), ("color_products", C.c_int32),
+        ("engine", C.c_int32), ("color_products", C.c_int32), ("wgrad_products", C.c_int32),
     ]
 
 

@@ -61,7 +61,7 @@ inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t
   (void)w;
   if (pl.cfg.engine == 1) {
     tc::SplitPtr a{A16.hi, A16.lo, lda}, b{B16.hi, B16.lo, ldb};
-    if (single) return tc::launch_gemm_tc_tn<1>(st, P, N1, N2, a, b, C, ldc, bias_out);
+    if (single || pl.cfg.wgrad_products == 1) return tc::launch_gemm_tc_tn<1>(st, P, N1, N2, a, b, C, ldc, bias_out);
     return tc::launch_gemm_tc_tn<3>(st, P, N1, N2, a, b, C, ldc, bias_out);
   }
   AVC_TRY(launch_gemm_tn(st, P, N1, N2, A, lda, B, ldb, C, ldc));

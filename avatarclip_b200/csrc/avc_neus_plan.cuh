@@ -56,6 +56,7 @@ static inline int build_plan(const avc_neus_cfg* c, NeusPlan* p) {
   if (c->n_importance % c->up_sample_steps) return AVC_E_BADCFG;
   if (c->engine != 0 && c->engine != 1) return AVC_E_BADCFG;
   if (c->color_products != 0 && c->color_products != 1 && c->color_products != 3) return AVC_E_BADCFG;
+  if (c->wgrad_products != 0 && c->wgrad_products != 1 && c->wgrad_products != 3) return AVC_E_BADCFG;
   if (c->engine == 1 && (c->sdf_d_hidden % 8 || c->col_d_hidden % 8 || (c->sdf_d_out - 1) % 8)) return AVC_E_BADCFG;
   p->E = 3 * (1 + 2 * c->sdf_multires);
   p->EP = (int)round_up(p->E, 8);   // multiples of 8: bf16 rows stay 16-byte aligned for TMA

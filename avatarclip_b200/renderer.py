@@ -176,7 +176,7 @@ class NeuSRenderer:
 
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
                  up_sample_steps, perturb, extra_color=False, engine: int = 0, max_rays_per_chunk: int = 4096,
-                 color_products: Optional[int] = None):
+                 color_products: Optional[int] = None, wgrad_products: Optional[int] = None):
         if n_outside != 0:
             raise NotImplementedError("n_outside > 0 (NeRF background) is not part of the AvatarCLIP hot path")
         if not extra_color:
@@ -197,7 +197,9 @@ class NeuSRenderer:
             n_samples=self.n_samples, n_importance=self.n_importance, up_sample_steps=self.up_sample_steps,
             engine=int(engine),
             # tcgen05 engine: MMAs per product in the colour net; None -> AVC_COLOR_PRODUCTS (default 3 = split operands)
-            color_products=int(os.environ.get("AVC_COLOR_PRODUCTS", "3") if color_products is None else color_products))
+            color_products=int(os.environ.get("AVC_COLOR_PRODUCTS", "3") if color_products is None else color_products),
+            # MMAs per product in the weight-gradient tiles; None -> AVC_WGRAD_PRODUCTS
+            wgrad_products=int(os.environ.get("AVC_WGRAD_PRODUCTS", "3") if wgrad_products is None else wgrad_products))
         self._flat: Optional[FlatParams] = None
         self._hook = torch.zeros((), requires_grad=True)
         self._ws_cache: Dict[int, torch.Tensor] = {}

@@ -72,6 +72,9 @@ typedef struct avc_neus_cfg {
    * as the SDF trunk; 1 = single-pass bf16 on the hi halves (the colour net tolerates it in the
    * rendered RGB; the flat parameter gradient moves from ~4e-5 to 3e-4 .. 1e-3 rel-L2). */
   int32_t color_products;
+  /* tcgen05 engine only: MMAs per product in the WEIGHT-GRADIENT tiles (dW += zbar^T in, qt^T ubar, ... : sums over all
+   * sample points of a chunk).  3 (or 0) = two-term split operands; 1 = single-pass bf16 on the hi halves. */
+  int32_t wgrad_products;
 } avc_neus_cfg;
 
 /* Flat parameter vector layout (fp32), identical for the gradient vector:
