@@ -85,8 +85,8 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  static int on = -1;      // AVC_TC_PDL=0: plain stream-ordered launches (A-B knob)
-  if (on < 0) { const char* e = getenv("AVC_TC_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  const char* e = getenv("AVC_TC_PDL");      // AVC_TC_PDL=0: plain stream-ordered launches (A-B knob; read on every call:
+  const int on = (e && atoi(e) == 0) ? 0 : 1;      // bench.py takes its per-kernel durations with plain launches)
   cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }

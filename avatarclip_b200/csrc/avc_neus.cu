@@ -381,6 +381,9 @@ int fine_forward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, bool wr
   return 0;
 }
 
+// (Measured and removed, r2: setting 32 / 48 / 64 MB of L2 aside for persisting accesses and making the operand pair a
+// backward kernel writes -- zbar_{l-1}, ubar_{l+1}: read again by the next TN and the next NT -- the stream's access-policy
+// window cost 1.5 / 4 / 14 % of the step: the carve-out takes L2 from the A-tile and epilogue-operand prefetches.)
 // -------------------------------------------------------------------------------- backward
 template <int NI>
 int thin_tn(cudaStream_t st, const float* S, int lds, float s_scale, const float* Hm, int ldh, int NC, int64_t P,

@@ -259,10 +259,19 @@ def run_native(args):
     barrier()
     # one extra step on EVERY rank (it contains the all-reduce); only rank 0 records it with CUPTI
     launches_per_step, total_launches, table = (None, None, {})
+    # The profiled step runs with PLAIN launches of the tcgen05 NeuS kernels (AVC_TC_PDL=0, read per launch): under
+    # programmatic dependent launch a kernel's CUPTI record starts when its first CTA becomes resident and includes the
+    # wait for its predecessor, so durations overlap; the roofline wants the kernel's own duration.
+    old_pdl = os.environ.get("AVC_TC_PDL")
+    os.environ["AVC_TC_PDL"] = "0"
     if rank == 0:
         launches_per_step, total_launches, table = count_my_launches(lambda: tr.step(resident[0]))
     else:
         tr.step(resident[0])
+    if old_pdl is None:
+        os.environ.pop("AVC_TC_PDL", None)
+    else:
+        os.environ["AVC_TC_PDL"] = old_pdl
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -399,7 +408,7 @@ def run_native(args):
                          "scope": "algorithmic FLOP executed by the dominant kernel's launches in one step (SURVEY 8d "
                                   "split: NT tiles 4.875 F_sdf + 2 F_col per point -- 4.0 F_sdf when the fused value-chain "
                                   "kernel runs the 0.875 F_sdf of the placement passes --, TN tiles 2 F_sdf + F_col) / sum of "
-                                  "their device durations (CUPTI, live); peak = " + peak_src + "; the kernel runs 3 "
+                                  "their device durations (CUPTI, live, taken on a step with plain launches: under programmatic dependent launch a record includes the wait for the predecessor); peak = " + peak_src + "; the kernel runs 3 "
                                   "bf16 MMAs per product (two-term split), so its ceiling is peak/3",
                          "hbm_view": (lambda b, us: {"designed_bytes_per_step": b, "kernel_us_per_step": us,
                                                      "achieved_GBps": b / (us * 1e-6) / 1e9 if us else None,
