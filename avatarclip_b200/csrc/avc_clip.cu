@@ -7,8 +7,10 @@
 //
 // Shapes: M = B*T token rows (T = 50), width 768.  Every GEMM here has M <= 128*k rows and streams its
 // fp16 weight matrix exactly once: by bytes they are weight-bandwidth bound, in practice latency bound (~200 dependent
-// kernels per step), so the tiles are small (64 x 32 per CTA), deep (6-stage cp.async), split over K where N alone
-// cannot fill the SMs, and every kernel issues all its global loads in one batch.
+// kernels per step), so the tiles are small and split over K where N alone cannot fill the SMs, and every kernel issues
+// all its global loads in one batch.  Two GEMM kernels: k_gemm16_tc (default when M <= 128: TMA-fed
+// tcgen05 tiles of 128 x 32, the constant weight tiles issued before the programmatic-dependency wait) and k_gemm16
+// (mma.sync m16n8k16, 64 x 32 tiles, 6-stage cp.async; larger batches, the persistent variant, AVC_CLIP_TC=0).
 #include <cuda_fp16.h>
 
 #include <cstdlib>

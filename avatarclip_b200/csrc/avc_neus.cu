@@ -53,6 +53,9 @@ int gemm_nt_color(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t 
 
 int colsum(cudaStream_t st, const float* X, int ld, int NC, int64_t P, float scale, float* out);
 
+// (Measured and removed, r2: recording the ~21 weight-gradient GEMMs of a backward and running them as ONE persistent grouped
+// launch at the end -- a stand-alone launch has 9.5 us of fixed cost, profiles/r2_tn_scaling_probe.json -- gave 4.734 vs
+// 4.732 ms per step: under programmatic dependent launch the interleaved launches already hide that cost.)
 // C[N1][ldc] += A^T B ; optionally bias_out[i] += sum_p A[p,i] (the bias gradient of the same linear): fused into the
 // tcgen05 kernel as one extra 16-wide MMA against a tile of ones, a separate column-sum kernel for the fp32 engine.
 inline int gemm_tn(const NeusPlan& pl, const NeusWs& w, cudaStream_t st, int64_t P, int N1, int N2, const float* A,
@@ -491,11 +494,13 @@ int fine_backward(const NeusPlan& pl, const NeusWs& w, const ChunkIO& io, const 
     // tcgen05 engine: the fp32 copy of ubar_{l+1} is only read by the column sum at the last linear
     e.UNEXT = (pl.cfg.engine == 1 && l + 1 < pl.L) ? nullptr : w.ubar[ucur ^ 1];
     e.ldu = dn.Kp; e.s_next = dn.skip ? kSqrtHalf : 1.f;
-    e.u16 = with_ld(w.ubar16[ucur ^ 1], dn.Kp);
+    // the pair of ubar_L has no reader (the last linear only needs the column sum of the fp32 copy)
+    const Split16 unext16 = (pl.cfg.engine == 1 && l + 1 == pl.L) ? Split16{nullptr, nullptr, 0} : with_ld(w.ubar16[ucur ^ 1], dn.Kp);
+    e.u16 = unext16;
     AVC_TRY(gemm_nt(pl, w, st, P, d.N, d.K, ub, d.Kp, ub16, d.pk_W, d.Kp, e));
     if (dn.skip) {
       k_fill_gebar<<<blocks_for(P * pl.E, 256), 256, 0, st>>>(w.gebar, pl.EP, pl.E, P, w.ubar[ucur ^ 1], dn.Kp,
-                                                              dn.K - pl.E, with_ld(w.ubar16[ucur ^ 1], dn.Kp));
+                                                              dn.K - pl.E, unext16);
       AVC_LAUNCH_TRY();
     }
     ucur ^= 1;

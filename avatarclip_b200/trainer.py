@@ -228,6 +228,17 @@ class AppearanceTrainer:
         self._graph, self._graph_key = g, (id(dv), dv.bg_choice, float(cos_anneal))
         return g
 
+    def release_graph(self):
+        """Drop the captured step graph.  MUST run before the process group is destroyed when the graph holds the NCCL
+        all-reduce: a communicator cannot be torn down while a captured graph still references it
+        (`destroy_process_group()` then never returns)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
+            self._graph_key = None
+            self._graph_loss = None
+            torch.cuda.synchronize(self.device)
+
     def _set_device_adam(self, lr: float):
         self._adam_state[0].fill_(float(self.iter_step))
         self._adam_state[1].fill_(float(lr))

@@ -448,6 +448,11 @@ def run_native(args):
                 line["ref_gpu"] = reference_gpu(sp, cp, clip_sd, text, device, steps=max(5, min(K, 20)))
         real_stdout.emit(json.dumps(line))
     if world > 1:
+        tr.release_graph()          # the graph may hold the NCCL all-reduce: it has to go before the communicator
+        del tr
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         torch.distributed.destroy_process_group()
 
 
