@@ -32,9 +32,9 @@ import torch  # noqa: E402
 from avatarclip_b200 import workload as WL  # noqa: E402  (host-side numpy / CPU torch only)
 
 METRIC = "appearance-optim steps/sec (512 rays x 128 samples, CLIP loss)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu (profiles/r1_launches_tcgen05_engine.txt): mean over the
-# 73 NT / 21 TN launches of one step (NT: 7.99 GB per step; the launches of the fine pass move 87-350 MB each)
-TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 128.6e6, "avc::tc::gemm_tc_nt_kernel": 109.4e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu (profiles/r2_launches_tcgen05_engine.txt, final round-2
+# build): mean over the 41 NT / 21 TN launches of one step (all in the fine pass; 11.1 GB of DRAM traffic per step in total)
+TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 128.0e6, "avc::tc::gemm_tc_nt_kernel": 188.6e6}
 N_RAYS, CANVAS = 512, 224
 SDF_KW, COL_KW, REN_KW = WL.B2_SDF_KW, WL.B2_COL_KW, WL.B2_REN_KW
 VARIANCE = 0.3
