@@ -719,7 +719,7 @@ int avc_neus_render_bwd(const avc_neus_cfg* cfg, const float* params, const floa
   AVC_LAUNCH_TRY();
   for (int64_t r0 = 0; r0 < R; r0 += Rc_max) {   // eikonal normaliser over ALL rays of the call
     const int64_t Rc = (R - r0) < Rc_max ? (R - r0) : Rc_max;
-    k_relax_count<<<blocks_for(Rc, 128), 128, 0, st>>>(rays_o + r0 * 3, rays_d + r0 * 3, fwd_out->z_vals + r0 * pl.S,
+    k_relax_count<<<blocks_for(Rc, 8), 256, 0, st>>>(rays_o + r0 * 3, rays_d + r0 * 3, fwd_out->z_vals + r0 * pl.S,
                                                        pl.S, Rc, 2.0f / (float)pl.n0, w.ray_part);
     k_reduce_ray_part<<<1, 1024, 0, st>>>(w.ray_part, Rc, 1, w.ctx + CTX_EIK_DEN);
     AVC_LAUNCH_TRY();
