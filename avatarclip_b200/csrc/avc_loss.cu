@@ -8,6 +8,9 @@
 //             k_loss_final  scalars
 //   backward  k_shade_bwd   one warp per ray: gather d canvas, back through the shading to the cotangents
 //                           of color_fine / extra_color_fine / gradients / weights / weight_sum
+// The ablation confs (confs/ablation/*_0..2.conf) switch train.texture_cast_light and / or train.add_no_texture off:
+// `plain_texture` puts the un-shaded extra colour on canvas 0 (main.py:515-520), `no_shading_term` drops the CLIP term on
+// canvas 1 (main.py:521,533).
 #include "avc_common.cuh"
 
 using namespace avc;
@@ -115,7 +118,8 @@ k_shade_fwd(avc_loss_inputs in, float* __restrict__ canvases, float* __restrict_
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float ex = in.extra_color_fine[(size_t)r * 3 + c];
-    t[c] = fminf(fmaxf(ex * s.shade2, 0.f), 1.f);                      // texture_shading (:453)
+    t[c] = in.plain_texture ? ex                                       // full_extra_color_fine (:475-477), cast light off
+                            : fminf(fmaxf(ex * s.shade2, 0.f), 1.f);   // texture_shading (:453)
     sh[c] = s.low ? ex : s.shade;                                      // rand_shading_rgb (:445-448)
     float e = in.color_fine[(size_t)r * 3 + c] - in.true_rgb[(size_t)p * 3 + c];
     l1 += fabsf(e * m);
@@ -165,11 +169,17 @@ k_shade_bwd(avc_loss_inputs in, const float* __restrict__ d_canvases, const floa
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float ex = in.extra_color_fine[(size_t)r * 3 + c];
-    float prod = ex * s.shade2;
-    float inr = (prod >= 0.f && prod <= 1.f) ? 1.f : 0.f;              // clamp(0,1) backward: inclusive, like torch
-    dex[c] = dt[c] * inr * s.shade2;
-    if (!s.low) d_shade += dt[c] * inr * ex;                           // shade2 = shade unless low
-    if (s.low) dex[c] += ds[c]; else d_shade += ds[c];                 // rand_shading_rgb
+    if (in.plain_texture) {
+      dex[c] = dt[c];                                                  // canvas 0 is the extra colour itself
+    } else {
+      float prod = ex * s.shade2;
+      float inr = (prod >= 0.f && prod <= 1.f) ? 1.f : 0.f;            // clamp(0,1) backward: inclusive, like torch
+      dex[c] = dt[c] * inr * s.shade2;
+      if (!s.low) d_shade += dt[c] * inr * ex;                         // shade2 = shade unless low
+    }
+    if (!in.no_shading_term) {                                         // rand_shading_rgb feeds a CLIP term (:521-526)
+      if (s.low) dex[c] += ds[c]; else d_shade += ds[c];
+    }
     float e = in.color_fine[(size_t)r * 3 + c] - in.true_rgb[(size_t)p * 3 + c];
     float sg = (e * m > 0.f) ? 1.f : ((e * m < 0.f) ? -1.f : 0.f);     // d|x|/dx, 0 at 0 (l1_loss)
     dcol[c] = sg * m / mask_sum;
@@ -211,6 +221,7 @@ int check_inputs(const avc_loss_inputs* in) {
   if (in->R < 1 || in->S < 1 || in->H < 1 || in->W < 1) return AVC_E_SIZE;
   if (in->bg_choice < 0 || in->bg_choice > 3) return AVC_E_BADCFG;
   if ((in->bg_choice == 1 || in->bg_choice == 2) && !in->background) return AVC_E_NULL;
+  if ((in->plain_texture | in->no_shading_term) & ~1) return AVC_E_BADCFG;
   return 0;
 }
 

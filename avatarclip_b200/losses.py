@@ -1,6 +1,6 @@
 """Host-side wrapper of the shading / canvas / loss-stage kernels (``avc_loss_stage_*``), i.e. of
-AvatarGen/AppearanceGen/main.py:417-497,528-534 for the train_clip configuration every shipped conf uses
-(use_silhouettes, add_no_texture, texture_cast_light).  ``shade_and_losses`` is an autograd function so the
+AvatarGen/AppearanceGen/main.py:417-497,528-534 for use_silhouettes = True (every shipped train_clip conf), with the
+add_no_texture / texture_cast_light switches of the ablation confs.  ``shade_and_losses`` is an autograd function so the
 stage can sit between ``NeuSRenderer.render`` and the CLIP tower in an unmodified training loop; the fused
 train step (``avatarclip_b200.trainer``) calls the same C entry points directly.
 """
@@ -23,7 +23,8 @@ class LossInputs(C.Structure):
                                           "gradient_error", "pix", "in_mask", "true_rgb", "mask", "background")] + \
                [("bg_choice", C.c_int32), ("light_dir", C.c_float * 3), ("ambience", C.c_float),
                 ("view_scalars", C.c_void_p), ("igr_weight", C.c_float), ("mask_weight", C.c_float), ("clip_weight", C.c_float),
-                ("R", C.c_int32), ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+                ("R", C.c_int32), ("S", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("plain_texture", C.c_int32), ("no_shading_term", C.c_int32)]
 
 
 def _bind(L):
@@ -41,7 +42,8 @@ class StepInputs:
     """Per-step, non-differentiable inputs of the stage (all CUDA tensors)."""
 
     def __init__(self, pix, in_mask, true_rgb, mask, H, W, light_dir, ambience, bg_choice=3, background=None,
-                 igr_weight=0.1, mask_weight=0.5, clip_weight=1.0, view_scalars=None):
+                 igr_weight=0.1, mask_weight=0.5, clip_weight=1.0, view_scalars=None,
+                 texture_cast_light: bool = True, add_no_texture: bool = True):
         self.pix = pix.to(torch.int32).contiguous()
         self.in_mask = in_mask.to(torch.uint8).contiguous().reshape(-1)
         self.true_rgb = true_rgb.float().contiguous().reshape(-1, 3)
@@ -55,6 +57,9 @@ class StepInputs:
         # captured CUDA graph of the step can be replayed on a new view
         self.view_scalars = view_scalars
         self.igr_weight, self.mask_weight, self.clip_weight = float(igr_weight), float(mask_weight), float(clip_weight)
+        # the two switches the shipped ablation confs turn off (main.py:509-526): without texture_cast_light canvas 0 is
+        # the un-shaded extra colour; without add_no_texture the shading canvas carries no CLIP term
+        self.texture_cast_light, self.add_no_texture = bool(texture_cast_light), bool(add_no_texture)
 
 
 def make_inputs(render_out: Dict[str, torch.Tensor], si: StepInputs) -> LossInputs:
@@ -70,6 +75,7 @@ def make_inputs(render_out: Dict[str, torch.Tensor], si: StepInputs) -> LossInpu
     li.ambience, li.igr_weight, li.mask_weight, li.clip_weight = si.ambience, si.igr_weight, si.mask_weight, si.clip_weight
     li.view_scalars = None if si.view_scalars is None else si.view_scalars.data_ptr()
     li.R, li.S, li.H, li.W = R, S, si.H, si.W
+    li.plain_texture, li.no_shading_term = int(not si.texture_cast_light), int(not si.add_no_texture)
     return li
 
 

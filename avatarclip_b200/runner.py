@@ -231,7 +231,9 @@ class Runner:
             self.trainer = AppearanceTrainer(self.renderer, self.clip_tower, self.encoded_text, lr=self.learning_rate,
                                              igr_weight=self.igr_weight, mask_weight=self.mask_weight,
                                              clip_weight=1.0 if self.clip_weight is None else self.clip_weight,
-                                             process_group=self.process_group, device=self.device)
+                                             process_group=self.process_group, device=self.device,
+                                             texture_cast_light=self.texture_cast_light,
+                                             add_no_texture=self.add_no_texture)
             self.trainer.iter_step = self.iter_step
             if self._pending_optimizer_state is not None:      # checkpoint loaded before init_clip() (the CLI order)
                 self._load_optimizer_state_dict(self._pending_optimizer_state)
@@ -243,9 +245,10 @@ class Runner:
         """The appearance-optimisation loop.  ``view_source(step) -> view`` overrides the per-step view (tests /
         synthetic workloads); by default every step draws a camera, rasterises the template (``init_smpl``) and prepares
         the silhouette rays on the device, one step ahead of the optimiser."""
-        if not (self.use_silhouettes and self.add_no_texture and self.texture_cast_light and self.extra_color):
-            raise NotImplementedError("avatarclip_b200 implements the train_clip configuration every shipped conf uses: "
-                                      "use_silhouettes, add_no_texture, texture_cast_light, extra_color (DESIGN.md)")
+        if not (self.use_silhouettes and self.extra_color):
+            raise NotImplementedError("avatarclip_b200 implements the train_clip configurations of the shipped confs: "
+                                      "use_silhouettes and extra_color on (all 179 train_clip confs); add_no_texture / "
+                                      "texture_cast_light / use_bg_aug / face and back prompts as the conf says (DESIGN.md)")
         from .views import ViewBuilder
         tr = self._ensure_trainer()
         self.writer = self._make_writer()
@@ -254,7 +257,8 @@ class Runner:
             if self.v is None:
                 raise RuntimeError("call init_smpl() first (main.py:973): train_clip rasterises the posed template")
             sampler = StepSampler(self.seed, self.use_face_prompt, self.head_height, self.use_bg_aug,
-                                  rng=np.random if self.seed is not None else None)
+                                  rng=np.random if self.seed is not None else None,
+                                  cast_light=self.add_no_texture or self.texture_cast_light)            # main.py:425
             builder = ViewBuilder(self.v, self.f, self.max_ray_num, self.mask_weight, self.device,
                                   image_size=self.dataset.H,
                                   camera_angle_x=2 * np.arctan(0.5 * self.dataset.W / self.dataset.focal))

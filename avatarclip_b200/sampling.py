@@ -9,6 +9,8 @@ main.py:104-114).  ``StepSampler`` reproduces the numpy stream draw for draw, in
                              normal(0, 0.1) x 3 [look-at point]                             (utils.py:66-70)
     background   choice(4) when use_bg_aug; mode 2 additionally choice(arange(10, 20))      (main.py:388-400)
     light        uniform(-pi/4, pi/4) x 2, then ambience uniform(0, 0.2)                    (main.py:433,440)
+                 -- only when add_no_texture or texture_cast_light (the block of main.py:425-453; the ablation confs
+                 *_0 / *_1 switch both off and the stream then has no light draws)
 
 so that with the same seed the same cameras, backgrounds modes, light directions and ambiences come out
 (``oracle/pin_sampling.py`` executes the reference's own lines against this file).  Draws the reference takes from
@@ -100,12 +102,13 @@ class StepDraw:
 
 class StepSampler:
     def __init__(self, seed: Optional[int] = None, use_face_prompt: bool = False, head_height: float = 0.65,
-                 use_bg_aug: bool = True, rng=None):
+                 use_bg_aug: bool = True, rng=None, cast_light: bool = True):
         """``seed`` None: numpy's global generator, as the reference when ``train.seed`` is absent; an int: a private
         ``RandomState(seed)`` -- the same stream ``np.random.seed(seed)`` gives the reference (main.py:104-110)."""
         self.rng = rng if rng is not None else (np.random if seed is None else np.random.RandomState(seed))
         self.seed = 0 if seed is None else int(seed)
         self.use_face_prompt, self.head_height, self.use_bg_aug = bool(use_face_prompt), float(head_height), bool(use_bg_aug)
+        self.cast_light = bool(cast_light)      # train.add_no_texture or train.texture_cast_light (main.py:425)
         import torch
         self._tgen = torch.Generator().manual_seed(self.seed)
         self.count = 0
@@ -129,8 +132,11 @@ class StepSampler:
         if bg_choice == 2:
             chess_div = int(rng.choice(np.arange(10, 20)))
             sigma = float(torch.empty(1).uniform_(0.1, 2.0, generator=self._tgen))
-        light = sphere_coord(theta + rng.uniform(-np.pi / 4, np.pi / 4), phi + rng.uniform(-np.pi / 4, np.pi / 4))
-        ambience = float(rng.uniform(0, 0.2))
+        if self.cast_light:
+            light = sphere_coord(theta + rng.uniform(-np.pi / 4, np.pi / 4), phi + rng.uniform(-np.pi / 4, np.pi / 4))
+            ambience = float(rng.uniform(0, 0.2))
+        else:                                   # no shading block in the step: no draws, the values are never used
+            light, ambience = np.array([0.0, 0.0, 1.0]), 0.0
         d = StepDraw(self.count, face, eye, at, float(theta), float(phi), int(is_front), pose, bg_choice, chess_div, sigma,
                      light.astype(np.float32), ambience, (self.seed * 1000003 + self.count) & 0x7FFFFFFF)
         self.count += 1

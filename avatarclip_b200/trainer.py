@@ -54,8 +54,14 @@ class DeviceView:
 class AppearanceTrainer:
     def __init__(self, renderer: NeuSRenderer, clip_tower, text_emb: torch.Tensor, lr: float = 5e-4,
                  igr_weight: float = 0.1, mask_weight: float = 0.5, clip_weight: float = 1.0,
-                 betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, device="cuda"):
+                 betas=(0.9, 0.999), eps: float = 1e-8, process_group=None, device="cuda",
+                 texture_cast_light: bool = True, add_no_texture: bool = True):
         self.renderer, self.clip = renderer, clip_tower
+        # train.texture_cast_light / train.add_no_texture (main.py:509-534; off in confs/ablation/*_0..2.conf): without the
+        # first, canvas 0 carries the un-shaded extra colour; without the second, the loss has no CLIP term on the shading
+        # canvas.  The CLIP batch stays B = 2 in every configuration (one launch structure); the loss stage's backward
+        # ignores the second canvas' cotangent when its term is absent.
+        self.texture_cast_light, self.add_no_texture = bool(texture_cast_light), bool(add_no_texture)
         self.device = torch.device(device)
         self.fp = renderer.flat_params(self.device)
         self.exp_avg = torch.zeros_like(self.fp.flat)
@@ -112,7 +118,8 @@ class AppearanceTrainer:
         mark("render_fwd")
         si = losses.StepInputs(dv.pix, dv.in_mask, dv.true_rgb, dv.mask, dv.H, dv.W, dv.light_dir, dv.ambience,
                                dv.bg_choice, dv.canvas_background, self.igr_weight, self.mask_weight, self.clip_weight,
-                               view_scalars=dv.scalars)
+                               view_scalars=dv.scalars, texture_cast_light=self.texture_cast_light,
+                               add_no_texture=self.add_no_texture)
         canv, scal = losses.stage_forward(out, si)
         self.scalars = scal
         mark("loss_stage_fwd")
@@ -144,6 +151,8 @@ class AppearanceTrainer:
 
     def loss_value(self) -> torch.Tensor:
         """Total loss of main.py:528-534 as a device scalar (one tiny kernel; read it with .item() to sync)."""
+        if not self.add_no_texture:                                   # main.py:528-531 without :533-534
+            return self.scalars[losses.S_BASE] + (1.0 - self.cos[0]) * self.clip_weight
         return self.scalars[losses.S_BASE] + ((1.0 - self.cos) * self.clip_weight).sum()
 
     def optimizer_step(self, lr: Optional[float] = None):

@@ -37,7 +37,7 @@ typedef void* avc_stream_t; /* cudaStream_t */
 #define AVC_E_ALIGN (-4)    /* pointer not 16-byte aligned                              */
 #define AVC_E_NOSTASH (-5)  /* backward called on a workspace with no matching forward  */
 
-#define AVC_ABI_VERSION 2
+#define AVC_ABI_VERSION 3
 int avc_abi_version(void);
 /* Compiled-for architecture string, e.g. "sm_100a". */
 const char* avc_build_arch(void);
@@ -217,7 +217,9 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* w, int32_
 
 /* ------------------------------------------------------------------------------------------
  * Shading + canvas scatter + non-CLIP losses of Runner.train_clip (main.py:417-497, 528-534) with
- * use_silhouettes / add_no_texture / texture_cast_light = True (every shipped train_clip conf).
+ * use_silhouettes = True (every shipped train_clip conf).  The two switches the shipped confs vary
+ * (confs/ablation/*_0..2.conf) are the last two fields: zero-initialised = add_no_texture = texture_cast_light =
+ * True, the configuration of confs/examples*.
  * Rays are the True pixels of the dilated mask; pix[r] is the flat canvas index (y*W + x) of ray r.
  * ------------------------------------------------------------------------------------------ */
 typedef struct avc_loss_inputs {
@@ -241,13 +243,19 @@ typedef struct avc_loss_inputs {
                                     (lets a captured CUDA graph of the step be replayed with new per-view draws) */
   float igr_weight, mask_weight, clip_weight;  /* conf train.* */
   int32_t R, S, H, W;
+  /* ABI 3 */
+  int32_t plain_texture;         /* 1: train.texture_cast_light = False -- canvas 0 is the extra colour itself
+                                    (full_extra_color_fine, main.py:475-477,516), no shading factor, no clamp */
+  int32_t no_shading_term;       /* 1: train.add_no_texture = False -- the loss has no CLIP term on canvas 1
+                                    (main.py:521,533): the backward ignores d_canvases[1] */
 } avc_loss_inputs;
 
 /* scalars written by the forward: [0] color_loss, [1] eikonal, [2] mask_loss (BCE), [3] psnr,
  * [4] base_loss = color + igr*eik + mask_w*bce, [5..7] internal sums (l1, bce, sq), [8] mask_sum */
 #define AVC_LOSS_SCALARS 16
-/* Forward: fills canvases[2][H][W][3] (0: texture_shading, 1: rand_shading_rgb; main.py:466-473)
- * and scalars[AVC_LOSS_SCALARS]. */
+/* Forward: fills canvases[2][H][W][3] (0: texture_shading -- or the extra colour when plain_texture --,
+ * 1: rand_shading_rgb; main.py:466-477) and scalars[AVC_LOSS_SCALARS].  Canvas 1 is always written (finite values)
+ * so that a caller may keep one B = 2 CLIP batch for every configuration. */
 int avc_loss_stage_fwd(const avc_loss_inputs* in, float* canvases, float* scalars, avc_stream_t stream);
 /* Backward: d_canvases[2][H][W][3] = d loss / d canvases (from the CLIP backward) plus the direct
  * loss terms -> cotangents of the render outputs (struct avc_neus_cotangents, written in full:

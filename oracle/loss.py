@@ -56,8 +56,12 @@ def pinhole_rays(pose, H, W, full_res=256, fov=math.pi / 3):
 def shading_and_losses(render_out: Dict[str, torch.Tensor], dilated_mask: torch.Tensor, H: int, W: int,
                        true_rgb: torch.Tensor, mask: torch.Tensor, light_dir: torch.Tensor, ambience: float,
                        background_choice: int = 3, background_rgb: Optional[torch.Tensor] = None,
-                       igr_weight: float = 0.1, mask_weight: float = 0.1):
-    """main.py:417-497 with use_silhouettes=True, add_no_texture=texture_cast_light=True.
+                       igr_weight: float = 0.1, mask_weight: float = 0.1, add_no_texture: bool = True,
+                       texture_cast_light: bool = True):
+    """main.py:417-497 with use_silhouettes=True.  ``add_no_texture`` / ``texture_cast_light`` are the switches of
+    main.py:425,466,509-526 (both True in confs/examples*, switched off in confs/ablation/*_0..2.conf): "texture_canvas" is
+    the image the first CLIP term sees (texture_shading, or the extra-colour canvas of :475-477 without cast light),
+    "shading_canvas" the one of the second term (None without add_no_texture).
 
     render_out : dict from NeuSRenderer.render for the R rays of the dilated mask (row-major order of True pixels)
     dilated_mask : bool [H, W] with R True entries
@@ -69,6 +73,7 @@ def shading_and_losses(render_out: Dict[str, torch.Tensor], dilated_mask: torch.
     color_fine = render_out["color_fine"]
     extra = render_out["extra_color_fine"]
     dt = color_fine.dtype
+    shading = add_no_texture or texture_cast_light                       # :425
     # ---- cast light (:425-453)
     normals = (render_out["gradients"] * render_out["weights"][:, :, None]).sum(dim=1)
     normals = normals / (torch.norm(normals, dim=-1, keepdim=True) + 1e-7)
@@ -96,8 +101,8 @@ def shading_and_losses(render_out: Dict[str, torch.Tensor], dilated_mask: torch.
         out[dilated_mask] = vals
         return out
 
-    full_texture = scatter(background, texture_shading)
-    full_shading = scatter(background, rand_shading_rgb)
+    full_texture = scatter(background, texture_shading if texture_cast_light else extra)     # :466-477, :509-520
+    full_shading = scatter(background, rand_shading_rgb) if (shading and add_no_texture) else None
     full_color = scatter(torch.zeros(H, W, 3, dtype=dt), color_fine).reshape(-1, 3)
     full_wsum = scatter(torch.zeros(H, W, 1, dtype=dt), render_out["weight_sum"]).reshape(-1, 1)
     # ---- losses (:489-497)
@@ -113,8 +118,9 @@ def shading_and_losses(render_out: Dict[str, torch.Tensor], dilated_mask: torch.
 
 
 def total_loss(stage: Dict[str, torch.Tensor], cosine_texture, cosine_shading, clip_weight: float = 1.0):
-    """main.py:528-534 with add_no_texture=True."""
-    return stage["base_loss"] + (1.0 - cosine_texture) * clip_weight + (1.0 - cosine_shading) * clip_weight
+    """main.py:528-534; ``cosine_shading`` None = add_no_texture off (no second CLIP term)."""
+    loss = stage["base_loss"] + (1.0 - cosine_texture) * clip_weight
+    return loss if cosine_shading is None else loss + (1.0 - cosine_shading) * clip_weight
 
 
 # ----------------------------------------------------------------------------- schedules

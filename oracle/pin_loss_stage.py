@@ -88,8 +88,9 @@ def synthetic_inputs(H, seed, choice_i):
 
 # ------------------------------------------------------------------------------------------------ reference run
 def run_reference_stage(snippet, ro, dilated, true_rgb, mask, background_rgb, choice_i, H, S, clip_state, text,
-                        theta, phi, np_seed, weights):
+                        theta, phi, np_seed, weights, flags=(True, True)):
     igr_w, mask_w, clip_w = weights
+    add_no_texture, texture_cast_light = flags
     from torchvision import transforms
     leaves = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in ro.items()}
 
@@ -100,7 +101,8 @@ def run_reference_stage(snippet, ro, dilated, true_rgb, mask, background_rgb, ch
 
     perceptor = types.SimpleNamespace(encode_image=lambda x: cv.encode_image(clip_state, x))
     self = types.SimpleNamespace(
-        renderer=Renderer(), get_cos_anneal_ratio=lambda: 1.0, add_no_texture=True, texture_cast_light=True,
+        renderer=Renderer(), get_cos_anneal_ratio=lambda: 1.0, add_no_texture=add_no_texture,
+        texture_cast_light=texture_cast_light,
         use_silhouettes=True, use_face_prompt=False, use_back_prompt=False, igr_weight=igr_w, mask_weight=mask_w,
         clip_weight=clip_w, perceptor=perceptor, encoded_text=text,
         clip_normalizer=transforms.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)),
@@ -124,28 +126,34 @@ def run_reference_stage(snippet, ro, dilated, true_rgb, mask, background_rgb, ch
     loss = ns["loss"]
     diff = [k for k in ("color_fine", "extra_color_fine", "gradients", "weights", "weight_sum", "gradient_error")]
     grads = torch.autograd.grad(loss, [leaves[k] for k in diff], allow_unused=True)
-    out = {k: ns[k].detach() for k in ("loss", "color_fine_loss", "mask_loss", "eikonal_loss", "psnr", "cosine",
-                                        "cosine_shading", "texture_shading", "rand_shading_rgb")}
+    out = {k: ns[k].detach() for k in ("loss", "color_fine_loss", "mask_loss", "eikonal_loss", "psnr", "cosine")}
+    # the image the first CLIP term saw (main.py:509-520): texture_shading, or the extra-colour canvas without cast light
+    out["texture_shading"] = (ns["texture_shading"] if texture_cast_light else ns["extra_color_fine"]).detach()
+    out["cosine_shading"] = ns["cosine_shading"].detach() if add_no_texture else None
+    out["rand_shading_rgb"] = ns["rand_shading_rgb"].detach() if (add_no_texture or texture_cast_light) else None
     out["grads"] = {k: (torch.zeros_like(leaves[k]) if g is None else g.detach()) for k, g in zip(diff, grads)}
     return out
 
 
 def run_oracle_stage(ro, dilated, true_rgb, mask, background_rgb, choice_i, H, clip_state, text, light_dir, ambience,
-                     weights):
+                     weights, flags=(True, True)):
     igr_w, mask_w, clip_w = weights
+    add_no_texture, texture_cast_light = flags
     leaves = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in ro.items()}
     m = (mask > 0.5).float() if mask_w > 0.0 else torch.ones_like(mask)
     st = ol.shading_and_losses(leaves, dilated, H, H, true_rgb, m, torch.as_tensor(light_dir, dtype=torch.float32),
-                               float(ambience), choice_i, background_rgb if choice_i in (1, 2) else None, igr_w, mask_w)
+                               float(ambience), choice_i, background_rgb if choice_i in (1, 2) else None, igr_w, mask_w,
+                               add_no_texture=add_no_texture, texture_cast_light=texture_cast_light)
     c_tex = cv.clip_cosine(clip_state, st["texture_canvas"], text)
-    c_sh = cv.clip_cosine(clip_state, st["shading_canvas"], text)
+    c_sh = cv.clip_cosine(clip_state, st["shading_canvas"], text) if add_no_texture else None
     loss = ol.total_loss(st, c_tex, c_sh, clip_w)
     diff = ["color_fine", "extra_color_fine", "gradients", "weights", "weight_sum", "gradient_error"]
     grads = torch.autograd.grad(loss, [leaves[k] for k in diff], allow_unused=True)
     out = {"loss": loss.detach(), "color_fine_loss": st["color_loss"].detach(), "mask_loss": st["mask_loss"].detach(),
            "eikonal_loss": st["eikonal_loss"].detach(), "psnr": st["psnr"].detach(), "cosine": c_tex.detach(),
-           "cosine_shading": c_sh.detach(), "texture_shading": st["texture_canvas"].reshape(-1, 3).detach(),
-           "rand_shading_rgb": st["shading_canvas"].reshape(-1, 3).detach()}
+           "cosine_shading": None if c_sh is None else c_sh.detach(),
+           "texture_shading": st["texture_canvas"].reshape(-1, 3).detach(),
+           "rand_shading_rgb": None if st["shading_canvas"] is None else st["shading_canvas"].reshape(-1, 3).detach()}
     out["grads"] = {k: (torch.zeros_like(leaves[k]) if g is None else g.detach()) for k, g in zip(diff, grads)}
     return out
 
@@ -226,9 +234,16 @@ def main():
     text = torch.randn(1, 512, generator=torch.Generator().manual_seed(11))
     golden = {"cases": []}
     # the 64 x 64 cases are also written to the golden fixture (small); all canvases are <= 224 (up-sampling / identity)
-    for (H, choice_i, seed, weights) in ((112, 3, 1, (0.1, 0.5, 1.0)), (112, 1, 2, (0.1, 0.5, 1.0)),
-                                         (224, 0, 3, (0.2, 0.0, 0.7)), (112, 2, 4, (0.1, 0.1, 1.0)),
-                                         (64, 3, 5, (0.1, 0.5, 1.0)), (64, 1, 6, (0.1, 0.5, 1.0)), (64, 0, 7, (0.3, 0.0, 0.5))):
+    # flags = (add_no_texture, texture_cast_light): (True, True) is confs/examples*; the 48 x 48 cases are the switches of
+    # confs/ablation/*_0.conf (no shading block at all, black background), *_1.conf (the same with background
+    # augmentation), *_2.conf (shading term, un-shaded texture) and the remaining combination
+    T2 = (True, True)
+    for (H, choice_i, seed, weights, flags) in (
+            (112, 3, 1, (0.1, 0.5, 1.0), T2), (112, 1, 2, (0.1, 0.5, 1.0), T2), (224, 0, 3, (0.2, 0.0, 0.7), T2),
+            (112, 2, 4, (0.1, 0.1, 1.0), T2), (64, 3, 5, (0.1, 0.5, 1.0), T2), (64, 1, 6, (0.1, 0.5, 1.0), T2),
+            (64, 0, 7, (0.3, 0.0, 0.5), T2),
+            (48, 3, 8, (0.1, 0.5, 1.0), (False, False)), (48, 1, 9, (0.1, 1.0, 1.0), (False, False)),
+            (48, 0, 10, (0.1, 0.5, 1.0), (True, False)), (48, 3, 11, (0.1, 0.5, 0.8), (False, True))):
         ro, dilated, true_rgb, mask, bg, S = synthetic_inputs(H, seed, choice_i)
         theta, phi, np_seed = 1.2 + 0.1 * seed, 0.4 * seed, 100 + seed
         np.random.seed(np_seed)                     # replay the snippet's three draws (main.py:433, 440)
@@ -236,20 +251,26 @@ def main():
         light_dir = REF_FUNCS["sphere_coord"](theta + u1, phi + u2)
         ambience = np.random.uniform(0, 0.2)
         ref = run_reference_stage(snippet, ro, dilated, true_rgb, mask, bg, choice_i, H, S, clip_state, text, theta, phi,
-                                  np_seed, weights)
-        orc = run_oracle_stage(ro, dilated, true_rgb, mask, bg, choice_i, H, clip_state, text, light_dir, ambience, weights)
+                                  np_seed, weights, flags)
+        orc = run_oracle_stage(ro, dilated, true_rgb, mask, bg, choice_i, H, clip_state, text, light_dir, ambience, weights,
+                               flags)
         for k in ("loss", "color_fine_loss", "mask_loss", "eikonal_loss", "psnr", "cosine", "cosine_shading",
                   "texture_shading", "rand_shading_rgb"):
-            note("stage." + k, rel(orc[k], ref[k]), 2e-6)
+            if k == "rand_shading_rgb" and not flags[0]:
+                continue                            # computed by the reference (with cast light) but feeds no loss term
+            assert (orc[k] is None) == (ref[k] is None), k
+            if ref[k] is not None:
+                note("stage." + k, rel(orc[k], ref[k]), 2e-6)
         for k in ref["grads"]:
             note("stage.grad." + k, rel(orc["grads"][k], ref["grads"][k]), 2e-5)
-        if H == 64:
-            golden["cases"].append({"H": H, "choice_i": choice_i, "weights": weights, "render_out": ro, "dilated_mask": dilated,
+        if H <= 64:
+            golden["cases"].append({"H": H, "choice_i": choice_i, "weights": weights, "flags": flags,
+                                    "render_out": ro, "dilated_mask": dilated,
                                     "true_rgb": true_rgb, "mask": mask, "background_rgb": bg,
                                     "light_dir": torch.as_tensor(light_dir), "ambience": float(ambience), "clip_seed": 3,
                                     "text": text, "ref": {k: v for k, v in ref.items() if k != "grads"},
                                     "ref_grads": ref["grads"]})
-        print(f"case H={H} bg={choice_i}: loss ref {float(ref['loss']):.6f} oracle {float(orc['loss']):.6f}")
+        print(f"case H={H} bg={choice_i} flags={flags}: loss ref {float(ref['loss']):.6f} oracle {float(orc['loss']):.6f}")
     # ray fixture: a smaller ray budget keeps the file small (the 12 544-ray case above is asserted, not stored)
     mo2, mv2, Wc2, dm2 = REF_FUNCS["gen_rays_silhouettes"](ds, pose, 2048, sil)
     n2, f2 = REF_FUNCS["near_far_from_sphere"](ds, mo2.float(), mv2.float())

@@ -12,6 +12,8 @@ arithmetic and the order of the numpy draws are the reference's own text:
 and replays ``np.random.seed(s)`` on both sides for 24 consecutive steps with use_face_prompt on (every 4th step is a
 face step) and background augmentation on.  Bit-exact equality is asserted for every numpy-derived quantity; the
 reference's values are written to tests/golden/sampling.json so the CPU test-suite replays them without /root/reference.
+The streams of the ablation confs (no face prompt; with / without background augmentation; no shading block, i.e. no
+light / ambience draws, main.py:425) are replayed the same way for 12 steps each.
 """
 from __future__ import annotations
 
@@ -30,7 +32,8 @@ from avatarclip_b200.sampling import StepSampler  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden", "sampling.json")
 
 
-def reference_draws(seed: int, n_steps: int, head_height: float):
+def reference_draws(seed: int, n_steps: int, head_height: float, face: bool = True, bg_aug: bool = True,
+                    shading: bool = True):
     ns = {"np": np}
     exec(cut("models/utils.py", 6, 70, "def norm_np_arr", ").clip(-0.3, 0.3)"), ns)
     cam = cut("main.py", 348, 359, "if self.use_face_prompt and iter_i % 4 == 0", "pose = lookat(eye, at")
@@ -40,7 +43,7 @@ def reference_draws(seed: int, n_steps: int, head_height: float):
     amb = cut("main.py", 440, 440, "ambience = np.random.uniform(0, 0.2)", "")
 
     class Self:
-        use_face_prompt, use_bg_aug = True, True
+        use_face_prompt, use_bg_aug = face, bg_aug
     Self.head_height = head_height
     np.random.seed(seed)
     out = []
@@ -50,21 +53,23 @@ def reference_draws(seed: int, n_steps: int, head_height: float):
         exec(bgc, loc)
         if loc["choice_i"] == 2:
             exec(chess, loc)
-        exec(light, loc)
-        exec(amb, loc)
+        if shading:               # main.py:425: `if self.add_no_texture or self.texture_cast_light:` guards both draws
+            exec(light, loc)
+            exec(amb, loc)
         out.append({"eye": loc["eye"].tolist(), "at": np.asarray(loc["at"]).tolist(), "theta": float(loc["theta"]),
                     "phi": float(loc["phi"]), "is_front": int(loc["is_front"]), "pose": loc["pose"].tolist(),
                     "choice_i": int(loc["choice_i"]),
                     "chess_length": int(loc["chess_length"]) if loc["choice_i"] == 2 else None,
-                    "light_dir": loc["light_dir"].tolist(), "ambience": float(loc["ambience"])})
+                    "light_dir": loc["light_dir"].tolist() if shading else None,
+                    "ambience": float(loc["ambience"]) if shading else None})
     return out
 
 
-def compare(ref, seed, head_height):
-    s = StepSampler(seed=seed, use_face_prompt=True, head_height=head_height, use_bg_aug=True)
+def compare(ref, seed, head_height, face=True, bg_aug=True, shading=True):
+    s = StepSampler(seed=seed, use_face_prompt=face, head_height=head_height, use_bg_aug=bg_aug, cast_light=shading)
     for i, r in enumerate(ref):
         d = s.draw(i)
-        assert d.face_step == (i % 4 == 0)
+        assert d.face_step == (face and i % 4 == 0)
         assert np.array_equal(d.eye, np.asarray(r["eye"], dtype=np.float32)), (i, "eye")
         assert np.array_equal(d.at, np.asarray(r["at"], dtype=np.float32)), (i, "at")
         assert d.theta == r["theta"] and d.phi == r["phi"] and d.is_front == r["is_front"], (i, "angles")
@@ -72,15 +77,24 @@ def compare(ref, seed, head_height):
         assert d.bg_choice == r["choice_i"], (i, "bg")
         if r["choice_i"] == 2:
             assert 224 // d.chess_div == r["chess_length"], (i, "chess")
-        assert np.array_equal(d.light_dir, np.asarray(r["light_dir"]).astype(np.float32)), (i, "light")
-        assert d.ambience == r["ambience"], (i, "ambience")
+        if shading:
+            assert np.array_equal(d.light_dir, np.asarray(r["light_dir"]).astype(np.float32)), (i, "light")
+            assert d.ambience == r["ambience"], (i, "ambience")
 
 
 def main():
     seed, n, hh = 2022, 24, 0.65
     ref = reference_draws(seed, n, hh)
     compare(ref, seed, hh)
-    json.dump({"seed": seed, "head_height": hh, "steps": ref}, open(GOLDEN, "w"))
+    # the streams of the ablation confs (confs/ablation/*_0.conf: no background augmentation, no shading block;
+    # *_1.conf: background augmentation, no shading block; neither uses the face / back prompts)
+    ablation = {}
+    for name, kw in (("ablation_0", dict(face=False, bg_aug=False, shading=False)),
+                     ("ablation_1", dict(face=False, bg_aug=True, shading=False))):
+        r = reference_draws(seed, 12, hh, **kw)
+        compare(r, seed, hh, **kw)
+        ablation[name] = dict(kw, steps=r)
+    json.dump({"seed": seed, "head_height": hh, "steps": ref, "ablation": ablation}, open(GOLDEN, "w"))
     modes = sorted(set(r["choice_i"] for r in ref))
     print(f"[pin] sampling: {n} steps bit-exact against main.py:348-359,388-399,433,440 + utils.py:6-70 "
           f"(background modes seen: {modes}); wrote {GOLDEN}")

@@ -21,7 +21,9 @@ class OracleTrainer:
                  sdf_state: Dict[str, torch.Tensor], col_state: Dict[str, torch.Tensor], variance: float,
                  clip_state: Dict[str, torch.Tensor], text_emb: torch.Tensor, lr: float = 5e-4,
                  igr_weight: float = 0.1, mask_weight: float = 0.5, clip_weight: float = 1.0,
-                 dtype=torch.float32, clip_conf: clip_vit.ViTConf = None):
+                 dtype=torch.float32, clip_conf: clip_vit.ViTConf = None, add_no_texture: bool = True,
+                 texture_cast_light: bool = True):
+        self.add_no_texture, self.texture_cast_light = add_no_texture, texture_cast_light     # main.py:509-534
         self.sconf, self.cconf, self.rconf = sconf, cconf, rconf
         self.clip_conf = clip_conf if clip_conf is not None else clip_vit.ViTConf()
         self.dtype = dtype
@@ -60,11 +62,13 @@ class OracleTrainer:
         stage = oloss.shading_and_losses(out, dm, H, W, view.true_rgb.to(dt), view.mask.to(dt).reshape(-1, 1),
                                          torch.as_tensor(view.light_dir, dtype=dt), view.ambience,
                                          background_choice=view.bg_choice, background_rgb=cbg,
-                                         igr_weight=igr, mask_weight=mw)
+                                         igr_weight=igr, mask_weight=mw, add_no_texture=self.add_no_texture,
+                                         texture_cast_light=self.texture_cast_light)
         cos_t = clip_vit.clip_cosine(self.clip_state, stage["texture_canvas"], self.text[0], self.clip_conf)
-        cos_s = clip_vit.clip_cosine(self.clip_state, stage["shading_canvas"], self.text[1], self.clip_conf)
+        cos_s = clip_vit.clip_cosine(self.clip_state, stage["shading_canvas"], self.text[1], self.clip_conf) \
+            if self.add_no_texture else None
         total = oloss.total_loss(stage, cos_t, cos_s, cw)
-        return total, {"out": out, "stage": stage, "cos": torch.stack([cos_t, cos_s])}
+        return total, {"out": out, "stage": stage, "cos": torch.stack([cos_t, cos_s] if cos_s is not None else [cos_t])}
 
     def step(self, view, cos_anneal: float = 1.0):
         """zero_grad / backward / Adam.step (main.py:536-538).  Returns (loss, aux)."""

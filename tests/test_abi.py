@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 8
     for s in syms:
         assert hasattr(L, s), s
-    assert L.avc_abi_version() == 2
+    assert L.avc_abi_version() == 3
     assert L.avc_build_arch() == b"sm_100a"
 
 

@@ -74,25 +74,32 @@ def _rel(a, b):
     return float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
 
 
-@pytest.mark.parametrize("case", [0, 1, 2])
+@pytest.mark.parametrize("case", [0, 1, 2, 3, 4, 5, 6])
 def test_loss_stage_restatement_matches_reference_lines(case):
+    """Cases 0-2: add_no_texture = texture_cast_light = True (confs/examples*); 3-6: the switch combinations of
+    confs/ablation/*_0..2.conf (main.py:425,466,509-534)."""
     from oracle import clip_vit as cv
     from oracle import loss as ol
     c = _loss_golden()["cases"][case]
     H, choice = c["H"], c["choice_i"]
     igr_w, mask_w, clip_w = c["weights"]
+    no_tex, cast = c["flags"]
     leaves = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in c["render_out"].items()}
     mask = (c["mask"] > 0.5).float() if mask_w > 0.0 else torch.ones_like(c["mask"])          # main.py:407-410
     st = ol.shading_and_losses(leaves, c["dilated_mask"], H, H, c["true_rgb"], mask, c["light_dir"].float(), c["ambience"],
-                               choice, c["background_rgb"] if choice in (1, 2) else None, igr_w, mask_w)
+                               choice, c["background_rgb"] if choice in (1, 2) else None, igr_w, mask_w,
+                               add_no_texture=no_tex, texture_cast_light=cast)
     clip_state = cv.random_vit_state(seed=c["clip_seed"])
     c_tex = cv.clip_cosine(clip_state, st["texture_canvas"], c["text"])
-    c_sh = cv.clip_cosine(clip_state, st["shading_canvas"], c["text"])
+    c_sh = cv.clip_cosine(clip_state, st["shading_canvas"], c["text"]) if no_tex else None
     loss = ol.total_loss(st, c_tex, c_sh, clip_w)
     ref = c["ref"]
     got = {"loss": loss, "color_fine_loss": st["color_loss"], "mask_loss": st["mask_loss"], "eikonal_loss": st["eikonal_loss"],
-           "psnr": st["psnr"], "cosine": c_tex, "cosine_shading": c_sh,
-           "texture_shading": st["texture_canvas"].reshape(-1, 3), "rand_shading_rgb": st["shading_canvas"].reshape(-1, 3)}
+           "psnr": st["psnr"], "cosine": c_tex, "texture_shading": st["texture_canvas"].reshape(-1, 3)}
+    if no_tex:
+        got.update({"cosine_shading": c_sh, "rand_shading_rgb": st["shading_canvas"].reshape(-1, 3)})
+    else:
+        assert ref["cosine_shading"] is None and st["shading_canvas"] is None
     for k, v in got.items():
         assert _rel(v.detach(), ref[k]) < 5e-6, k
     names = ["color_fine", "extra_color_fine", "gradients", "weights", "weight_sum", "gradient_error"]

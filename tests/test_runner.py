@@ -14,8 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CONF = os.path.join(HERE, "runner_conf_sample.conf")
 
 
-def _conf_text(tmp_path, data_dir=None):
+def _conf_text(tmp_path, data_dir=None, edits=()):
     text = open(CONF).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "exp"))
+    for old, new in edits:
+        assert old in text
+        text = text.replace(old, new)
     if data_dir is not None:
         text = text.replace("./data/zero_beta_tpose_render", str(data_dir))
     p = tmp_path / "run.conf"
@@ -23,9 +26,9 @@ def _conf_text(tmp_path, data_dir=None):
     return str(p)
 
 
-def _runner(tmp_path, device, mode="train_clip", data_dir=None, is_continue=False):
+def _runner(tmp_path, device, mode="train_clip", data_dir=None, is_continue=False, edits=()):
     from avatarclip_b200.runner import Runner
-    return Runner(_conf_text(tmp_path, data_dir), mode=mode, case="smpl", device=device, is_continue=is_continue)
+    return Runner(_conf_text(tmp_path, data_dir, edits), mode=mode, case="smpl", device=device, is_continue=is_continue)
 
 
 def test_runner_construction_schedule_and_checkpoint_layout(tmp_path):
@@ -105,6 +108,50 @@ def test_runner_train_clip_real_loop_and_cli_order_resume(tmp_path):
     assert float(tr2.exp_avg.abs().max()) > 0
     img = r2.render_image(ol.lookat([0.0, 0.0, 1.6], [0.0, 0.0, 0.0]), resolution_level=8)
     assert img.shape == (32, 32, 3) and torch.isfinite(img).all()
+
+
+# the switch settings of confs/ablation/*_0.conf, *_1.conf, *_2.conf (no face / back prompts there)
+_NO_PROMPTS = (("use_face_prompt = True", "use_face_prompt = False"), ("use_back_prompt = True", "use_back_prompt = False"))
+ABLATIONS = {
+    "0": _NO_PROMPTS + (("add_no_texture = True", "add_no_texture = False"), ("texture_cast_light = True", "texture_cast_light = False"),
+                        ("use_silhouettes = True", "use_silhouettes = True\n    use_bg_aug = False")),
+    "1": _NO_PROMPTS + (("add_no_texture = True", "add_no_texture = False"), ("texture_cast_light = True", "texture_cast_light = False")),
+    "2": _NO_PROMPTS + (("texture_cast_light = True", "texture_cast_light = False"),),
+}
+
+
+def test_ablation_confs_construct_with_their_switches(tmp_path):
+    r = _runner(tmp_path, "cpu", mode="validate", edits=ABLATIONS["0"])
+    assert not (r.add_no_texture or r.texture_cast_light or r.use_bg_aug or r.use_face_prompt or r.use_back_prompt)
+    r = _runner(tmp_path, "cpu", mode="validate", edits=ABLATIONS["2"])
+    assert r.add_no_texture and not r.texture_cast_light and r.use_bg_aug
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
+def test_runner_train_clip_with_the_ablation_conf_switches(tmp_path, variant):
+    """The 18 confs under confs/ablation/*_{0,1,2}.conf switch add_no_texture / texture_cast_light (and use_bg_aug) off
+    (main.py:388-391,425,509-534): the real loop runs them -- finite losses, parameters move, the loss of a
+    step without the shading term is the base loss plus ONE CLIP term."""
+    from avatarclip_b200.workload import synthetic_body_mesh
+    from avatarclip_b200 import losses as PL
+    sd, text, _, _ = _clip_args()
+    v, f = synthetic_body_mesh(12, 16)
+    r = _runner(tmp_path, "cuda", edits=ABLATIONS[variant])
+    r.init_clip(sd, text)
+    r.init_smpl(v, f)
+    r.report_freq = 1
+    logs = []
+    before = r.color_network.lin0.weight_v.detach().clone()
+    assert r.train_clip(max_steps=3, log=logs.append, validate=False) == 3
+    vals = [float(str(m).split("loss = ")[1].split(" ")[0]) for m in logs if "loss = " in str(m)]
+    assert len(vals) == 3 and all(np.isfinite(vals))
+    assert not torch.equal(before, r.color_network.lin0.weight_v)
+    tr = r.trainer
+    n_terms = 2 if r.add_no_texture else 1
+    want = tr.scalars[PL.S_BASE] + ((1.0 - tr.cos[:n_terms]) * tr.clip_weight).sum()
+    assert abs(float(tr.loss_value()) - float(want)) < 1e-6
+    assert (tr.add_no_texture, tr.texture_cast_light) == (r.add_no_texture, r.texture_cast_light)
 
 
 @pytest.mark.gpu

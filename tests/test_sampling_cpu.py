@@ -32,6 +32,26 @@ def test_step_draws_match_reference_lines_bit_exactly():
     assert modes == {0, 1, 2, 3}
 
 
+def test_ablation_conf_streams_match_reference_lines_bit_exactly():
+    """confs/ablation/*_0.conf (no background augmentation) and *_1.conf: add_no_texture = texture_cast_light = False, so
+    the step has no shading block and the numpy stream no light / ambience draws (main.py:425); no face prompt."""
+    g = json.load(open(GOLDEN))
+    for name, rec in g["ablation"].items():
+        s = StepSampler(seed=g["seed"], use_face_prompt=rec["face"], head_height=g["head_height"], use_bg_aug=rec["bg_aug"],
+                        cast_light=rec["shading"])
+        for i, r in enumerate(rec["steps"]):
+            d = s.draw(i)
+            assert not d.face_step
+            assert np.array_equal(d.eye, np.asarray(r["eye"], dtype=np.float32)), (name, i)
+            assert np.array_equal(d.at, np.asarray(r["at"], dtype=np.float32)), (name, i)
+            assert np.array_equal(d.pose, np.asarray(r["pose"])), (name, i)
+            assert d.bg_choice == r["choice_i"], (name, i)
+            if r["choice_i"] == 2:
+                assert 224 // d.chess_div == r["chess_length"], (name, i)
+        if not rec["bg_aug"]:
+            assert all(r["choice_i"] == 3 for r in rec["steps"])
+
+
 def test_rank_strided_stream_equals_single_rank_stream():
     """N ranks x 1 view == 1 rank x N views: rank r of N gets draw number step * N + r of the same seeded stream."""
     one = StepSampler(seed=7)

@@ -10,7 +10,7 @@ from oracle.train_step import OracleTrainer
 pytestmark = pytest.mark.gpu
 
 
-def _setup(case, n_rays, H, bg_choice, seed=0, engine=0):
+def _setup(case, n_rays, H, bg_choice, seed=0, engine=0, add_no_texture=True, texture_cast_light=True):
     from avatarclip_b200.clip_vit import ClipImageTower
     from avatarclip_b200.trainer import AppearanceTrainer, DeviceView
     from avatarclip_b200.workload import make_view
@@ -21,8 +21,9 @@ def _setup(case, n_rays, H, bg_choice, seed=0, engine=0):
     text = torch.randn(2, 512, generator=torch.Generator().manual_seed(seed + 5))
     sdf, col, var, ren = U.build_product(sdf_kw, col_kw, ren_kw, sp, cp, 0.3, "cuda", engine=engine)
     tower = ClipImageTower(clip_sd, device="cuda")
-    tr = AppearanceTrainer(ren, tower, text, lr=5e-4)
-    orc = OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text, lr=5e-4)
+    flags = dict(add_no_texture=add_no_texture, texture_cast_light=texture_cast_light)
+    tr = AppearanceTrainer(ren, tower, text, lr=5e-4, **flags)
+    orc = OracleTrainer(sconf, cconf, rconf, sp, cp, 0.3, clip_sd, text, lr=5e-4, **flags)
     hv = make_view(3, n_rays=n_rays, H=H, W=H, seed=seed, bg_choice=bg_choice)
     return tr, orc, hv, DeviceView(hv, "cuda"), (sdf, col, var)
 
@@ -139,6 +140,37 @@ def test_fused_step_tcgen05_engine_matches_oracle():
     U.log_parity("fused_step", {"case": "shipped", "engine": 1, "bg": 3, "loss_rel": abs(loss_p - loss_o) / abs(loss_o),
                                 "grad_rel_l2": rel_l2})
     assert rel_l2 < 1e-3
+
+
+@pytest.mark.parametrize("no_tex,cast,bg,engine", [(False, False, 3, 0), (True, False, 1, 1), (False, True, 0, 0)])
+def test_fused_step_with_the_ablation_switches_matches_oracle(no_tex, cast, bg, engine):
+    """train.add_no_texture / train.texture_cast_light switched off as in confs/ablation/*_0..2.conf (main.py:425,509-534):
+    the first CLIP term then sees the un-shaded extra colour and / or the second term is absent.  Loss and flat gradient of
+    the fused step against the CPU oracle step with the same switches."""
+    tr, orc, hv, dv, mods = _setup("shipped", 96, 80, bg, engine=engine, add_no_texture=no_tex, texture_cast_light=cast)
+    grad = tr.forward_backward(dv).clone()
+    loss_p = tr.loss_value().item()
+    total, aux = orc.loss(hv)
+    gs = torch.autograd.grad(total, [v for _, v in orc.named_params()], allow_unused=True)
+    loss_o = total.item()
+    named = {}
+    for (p, o, m) in tr.fp.slots:
+        for pre, mod in (("sdf.", mods[0]), ("col.", mods[1]), ("var.", mods[2])):
+            for k, q in mod.named_parameters():
+                if q is p:
+                    named[pre + k] = grad[o:o + m].view(p.shape).cpu()
+    diff2, ref2 = 0.0, 0.0
+    for (k, v), g in zip(orc.named_params(), gs):
+        g = torch.zeros_like(v) if g is None else g
+        diff2 += (named[k] - g).double().pow(2).sum().item()
+        ref2 += g.double().pow(2).sum().item()
+    rel_l2 = (diff2 / ref2) ** 0.5
+    loss_rel = abs(loss_p - loss_o) / abs(loss_o)
+    print(f"add_no_texture {no_tex} texture_cast_light {cast} engine {engine}: loss product {loss_p:.6f} oracle {loss_o:.6f} "
+          f"({loss_rel:.2e}); flat-gradient rel-L2 {rel_l2:.3e}")
+    U.log_parity("fused_step_ablation", {"add_no_texture": no_tex, "texture_cast_light": cast, "engine": engine, "bg": bg,
+                                         "loss_rel": loss_rel, "grad_rel_l2": rel_l2})
+    assert loss_rel < 1e-3 and rel_l2 < 1e-3
 
 
 def test_fused_adam_matches_torch_adam_over_5_steps():
