@@ -112,20 +112,23 @@ class RenderingNetwork(nn.Module):
     def __init__(self, d_feature, mode, d_in, d_out, d_hidden, n_layers, weight_norm=True, multires_view=0,
                  squeeze_out=True, extra_color=False):
         super().__init__()
-        if not weight_norm or mode != "no_view_dir" or multires_view != 0 or not squeeze_out or not extra_color \
-                or d_in != 6 or d_out != 3:
+        if not weight_norm or mode != "no_view_dir" or multires_view != 0 or not squeeze_out or d_in != 6 or d_out != 3:
             raise NotImplementedError(
-                "avatarclip_b200 implements mode='no_view_dir', multires_view=0, squeeze_out, extra_color, "
-                "weight_norm, d_in=6, d_out=3 -- the configuration of every shipped conf; see DESIGN.md")
-        self.mode, self.squeeze_out, self.extra_color = mode, squeeze_out, extra_color
+                "avatarclip_b200 implements mode='no_view_dir', multires_view=0, squeeze_out, weight_norm, d_in=6, "
+                "d_out=3 -- the configuration of every shipped conf; see DESIGN.md")
+        self.mode, self.squeeze_out, self.extra_color = mode, squeeze_out, bool(extra_color)
         self.d_feature, self.d_hidden, self.n_layers = d_feature, d_hidden, n_layers
         dims = [d_in + d_feature] + [d_hidden for _ in range(n_layers)] + [d_out]
         self.num_layers = len(dims)
         for l in range(0, self.num_layers - 1):
             w, b = _default_linear_init(dims[l], dims[l + 1])
             setattr(self, "lin" + str(l), WNLinear(dims[l], dims[l + 1], w, b))
-        w, b = _default_linear_init(dims[self.num_layers - 2], d_out)
-        self.extra_lin = WNLinear(dims[self.num_layers - 2], d_out, w, b)
+        if self.extra_color:                                  # models/fields.py:147-150
+            w, b = _default_linear_init(dims[self.num_layers - 2], d_out)
+            self.extra_lin = WNLinear(dims[self.num_layers - 2], d_out, w, b)
+        # extra_color=False (confs/base_models/astrongman.conf, the --mode train pre-fit): no second head, no extra
+        # parameters, no extra draws from torch's generator -- exactly the reference's module.  The kernels' slot for the
+        # head is then a constant zero map inside the flat parameter vector (renderer.FlatParams), not a Parameter.
 
 
 class SingleVarianceNetwork(nn.Module):

@@ -61,7 +61,15 @@ class FlatParams:
             bind(getattr(sdf_network, f"lin{l}"), 0, l)
         for l in range(cfg.col_n_layers + 1):
             bind(getattr(color_network, f"lin{l}"), 1, l)
-        bind(color_network.extra_lin, 2, 0)
+        if getattr(color_network, "extra_color", True):
+            bind(color_network.extra_lin, 2, 0)
+        else:
+            # RenderingNetwork(extra_color=False) has no second head (models/fields.py:147).  The kernels always evaluate
+            # one: its slot holds the constant map W = g v / ||v|| = 0 (g = 0, v = 1, bias = 0); it is not a Parameter (not
+            # trained, absent from state dicts), its output is dropped by NeuSRenderer.render and nothing back-propagates
+            # into it (zero cotangent).
+            o, m = off(2, 0, 1)
+            self.flat[o:o + m] = 1.0
         o, m = off(3, 0, 0)
         self.slots.append((deviation_network.variance, o, m))
         self.rehome()
@@ -172,21 +180,23 @@ class _RenderFn(torch.autograd.Function):
 
 class NeuSRenderer:
     """Drop-in for models/renderer.py:72-404 (``n_outside`` must be 0 and ``nerf`` None, as in every
-    shipped conf -- main.py:136; the reference's ``render_core_outside`` is dead code there)."""
+    shipped conf -- main.py:136; the reference's ``render_core_outside`` is dead code there).  ``extra_color`` True is the
+    train_clip configuration (179 confs), False the NeuS pre-fit of confs/base_models/astrongman.conf."""
 
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
                  up_sample_steps, perturb, extra_color=False, engine: int = 0, max_rays_per_chunk: int = 4096,
                  color_products: Optional[int] = None, wgrad_products: Optional[int] = None):
         if n_outside != 0:
             raise NotImplementedError("n_outside > 0 (NeRF background) is not part of the AvatarCLIP hot path")
-        if not extra_color:
-            raise NotImplementedError("extra_color=False: not used by any AvatarCLIP conf")
+        if bool(extra_color) != bool(getattr(color_network, "extra_color", True)):
+            raise ValueError("NeuSRenderer(extra_color=...) and RenderingNetwork(extra_color=...) must agree "
+                             "(models/renderer.py:227-232 reshapes the colour net's output to 6 or 3 channels)")
         self.nerf = nerf
         self.sdf_network = sdf_network
         self.deviation_network = deviation_network
         self.color_network = color_network
         self.n_samples, self.n_importance, self.n_outside = int(n_samples), int(n_importance), int(n_outside)
-        self.up_sample_steps, self.perturb, self.extra_color = int(up_sample_steps), perturb, extra_color
+        self.up_sample_steps, self.perturb, self.extra_color = int(up_sample_steps), perturb, bool(extra_color)
         self.max_rays_per_chunk = int(max_rays_per_chunk)
         self.cfg = NeusCfg(
             sdf_d_in=sdf_network.d_in, sdf_d_out=sdf_network.d_out, sdf_d_hidden=sdf_network.d_hidden,
@@ -276,6 +286,11 @@ class NeuSRenderer:
                 bg, bg_kind = bgt.reshape(R), 2
             else:
                 raise ValueError("background_rgb must be [1,3] or [R,1] (main.py:393-405)")
+        color_bg = None
+        if not self.extra_color and bg is not None:
+            # renderer.py:277-281: without the extra head the fixed background goes onto `color` itself; the kernels put it
+            # on the extra colour, so they run without one and the (differentiable) blend happens on their outputs
+            color_bg, bg, bg_kind = (bg.reshape(1, 3) if bg_kind == 1 else bg.reshape(R, 1)), None, 0
         z_in = self._prep(z_vals, (R, self.n_samples + self.n_importance)) if z_vals is not None else None
         hook = self._hook if self._hook.device == dev else self._make_hook(dev)
         hook.requires_grad_(any(p.requires_grad for p in fp.params()))
@@ -284,6 +299,10 @@ class NeuSRenderer:
                                need_grad)
         ret = dict(zip(_OUT_KEYS, outs[:len(_OUT_KEYS)]))
         ret["z_vals"] = outs[-1]
+        if not self.extra_color:                                           # renderer.py:272-281,379
+            ret["extra_color_fine"] = None
+            if color_bg is not None:
+                ret["color_fine"] = ret["color_fine"] + color_bg * (1.0 - ret["weight_sum"])
         return ret
 
     def sdf_query(self, pts: torch.Tensor) -> torch.Tensor:

@@ -463,11 +463,13 @@ class Runner:
         return {k: torch.cat(v, 0) for k, v in outs.items()}
 
     def render_image(self, pose, resolution_level=1):
-        """Full-image render of ``extra_color_fine`` for a camera-to-world pose -> [H, W, 3] tensor."""
+        """Full-image render of ``extra_color_fine`` (``color_fine`` for a network without the extra head) for a
+        camera-to-world pose -> [H, W, 3] tensor."""
         ro, rd = self.dataset.gen_rays_pose(pose, resolution_level)
         H, W = ro.shape[:2]
-        o = self._render_batches(ro.reshape(-1, 3), rd.reshape(-1, 3), keys=("extra_color_fine",))
-        return o["extra_color_fine"].reshape(H, W, 3)
+        ckey = "extra_color_fine" if self.extra_color else "color_fine"
+        o = self._render_batches(ro.reshape(-1, 3), rd.reshape(-1, 3), keys=(ckey,))
+        return o[ckey].reshape(H, W, 3)
 
     def validate_image(self, idx=-1, resolution_level=-1):
         """main.py:741-820: colour, extra colour and normal images of training camera ``idx``."""
@@ -481,7 +483,8 @@ class Runner:
         H, W, _ = ro.shape
         bg = torch.ones([1, 3], device=self.device) if self.use_white_bkgd else None
         o = self._render_batches(ro.reshape(-1, 3), rd.reshape(-1, 3), bg,
-                                 keys=("color_fine", "extra_color_fine", "gradients", "weights", "inside_sphere"))
+                                 keys=("color_fine",) + (("extra_color_fine",) if self.extra_color else ())
+                                 + ("gradients", "weights", "inside_sphere"))
         img_fine = (o["color_fine"].cpu().numpy().reshape([H, W, 3, -1]) * 255).clip(0, 255)
         extra_img = (o["extra_color_fine"].cpu().numpy().reshape([H, W, 3, -1]) * 255).clip(0, 255) if self.extra_color else None
         normals = (o["gradients"] * o["weights"][:, :, None] * o["inside_sphere"][..., None]).sum(dim=1).cpu().numpy()
@@ -536,6 +539,9 @@ class Runner:
     def render_geometry_cast_light(self):
         """main.py:634-739: 512 x 512 close-up of the head, texture x Lambert shading (ambience 0, black background)."""
         import cv2 as cv
+        if not self.extra_color:
+            raise RuntimeError("render_geometry_cast_light shades the extra colour (main.py:705-723): the conf has "
+                               "model.rendering_network.extra_color = False")
         eye = sphere_coord(0.0, 0.0, 0.5)
         at = np.array([0, self.head_height, 0.3])
         eye = eye + at

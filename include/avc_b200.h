@@ -45,8 +45,11 @@ const char* avc_build_arch(void);
 /* ------------------------------------------------------------------------------------------
  * NeuS renderer: SDFNetwork + RenderingNetwork + SingleVarianceNetwork + NeuSRenderer.render
  * (models/fields.py:9-107,111-185,270-276; models/embedder.py:6-51; models/renderer.py:39-69,
- * 133-397).  Supported: mode 'no_view_dir', multires_view 0, squeeze_out, extra_color,
- * weight_norm, n_outside 0 -- i.e. every conf shipped under confs/ (SURVEY.md fact 1).
+ * 133-397).  Supported: mode 'no_view_dir', multires_view 0, squeeze_out, weight_norm, n_outside 0 -- i.e.
+ * every conf shipped under confs/ (SURVEY.md fact 1).  The kernels always evaluate the extra colour head
+ * (extra_color = True, 179 confs); for the one conf without it (base_models/astrongman.conf, --mode train) the host
+ * side fills the head's parameter slot with the constant zero map and blends the background into color_fine itself
+ * (models/renderer.py:272-281; avatarclip_b200/renderer.py).
  * ------------------------------------------------------------------------------------------ */
 typedef struct avc_neus_cfg {
   /* SDFNetwork ctor (models/fields.py:10-21) */

@@ -56,3 +56,31 @@ def test_all_shipped_confs_parse():
         assert kw["d_out"] in (257, 129) and isinstance(kw["skip_in"], list)
         assert {"n_samples", "n_importance", "n_outside", "up_sample_steps", "perturb"} <= set(c["model.neus_renderer"].keys())
         assert c.get_float("train.learning_rate") > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_every_shipped_conf_constructs_its_networks_and_is_a_supported_loop():
+    """All 180 shipped confs: the model subtrees are accepted as constructor kwargs (main.py:137-151) -- 3 distinct network
+    configurations, incl. the extra_color-less one of base_models/astrongman.conf -- and the train.* switches name a loop the
+    Runner implements (train_clip: use_silhouettes + extra_color; --mode train: astrongman.conf)."""
+    import json
+    import avatarclip_b200 as ab
+    files = sorted(glob.glob("/root/reference/AvatarGen/AppearanceGen/confs/**/*.conf", recursive=True))
+    built, n_clip = {}, 0
+    for f in files:
+        c = conf.parse_file(f)
+        key = json.dumps({k: dict(c["model." + k]) for k in ("sdf_network", "variance_network", "rendering_network",
+                                                              "neus_renderer")}, sort_keys=True)
+        if key not in built:
+            sdf = ab.SDFNetwork(**c["model.sdf_network"])
+            var = ab.SingleVarianceNetwork(**c["model.variance_network"])
+            col = ab.RenderingNetwork(**c["model.rendering_network"])
+            built[key] = ab.NeuSRenderer(None, sdf, var, col, **c["model.neus_renderer"])
+        ren = built[key]
+        if c.get_bool("train.use_silhouettes", default=False):            # a train_clip conf (main.py:337-566)
+            n_clip += 1
+            assert ren.extra_color and c.get_bool("model.rendering_network.extra_color", default=False)
+            assert c.get_float("train.clip_weight", default=None) is not None and c.get_string("clip.prompt")
+        else:                                                              # the NeuS pre-fit conf (main.py:180-256)
+            assert f.endswith("base_models/astrongman.conf") and not ren.extra_color
+    assert len(built) == 3 and n_clip == 179

@@ -155,9 +155,13 @@ def test_runner_train_clip_with_the_ablation_conf_switches(tmp_path, variant):
 
 
 @pytest.mark.gpu
-def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path):
+@pytest.mark.parametrize("extra_color", [True, False])
+def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path, extra_color):
     """ShapeGen hand-off (108 rendered views + transforms_train.json) -> SMPL_Dataset -> --mode train (NeuS pre-fit
-    through the autograd seam + torch.optim.Adam) -> validate_image PNGs and validate_mesh PLY."""
+    through the autograd seam + torch.optim.Adam) -> validate_image PNGs and validate_mesh PLY.  extra_color False is the
+    network of confs/base_models/astrongman.conf (the conf --mode train ships with): no second colour head, the fixed
+    background blends into `color` (models/renderer.py:272-281)."""
+    edits = () if extra_color else (("        extra_color = True\n", ""),)
     from avatarclip_b200.handoff import read_ply, render_coarse_shape
     from avatarclip_b200.workload import synthetic_body_mesh
     v, f = synthetic_body_mesh(12, 16)
@@ -165,8 +169,9 @@ def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path):
     render_coarse_shape(v, f, str(data_dir), image_size=64)
     meta = json.load(open(data_dir / "transforms_train.json"))
     assert len(meta["frames"]) == 108 and abs(meta["camera_angle_x"] - np.pi / 3) < 1e-12
-    r = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir)
+    r = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir, edits=edits)
     assert r.dataset.n_images == 108 and r.dataset.H == 64 and float(r.dataset.masks.mean()) > 0.01
+    assert r.extra_color == extra_color == r.renderer.extra_color == hasattr(r.color_network, "extra_lin")
     r.batch_size = 256
     losses = []
     r.report_freq = 5
@@ -174,7 +179,23 @@ def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path):
     vals = [float(str(m).split("loss = ")[1].split(" ")[0]) for m in losses if "loss = " in str(m)]
     assert len(vals) == 6 and all(np.isfinite(vals)) and vals[-1] < vals[0]
     img, extra, normal = r.validate_image(idx=3, resolution_level=2)
-    assert img.shape == (32, 32, 3)
+    assert img.shape == (32, 32, 3) and (extra is None) == (not extra_color)
+    if not extra_color:
+        # renderer.py:277-281 without the extra head: color = color + background * (1 - weight_sum), differentiable
+        ro, rd = r.dataset.gen_rays_at(3, resolution_level=4)
+        ro, rd = ro.reshape(-1, 3)[:200], rd.reshape(-1, 3)[:200]
+        near, far = r.dataset.near_far_from_sphere(ro, rd)
+        jit = torch.rand(200, device="cuda") - 0.5
+        plain = r.renderer.render(ro, rd, near, far, jitter=jit, cos_anneal_ratio=1.0)
+        white = r.renderer.render(ro, rd, near, far, jitter=jit, cos_anneal_ratio=1.0,
+                                  background_rgb=torch.ones([1, 3], device="cuda"))
+        assert plain["extra_color_fine"] is None and white["extra_color_fine"] is None
+        assert torch.allclose(white["color_fine"], plain["color_fine"] + (1.0 - plain["weight_sum"]), atol=1e-6)
+        for p in r._all_params():
+            p.grad = None
+        white["color_fine"].sum().backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in r._all_params())
+        assert "extra_lin.bias" not in r.color_network.state_dict()
     assert os.path.exists(os.path.join(r.base_exp_dir, "validations_fine", "{:0>8d}_0_3.png".format(r.iter_step)))
     assert os.path.exists(os.path.join(r.base_exp_dir, "normals", "{:0>8d}_0_3.png".format(r.iter_step)))
     path = r.validate_mesh(resolution=48)
@@ -183,7 +204,7 @@ def test_mode_train_on_handoff_directory_and_validation_outputs(tmp_path):
     assert ff.max() < vv.shape[0] and np.abs(vv).max() <= 1.02
     # resume --mode train with the torch optimizer state
     ck = r.save_checkpoint()
-    r2 = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir, is_continue=True)
+    r2 = _runner(tmp_path, "cuda", mode="train", data_dir=data_dir, is_continue=True, edits=edits)
     opt = r2._ensure_optimizer()
     assert r2.iter_step == 30 and len(opt.state) == len(r2._all_params())
 
