@@ -123,6 +123,10 @@ class Runner:
             self.file_backup()
 
     # ------------------------------------------------------------------ schedules (main.py:571-586)
+    def get_image_perm(self):
+        """main.py:568-569."""
+        return torch.randperm(self.dataset.n_images)
+
     def get_cos_anneal_ratio(self):
         return 1.0 if self.anneal_end == 0.0 else float(np.min([1.0, self.iter_step / self.anneal_end]))
 
@@ -322,7 +326,7 @@ class Runner:
         self.writer = self._make_writer()
         self.update_learning_rate()
         res_step = self.end_iter - self.iter_step
-        image_perm = torch.randperm(self.dataset.n_images)
+        image_perm = self.get_image_perm()
         for iter_i in range(res_step):
             if max_steps is not None and iter_i >= max_steps:
                 break
@@ -364,7 +368,7 @@ class Runner:
                 self.validate_mesh()
             self.update_learning_rate()
             if self.iter_step % len(image_perm) == 0:
-                image_perm = torch.randperm(self.dataset.n_images)
+                image_perm = self.get_image_perm()
         return self.iter_step
 
     # ------------------------------------------------------------------ checkpoints (main.py:601-632)
@@ -577,15 +581,18 @@ def main(argv=None):
     p.add_argument("--case", type=str, default="smpl")
     args = p.parse_args(argv)
     torch.cuda.set_device(args.gpu)
+    if args.mode in ("validate_mesh", "render_geometry_cast_light"):      # main.py:965-967: inference on the last checkpoint
+        args.is_continue = True
     runner = Runner(args.conf, args.mode, args.case, args.is_continue, device=f"cuda:{args.gpu}")
-    if args.mode == "train":                                        # main.py:965-975
+    if args.mode == "train":                                        # main.py:970-979
         runner.train()
+    elif args.mode == "validate_mesh":
+        runner.validate_mesh(world_space=True, resolution=512, threshold=args.mcube_threshold)   # world_space is unused (:850)
+        runner.render_geometry_cast_light()
     elif args.mode == "train_clip":
         runner.init_clip()
         runner.init_smpl()
         runner.train_clip()
-    elif args.mode == "validate_mesh":
-        runner.validate_mesh(world_space=False, resolution=512, threshold=args.mcube_threshold)
     elif args.mode == "render_geometry_cast_light":
         runner.render_geometry_cast_light()
     else:
