@@ -170,7 +170,7 @@ def test_fused_step_with_the_ablation_switches_matches_oracle(no_tex, cast, bg, 
           f"({loss_rel:.2e}); flat-gradient rel-L2 {rel_l2:.3e}")
     U.log_parity("fused_step_ablation", {"add_no_texture": no_tex, "texture_cast_light": cast, "engine": engine, "bg": bg,
                                          "loss_rel": loss_rel, "grad_rel_l2": rel_l2})
-    assert loss_rel < 1e-3 and rel_l2 < 1e-3
+    assert loss_rel < 1e-4 and rel_l2 < 1e-3          # measured: loss 1.2e-6, gradient 3.2e-6 .. 4.6e-5 (profiles/r2_parity.json)
 
 
 def test_fused_adam_matches_torch_adam_over_5_steps():

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src = os.path.join(ROOT, "gpurun_out", "r2_parity.jsonl")
 dst = os.path.join(ROOT, "profiles", "r2_parity.json")
 recs = {}
-KEYS = ("test", "case", "golden", "engine", "R", "H", "P", "bg", "mode")
+KEYS = ("test", "case", "golden", "engine", "R", "H", "P", "bg", "mode", "add_no_texture", "texture_cast_light")
 if os.path.exists(dst):          # every gpurun call starts with an empty gpurun_out/: accumulate across calls
     for r in json.load(open(dst)):
         recs[tuple((k, r[k]) for k in KEYS if k in r)] = r
