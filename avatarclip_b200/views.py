@@ -165,7 +165,15 @@ class ViewBuilder:
             v.scalars = sc.to(dev, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(self.stream)
-        torch.cuda.current_stream(dev).wait_event(ready)      # the step (on the caller's stream) starts after the view
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready)                                   # the step (on the caller's stream) starts after the view
+        # The view's tensors were allocated on the side stream and are consumed on the caller's: tell the caching allocator,
+        # or a block freed when the caller drops the view could be handed to the NEXT view's preparation while the step
+        # that reads it is still running (the loop does not synchronise every step when no scalar writer is attached).
+        for name in PreparedView.__slots__:
+            t = getattr(v, name, None)
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(cur)
         return v
 
     def build(self, draw: StepDraw) -> PreparedView:
