@@ -32,6 +32,9 @@ import torch  # noqa: E402
 from avatarclip_b200 import workload as WL  # noqa: E402  (host-side numpy / CPU torch only)
 
 METRIC = "appearance-optim steps/sec (512 rays x 128 samples, CLIP loss)"
+# config.workload of BOTH arms (the native line and `--impl reference`): the same string, so the two lines name one workload
+WORKLOAD = ("BASELINE configs[1]: 512 rays x (64+64) samples, 8x256 SDF + 4x256 colour, "
+            "CLIP ViT-B/32 loss on 2 canvases 224x224, Adam; 1 view per GPU per step")
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu (profiles/r2_launches_tcgen05_engine.txt, final round-2
 # build): mean over the 41 NT / 21 TN launches of one step (all in the fine pass; 11.1 GB of DRAM traffic per step in total)
 TRAFFIC_PER_LAUNCH = {"avc::tc::gemm_tc_tn_kernel": 128.0e6, "avc::tc::gemm_tc_nt_kernel": 188.6e6}
@@ -388,8 +391,7 @@ def run_native(args):
             "metric": METRIC, "value": world * K / (ms_value * 1e-3), "unit": "steps/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if args.engine == 0 else "bf16x3(split)->f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 512 rays x (64+64) samples, 8x256 SDF + 4x256 colour, "
-                                   "CLIP ViT-B/32 loss on 2 canvases 224x224, Adam; 1 view per GPU per step",
+            "config": {"workload": WORKLOAD,
                        "views_per_step": world, "engine": "fp32 FFMA tiles" if args.engine == 0 else "tcgen05 split",
                        "l2": "per-step working set (activation stash ~2.4 GB) >> 126 MB L2; no flush needed",
                        "parallelism": f"view-sharded dp{world}" if world > 1 else "single",
@@ -573,9 +575,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 512 rays x (64+64) samples, 8x256 SDF + 4x256 colour, CLIP "
-                                   "ViT-B/32 loss on 2 canvases 224x224, Adam (same as the native arm); reference "
-                                   "algorithm on the host cores, full ray count"},
+            # the native arm's workload string verbatim + what differs in THIS arm (rank 0 alone runs it: one view per step)
+            "config": {"workload": WORKLOAD, "views_per_step": 1, "engine": "reference algorithm, torch fp32 eager",
+                       "parallelism": "host cores of rank 0", "launch": "unmodified reference renderer (oracle/_ref) inside "
+                       "the restated step; full ray count, no extrapolation" if kind == "reference" else
+                       "oracle port of the reference renderer; full ray count, no extrapolation"},
             "cpu_baseline": {"value": val, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": kind,
                              "sample": f"{args.steps} full steps (512 rays), unmodified reference renderer"
                                        if kind == "reference" else f"{args.steps} full steps (512 rays), oracle port"},
