@@ -221,7 +221,7 @@ int avc_clip_loss_bwd(const avc_clip_cfg* cfg, const avc_clip_weights* w, int32_
 /* ------------------------------------------------------------------------------------------
  * Shading + canvas scatter + non-CLIP losses of Runner.train_clip (main.py:417-497, 528-534) with
  * use_silhouettes = True (every shipped train_clip conf).  The two switches the shipped confs vary
- * (confs/ablation/*_0..2.conf) are the last two fields: zero-initialised = add_no_texture = texture_cast_light =
+ * (the 18 confs/ablation files ending in _0 / _1 / _2) are the last two fields: zero-initialised = add_no_texture = texture_cast_light =
  * True, the configuration of confs/examples*.
  * Rays are the True pixels of the dilated mask; pix[r] is the flat canvas index (y*W + x) of ray r.
  * ------------------------------------------------------------------------------------------ */
