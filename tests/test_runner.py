@@ -55,6 +55,38 @@ def test_runner_construction_schedule_and_checkpoint_layout(tmp_path):
         assert torch.equal(a, b)
 
 
+def test_cli_dispatch_mirrors_the_reference_main(monkeypatch):
+    """main.py:953-979: flags, `is_continue` forced for the two inference modes, and what each mode calls, in order."""
+    from avatarclip_b200 import runner as R
+    calls = []
+
+    class Fake:
+        def __init__(self, conf, mode, case, is_continue, device=None):
+            calls.append(("init", conf, mode, case, is_continue, device))
+
+        def __getattr__(self, name):
+            return lambda *a, **k: calls.append((name, a, k))
+
+    monkeypatch.setattr(R, "Runner", Fake)
+    monkeypatch.setattr(R.torch.cuda, "set_device", lambda i: calls.append(("set_device", i)))
+    R.main(["--conf", "c.conf", "--mode", "validate_mesh", "--case", "x", "--gpu", "0", "--mcube_threshold", "0.25"])
+    assert calls[0] == ("set_device", 0) and calls[1] == ("init", "c.conf", "validate_mesh", "x", True, "cuda:0")
+    assert calls[2] == ("validate_mesh", (), {"world_space": True, "resolution": 512, "threshold": 0.25})
+    assert calls[3][0] == "render_geometry_cast_light" and len(calls) == 4
+    calls.clear()
+    R.main(["--conf", "c.conf", "--mode", "train_clip"])
+    assert calls[1] == ("init", "c.conf", "train_clip", "smpl", False, "cuda:0")
+    assert [c[0] for c in calls[2:]] == ["init_clip", "init_smpl", "train_clip"]
+    calls.clear()
+    R.main(["--conf", "c.conf", "--mode", "render_geometry_cast_light"])
+    assert calls[1][4] is True and [c[0] for c in calls[2:]] == ["render_geometry_cast_light"]
+    calls.clear()
+    R.main(["--conf", "c.conf", "--mode", "train", "--is_continue"])
+    assert calls[1][2] == "train" and calls[1][4] is True and [c[0] for c in calls[2:]] == ["train"]
+    with pytest.raises(SystemExit):
+        R.main(["--conf", "c.conf", "--mode", "nonsense"])
+
+
 def _clip_args():
     from avatarclip_b200.workload import random_vit_state
     g = torch.Generator().manual_seed(0)
