@@ -61,3 +61,22 @@ def test_camera_matrix_equals_the_reference_lines():
             eye = handoff.get_points_from_angles(2.2, e, a)
             ref, _, _, _ = ns["lookat"](eye, np.array([0, 0, 0]), np.array([0, 1, 0]))
             assert np.array_equal(ref, handoff.lookat_inverse_view(eye, np.array([0, 0, 0]), np.array([0, 1, 0])))
+
+
+def test_read_obj_triangulates_and_strips_texture_indices(tmp_path):
+    from avatarclip_b200.views import read_obj
+    p = tmp_path / "t.obj"
+    p.write_text("# comment\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1/1/1 2/1/1 3/1/1 4/1/1\nf 1 2 3\n")
+    v, f = read_obj(str(p))
+    assert v.shape == (4, 3) and v.dtype == np.float32
+    assert f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]] and f.dtype == np.int32          # quad -> fan of two triangles
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/AvatarGen/AppearanceGen/data/zero_beta_smpl.obj"),
+                    reason="reference checkout only exists in the build container")
+def test_read_obj_on_the_shipped_template():
+    """dataset.template_obj of the shipped confs (main.py:292,316): the SMPL topology, 6890 vertices / 13 776 triangles."""
+    from avatarclip_b200.views import read_obj
+    v, f = read_obj("/root/reference/AvatarGen/AppearanceGen/data/zero_beta_smpl.obj")
+    assert v.shape == (6890, 3) and f.shape == (13776, 3) and f.min() == 0 and f.max() == 6889
+    assert np.abs(v).max() < 1.5
