@@ -1,0 +1,91 @@
+"""Runner.validate_image's host side (batching, normal-image rotation, scaling, file names, image layout) against the reference's
+own method text (main.py:741-820) executed in place, both driven by the SAME fake dataset and the SAME fake renderer (deterministic
+functions of the rays, CPU tensors) -- the render itself is covered by the GPU parity tests.  Build container only."""
+import os
+import textwrap
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REF_MAIN = "/root/reference/AvatarGen/AppearanceGen/main.py"
+HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_MAIN), reason="reference checkout only exists in the build container")
+
+
+class FakeDataset:
+    n_images, H, W = 5, 24, 24
+
+    def __init__(self):
+        g = torch.Generator().manual_seed(3)
+        q, _ = torch.linalg.qr(torch.randn(5, 3, 3, generator=g))
+        self.poses = torch.eye(4).repeat(5, 1, 1)
+        self.poses[:, :3, :3] = q
+        self.poses[:, :3, 3] = torch.randn(5, 3, generator=g)
+
+    def gen_rays_at(self, idx, resolution_level=1):
+        n = self.H // resolution_level
+        yy, xx = torch.meshgrid(torch.linspace(-1, 1, n), torch.linspace(-1, 1, n), indexing="ij")
+        d = torch.stack([xx, -yy, -torch.ones_like(xx)], -1)
+        d = d / d.norm(dim=-1, keepdim=True)
+        d = torch.sum(d[..., None, :] * self.poses[idx, :3, :3], -1)
+        return self.poses[idx, None, None, :3, 3].expand(d.shape), d
+
+    def near_far_from_sphere(self, o, d, is_sphere=False):
+        return torch.zeros(o.shape[0], 1), torch.ones(o.shape[0], 1) * 2
+
+    def image_at(self, idx, resolution_level):
+        n = self.H // resolution_level
+        return ((np.arange(n * n * 3).reshape(n, n, 3) * 7 + idx) % 256).astype(np.uint8)
+
+
+class FakeRenderer:
+    n_samples, n_importance = 3, 2
+
+    def render(self, rays_o, rays_d, near, far, cos_anneal_ratio=0.0, background_rgb=None, **kw):
+        S = 5
+        k = torch.arange(1, S + 1, dtype=torch.float32)
+        w = torch.softmax(rays_d[:, :1] * k[None], dim=1)
+        return {"color_fine": torch.sigmoid(rays_d * 3 + rays_o),
+                "extra_color_fine": torch.sigmoid(rays_d * -2 + 0.3) * 1.3,                 # > 1 in places: exercises the clip
+                "gradients": torch.sin(rays_d[:, None, :] * k[None, :, None]), "weights": w,
+                "inside_sphere": (torch.arange(S) % 2).float()[None].expand(rays_d.shape[0], S),
+                "weight_sum": w.sum(1, keepdim=True), "mid_z_vals": w}
+
+
+def _reference_validate_image():
+    import cv2 as cv
+    lines = open(REF_MAIN).read().split("\n")[740:820]
+    assert lines[0].strip().startswith("def validate_image(self, idx=-1, resolution_level=-1)") and "normal_img[..., i])" in lines[-1]
+    ns = dict(np=np, torch=torch, os=os, cv=cv)
+    exec(textwrap.dedent("\n".join(lines)), ns)
+    return ns["validate_image"]
+
+
+@pytest.mark.parametrize("extra_color", [True, False])
+def test_validate_image_files_equal_the_reference_methods(tmp_path, extra_color):
+    import cv2 as cv
+    from avatarclip_b200.runner import Runner
+    conf = open(os.path.join(HERE, "runner_conf_sample.conf")).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "ours"))
+    if not extra_color:
+        conf = conf.replace("        extra_color = True\n", "")
+    p = tmp_path / "c.conf"
+    p.write_text(conf)
+    r = Runner(str(p), mode="validate", case="smpl", device="cpu")
+    r.dataset, r.iter_step, r.batch_size = FakeDataset(), 1234, 100              # 144 rays at level 2: two uneven batches
+    r.renderer.render = FakeRenderer().render
+    r.renderer.n_samples, r.renderer.n_importance = 3, 2
+    img, extra, normal = r.validate_image(idx=3, resolution_level=2)
+    ref_self = types.SimpleNamespace(dataset=FakeDataset(), iter_step=1234, batch_size=100, validate_resolution_level=1,
+                                     use_white_bkgd=False, extra_color=extra_color, renderer=FakeRenderer(),
+                                     base_exp_dir=str(tmp_path / "ref"), get_cos_anneal_ratio=lambda: 1.0)
+    _reference_validate_image()(ref_self, idx=3, resolution_level=2)
+    name = "00001234_0_3.png"
+    for d in ("validations_fine", "normals") + (("validations_extra_fine",) if extra_color else ()):
+        a = cv.imread(os.path.join(str(tmp_path / "ours"), d, name), cv.IMREAD_UNCHANGED)
+        b = cv.imread(os.path.join(str(tmp_path / "ref"), d, name), cv.IMREAD_UNCHANGED)
+        assert a is not None and b is not None and a.shape == b.shape and np.array_equal(a, b), d
+    assert img.shape == (12, 12, 3) and normal.shape == (12, 12, 3) and (extra is None) == (not extra_color)
+    if not extra_color:                       # the reference creates the directory but writes nothing into it
+        assert os.listdir(os.path.join(str(tmp_path / "ours"), "validations_extra_fine")) == []
