@@ -89,3 +89,68 @@ def test_validate_image_files_equal_the_reference_methods(tmp_path, extra_color)
     assert img.shape == (12, 12, 3) and normal.shape == (12, 12, 3) and (extra is None) == (not extra_color)
     if not extra_color:                       # the reference creates the directory but writes nothing into it
         assert os.listdir(os.path.join(str(tmp_path / "ours"), "validations_extra_fine")) == []
+
+
+def _reference_validate_mesh(captured):
+    lines = open(REF_MAIN).read().split("\n")[849:919]
+    assert lines[0].strip().startswith("def validate_mesh(self, world_space=False") and "logging.info('End')" in lines[-1]
+    import logging
+
+    class Trimesh:                      # stand-in for the absent trimesh package: records what would be exported
+        def __init__(self, vertices, triangles, vertex_colors=None):
+            captured.update(vertices=np.asarray(vertices), triangles=np.asarray(triangles), colors=np.asarray(vertex_colors))
+
+    tm = types.SimpleNamespace(Trimesh=Trimesh, exchange=types.SimpleNamespace(export=types.SimpleNamespace(
+        export_mesh=lambda mesh, path, file_type=None: captured.update(path=path, file_type=file_type))))
+    ns = dict(np=np, torch=torch, os=os, logging=logging, trimesh=tm, to8b=lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8))
+    exec(textwrap.dedent("\n".join(lines)), ns)
+    return ns["validate_mesh"]
+
+
+class MeshRenderer(FakeRenderer):
+    def __init__(self):
+        g = torch.Generator().manual_seed(5)
+        self.vertices = (torch.rand(257, 3, generator=g, dtype=torch.float64) - 0.5).numpy()
+        self.triangles = torch.randint(0, 257, (300, 3), generator=g).numpy()
+
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        return self.vertices, self.triangles
+
+    def render(self, rays_o, rays_d, near, far, cos_anneal_ratio=0.0, background_rgb=None, **kw):
+        out = super().render(rays_o, rays_d, near, far)
+        # view-dependent depth: which of the six views "sees" a vertex best differs from vertex to vertex
+        out["mid_z_vals"] = (rays_o.norm(dim=-1, keepdim=True) + torch.cos(rays_d[:, :1] * 9 + rays_o[:, 1:2])).expand(-1, 5)
+        return out
+
+
+@pytest.mark.parametrize("extra_color", [True, False])
+def test_validate_mesh_colours_equal_the_reference_methods(tmp_path, extra_color):
+    from avatarclip_b200.handoff import read_ply
+    from avatarclip_b200.runner import Runner
+    conf = open(os.path.join(HERE, "runner_conf_sample.conf")).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "ours"))
+    if not extra_color:
+        conf = conf.replace("        extra_color = True\n", "")
+    p = tmp_path / "c.conf"
+    p.write_text(conf)
+    r = Runner(str(p), mode="validate", case="smpl", device="cpu")
+    r.dataset, r.iter_step, r.batch_size = FakeDataset(), 77, 100               # 257 vertices: three uneven batches per view
+    r.dataset.object_bbox_min, r.dataset.object_bbox_max = np.array([-1.01] * 3), np.array([1.01] * 3)
+    mr = MeshRenderer()
+    r.renderer.render, r.renderer.extract_geometry = mr.render, mr.extract_geometry
+    path = r.validate_mesh(resolution=64)
+    captured = {}
+    ds = FakeDataset()
+    ds.object_bbox_min, ds.object_bbox_max = np.array([-1.01] * 3), np.array([1.01] * 3)
+    ref_self = types.SimpleNamespace(dataset=ds, iter_step=77, batch_size=100, use_white_bkgd=False, extra_color=extra_color,
+                                     renderer=MeshRenderer(), base_exp_dir=str(tmp_path / "ref"), get_cos_anneal_ratio=lambda: 1.0)
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self_, *a, **k: self_          # `.cuda()` (main.py:859,872): a device move, identity on this box
+    try:
+        _reference_validate_mesh(captured)(ref_self, resolution=64)
+    finally:
+        torch.Tensor.cuda = saved_cuda
+    v, f, c = read_ply(path)
+    assert os.path.basename(path) == os.path.basename(captured["path"]) == "00000077.ply" and captured["file_type"] == "ply"
+    assert np.array_equal(f, captured["triangles"].astype(np.int32)) and np.allclose(v, captured["vertices"].astype(np.float32))
+    assert c.shape == captured["colors"].shape == (257, 3)
+    assert np.array_equal(c, captured["colors"])                 # the same view wins for every vertex, the same 8-bit colour
