@@ -154,3 +154,59 @@ def test_validate_mesh_colours_equal_the_reference_methods(tmp_path, extra_color
     assert np.array_equal(f, captured["triangles"].astype(np.int32)) and np.allclose(v, captured["vertices"].astype(np.float32))
     assert c.shape == captured["colors"].shape == (257, 3)
     assert np.array_equal(c, captured["colors"])                 # the same view wins for every vertex, the same 8-bit colour
+
+
+def test_render_geometry_cast_light_equals_the_reference_method(tmp_path):
+    """main.py:634-739 executed in place (head close-up, one light draw, Lambert shading of the extra colour, ambience 0)
+    against Runner.render_geometry_cast_light under the same numpy seed, fake dataset and fake renderer."""
+    import cv2 as cv
+    from torchvision import transforms
+    from avatarclip_b200.runner import Runner
+    lines = open(REF_MAIN).read().split("\n")
+    body = lines[633:739]
+    assert body[0].strip().startswith("def render_geometry_cast_light(self)") and body[-1].strip() == ")"
+    uns = dict(np=np, torch=torch)
+    utils = open(os.path.join(os.path.dirname(REF_MAIN), "models", "utils.py")).read().split("\n")
+    exec(textwrap.dedent("\n".join(utils[5:27])), uns)            # norm_np_arr, lookat (models/utils.py:6-27)
+    exec(textwrap.dedent("\n".join(utils[58:64])), uns)          # sphere_coord (:59-64)
+    captured = {}
+    ns = dict(np=np, torch=torch, os=os, transforms=transforms, lookat=uns["lookat"], sphere_coord=uns["sphere_coord"],
+              imageio=types.SimpleNamespace(imwrite=lambda path, arr: captured.update(path=path, img=np.asarray(arr))),
+              to8b=lambda x: (255 * np.clip(x, 0, 1)).astype(np.uint8))
+    exec(textwrap.dedent("\n".join(body)), ns)
+
+    class DS(FakeDataset):
+        def gen_rays_pose(self, pose, resolution_level=1):
+            pose = torch.as_tensor(np.asarray(pose), dtype=torch.float32)
+            n = int(self.H // resolution_level)
+            yy, xx = torch.meshgrid(torch.linspace(-1, 1, n), torch.linspace(-1, 1, n), indexing="ij")
+            d = torch.stack([xx, -yy, -torch.ones_like(xx)], -1)
+            d = d / d.norm(dim=-1, keepdim=True)
+            d = torch.sum(d[..., None, :] * pose[:3, :3], -1)
+            return pose[None, None, :3, 3].expand(d.shape), d
+
+    conf = open(os.path.join(HERE, "runner_conf_sample.conf")).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "ours"))
+    p = tmp_path / "c.conf"
+    p.write_text(conf)
+    r = Runner(str(p), mode="validate", case="smpl", device="cpu")
+    r.dataset, r.batch_size = DS(), 500
+    r.renderer.render = FakeRenderer().render
+    r.renderer.n_samples, r.renderer.n_importance = 3, 2
+    np.random.seed(21)
+    path = r.render_geometry_cast_light()
+    next_ours = np.random.uniform()
+    ref_self = types.SimpleNamespace(dataset=DS(), batch_size=500, head_height=r.head_height, renderer=FakeRenderer(),
+                                     base_exp_dir=str(tmp_path / "ref"), get_cos_anneal_ratio=lambda: 1.0)
+    os.makedirs(ref_self.base_exp_dir, exist_ok=True)
+    saved_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self_, *a, **k: self_
+    np.random.seed(21)
+    try:
+        ns["render_geometry_cast_light"](ref_self)
+        next_ref = np.random.uniform()
+    finally:
+        torch.Tensor.cuda = saved_cuda
+    ours = cv.cvtColor(cv.imread(path, cv.IMREAD_UNCHANGED), cv.COLOR_BGR2RGB)
+    assert os.path.basename(path) == os.path.basename(captured["path"]) == "cast_light_texture_head_black.png"
+    assert ours.shape == captured["img"].shape == (48, 48, 3) and np.array_equal(ours, captured["img"])
+    assert next_ours == next_ref              # both sides consumed the same draws of numpy's global stream (main.py:671-674)
