@@ -112,3 +112,74 @@ def test_mode_train_loop_equals_the_reference_loop(tmp_path, mask_weight, white,
     lr_ours = [str(m).split("lr=")[1] for m in logs if "lr=" in str(m)]
     lr_ref = [l.split("lr=")[1] for l in ref_out.splitlines() if "lr=" in l]
     assert lr_ours == lr_ref and len(lr_ours) == 4                                   # the lr in force at steps 3, 6, 9, 12
+
+
+def test_train_clip_host_logic_equals_the_reference_lines(tmp_path, monkeypatch):
+    """What Runner.train_clip hands to the fused step, step by step -- camera pose, background mode, light, ambience (numpy's
+    global stream seeded by train.seed), WHICH cached text embedding (main.py:499-507: face every 4th step, back when the camera
+    is behind, else body), the learning rate in force (update_learning_rate before the loop and after every step, :339,563)
+    and the cosine-anneal ratio -- against the reference's own lines executed in place.  The step itself is mocked (GPU tests)."""
+    import numpy as np
+    from avatarclip_b200 import views
+    from avatarclip_b200.runner import Runner
+    from oracle.pin_loss_stage import cut
+    from oracle.pin_sampling import reference_draws
+    conf = open(os.path.join(HERE, "runner_conf_sample.conf")).read().replace("./exp/CASE_NAME/demo", str(tmp_path / "ours"))
+    conf = conf.replace("warm_up_end = 500", "warm_up_end = 5").replace("end_iter = 100000", "end_iter = 80")
+    p = tmp_path / "c.conf"
+    p.write_text(conf)
+    r = Runner(str(p), mode="train_clip", case="smpl", device="cpu")                  # seeds numpy with train.seed = 11
+    n_steps = 48
+    body, face, back = torch.zeros(1, 4), torch.ones(1, 4), torch.full((1, 4), 2.0)
+    r.encoded_text, r.encoded_face_text, r.encoded_back_text = body, face, back
+    r.clip_tower, r.v, r.f = object(), torch.zeros(1, 3, 3), np.zeros((1, 3), dtype=np.int64)
+    r.dataset = types.SimpleNamespace(H=256, W=256, focal=221.7, n_images=0)
+    rec = []
+
+    class FakeTrainer:
+        iter_step, scalars, cos, _out = 0, None, None, None
+
+        def set_text(self, emb):
+            self.text = emb
+
+        def step(self, view, lr=None, cos_anneal=1.0):
+            d = view.draw
+            rec.append(dict(text=float(self.text[0, 0]), lr=lr, cos_anneal=cos_anneal, pose=d.pose.copy(), bg=d.bg_choice,
+                            light=d.light_dir.copy(), ambience=d.ambience, face=d.face_step, is_front=d.is_front))
+            return torch.tensor(1.0)
+
+    class FakeBuilder:
+        def __init__(self, *a, **k):
+            pass
+
+        def submit(self, draw):
+            return draw
+
+        def finish(self, pending):
+            return types.SimpleNamespace(draw=pending)
+
+    r.trainer = FakeTrainer()
+    monkeypatch.setattr(views, "ViewBuilder", FakeBuilder)
+    r._make_writer = lambda: __import__("avatarclip_b200.runner", fromlist=["_NullWriter"])._NullWriter()
+    assert r.train_clip(max_steps=n_steps, log=lambda m: None, validate=False) == n_steps
+    # ---- the reference's lines
+    ref = reference_draws(r.seed, n_steps + 1, r.head_height, face=True, bg_aug=True, shading=True)   # ours looks one step ahead
+    prompt_lines = cut("main.py", 499, 507, "if self.use_face_prompt and iter_i % 4 == 0", "current_no_texture_text_encoding = self.encoded_text")
+    sched = {"np": np}
+    exec(cut("main.py", 571, 586, "def get_cos_anneal_ratio", "g['lr']"), sched)
+    for i, got in enumerate(rec):
+        s = types.SimpleNamespace(use_face_prompt=True, use_back_prompt=True, encoded_text=body, encoded_face_text=face,
+                                  encoded_back_text=back)
+        loc = dict(self=s, iter_i=i, is_front=ref[i]["is_front"])
+        exec(prompt_lines, loc)
+        assert got["text"] == float(loc["current_text_encoding"][0, 0]), i
+        assert float(loc["current_no_texture_text_encoding"][0, 0]) == got["text"]
+        sch = types.SimpleNamespace(iter_step=i, warm_up_end=5.0, end_iter=80, learning_rate_alpha=r.learning_rate_alpha,
+                                    learning_rate=r.learning_rate, anneal_end=0.0,
+                                    optimizer=types.SimpleNamespace(param_groups=[{"lr": None}]))
+        sched["update_learning_rate"](sch)
+        assert got["lr"] == sch.optimizer.param_groups[0]["lr"], i
+        assert got["cos_anneal"] == float(sched["get_cos_anneal_ratio"](sch))
+        assert np.array_equal(got["pose"], np.asarray(ref[i]["pose"])) and got["bg"] == ref[i]["choice_i"], i
+        assert np.array_equal(got["light"], np.asarray(ref[i]["light_dir"]).astype(np.float32)) and got["ambience"] == ref[i]["ambience"]
+    assert {g["text"] for g in rec} == {0.0, 1.0, 2.0}             # body, face and back prompts all occurred
